@@ -1,0 +1,13 @@
+"""amp_extensions_b200 — B200-native batched learned-dynamics env step of gym-simenv / MILO.
+
+Host-side mirror of the reference's plugin surface for this one hot path:
+
+  DynamicsEnsemble / DynamicsModel   (reference milo/milo/dynamics.py)
+  RBFLinearCost                      (reference milo/milo/linear_cost.py)
+  AmpDataset                         (reference milo/milo/datasets.py)
+  SimEnv / VecSimEnv                 (reference gym-simenv/gym_simenv/envs/sim_env.py)
+  ImitationReward                    (reference DeepMimicCore/scenes/SceneImitate.cpp)
+
+All compute goes through libsimstep.so (include/simstep.h); there is no CPU fallback.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,888 @@
+// C ABI of libsimstep.so (see include/simstep.h): handle, operand packing,
+// workspaces, tensor maps and the launch sequences of the env step.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/simstep.h"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+#include "imitation.cuh"
+
+using namespace simstep;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+thread_local std::string g_create_error;
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+struct Layer {
+  int in_ref = 0;   // reference nn.Linear in_features
+  int out = 0;      // out_features
+  int o_pad = 0;    // rows of the packed operand (multiple of kBlockN)
+  int k_pad = 0;    // packed K (multiple of the swizzle row)
+  int kb_x = 0, kb_h0 = 0, kb_h = 0;
+  int out_col0 = 0; // column of this layer's output inside the activation buffer
+  PackSegs segs{};
+  void* w = nullptr;      // [N][o_pad][k_pad] operand storage
+  float* bias = nullptr;  // [N][o_pad]
+  CUtensorMap tmap_w;
+};
+
+}  // namespace
+
+struct simstep_handle {
+  simstep_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  int esize = 4;  // bytes per GEMM operand element
+  int bk = 32;    // elements per 128-byte swizzle row
+  int S = 0, A = 0, N = 0, L = 0;
+  int XP = 0, HT = 0, SP = 0;
+  std::vector<Layer> layers;  // L hidden + 1 final
+  float* tf_dev = nullptr;         // mean_s | scale_s | mean_a | scale_a
+  float* out_scale_dev = nullptr;  // [SP]
+  float* out_shift_dev = nullptr;  // [SP]
+  bool have_ensemble = false;
+
+  long long cap_rows = 0;
+  void* xbuf = nullptr;
+  void* hbuf = nullptr;
+  float* dws = nullptr;
+  CUtensorMap tmap_x, tmap_h;
+
+  // RFF cost
+  bool have_rff = false;
+  int D = 0, D_pad = 0, rff_in = 0, RK = 0, RKT = 0, rff_split = 0;
+  void* rff_w = nullptr;
+  float* rff_b = nullptr;
+  float* rff_wpad = nullptr;
+  void* rffin = nullptr;
+  float* rff_part = nullptr;
+  double* colsum_partial = nullptr;
+  CUtensorMap tmap_rffw, tmap_rffin;
+
+  TermConst term{};
+  ImitConst* imit_dev = nullptr;
+  bool have_clip = false;
+  int dof = 0;
+
+  std::string err;
+};
+
+namespace {
+
+int fail(simstep_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+      return fail(h, SIMSTEP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                                        std::to_string(__LINE__) + ")");                                 \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// K-major operand [rows][cols] with a (128-byte x box_rows) box and 128-byte swizzle.
+int encode_operand(simstep_handle* h, CUtensorMap* map, int prec, void* base, long long cols, long long rows,
+                   long long pitch_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(h, SIMSTEP_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int es = prec == SIMSTEP_PREC_TF32 ? 4 : 2;
+  const CUtensorMapDataType dt = prec == SIMSTEP_PREC_TF32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : prec == SIMSTEP_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                             : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_elems) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, SIMSTEP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return SIMSTEP_OK;
+}
+
+template <typename E, int MODE>
+int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
+                  const GemmArgs& ga, int sm_count, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<E, MODE>;
+  if (!attr_set) {
+    CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem_bytes())));
+    attr_set = true;
+  }
+  const int total = ga.m_tiles * ga.n_tiles * ga.groups;
+  if (total <= 0) return SIMSTEP_OK;
+  const int grid = total < sm_count ? total : sm_count;
+  kern<<<grid, kGemmThreads, gemm_smem_bytes(), st>>>(ax, ah, b, ga);
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+template <int MODE>
+int launch_gemm(simstep_handle* h, int prec, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
+                const GemmArgs& ga, int sm_count, cudaStream_t st) {
+  switch (prec) {
+    case SIMSTEP_PREC_TF32: return launch_gemm_t<ElemTF32, MODE>(h, ax, ah, b, ga, sm_count, st);
+    case SIMSTEP_PREC_FP16: return launch_gemm_t<ElemF16, MODE>(h, ax, ah, b, ga, sm_count, st);
+    case SIMSTEP_PREC_BF16: return launch_gemm_t<ElemBF16, MODE>(h, ax, ah, b, ga, sm_count, st);
+  }
+  return fail(h, SIMSTEP_EINVAL, "unknown precision");
+}
+
+int grid_for(long long work_items, int threads, int sm_count) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int pack_matrix(simstep_handle* h, int prec, const float* src_dev, int src_pitch, int rows, void* dst,
+                long long dst_pitch, const PackSegs& segs, int mode, cudaStream_t st) {
+  if (rows <= 0) return SIMSTEP_OK;
+  switch (prec) {
+    case SIMSTEP_PREC_TF32:
+      pack_weight_kernel<ElemTF32><<<rows, 128, 0, st>>>(src_dev, src_pitch, rows, static_cast<float*>(dst),
+                                                         dst_pitch, segs, mode);
+      break;
+    case SIMSTEP_PREC_FP16:
+      pack_weight_kernel<ElemF16><<<rows, 128, 0, st>>>(src_dev, src_pitch, rows, static_cast<__half*>(dst),
+                                                        dst_pitch, segs, mode);
+      break;
+    default:
+      pack_weight_kernel<ElemBF16><<<rows, 128, 0, st>>>(src_dev, src_pitch, rows, static_cast<__nv_bfloat16*>(dst),
+                                                         dst_pitch, segs, mode);
+  }
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+void free_workspace(simstep_handle* h) {
+  cudaFree(h->xbuf); h->xbuf = nullptr;
+  cudaFree(h->hbuf); h->hbuf = nullptr;
+  cudaFree(h->dws); h->dws = nullptr;
+  cudaFree(h->rffin); h->rffin = nullptr;
+  cudaFree(h->rff_part); h->rff_part = nullptr;
+  h->cap_rows = 0;
+}
+
+long long chunk_limit(const simstep_handle* h) {
+  long long c = h->cfg.max_chunk_envs > 0 ? h->cfg.max_chunk_envs : 65536;
+  return round_up(c, kBlockM);
+}
+
+// Workspace for `rows` env rows per pass (grown on demand, never shrunk).
+int ensure_workspace(simstep_handle* h, long long rows) {
+  rows = round_up(rows < 1 ? 1 : rows, kBlockM);
+  if (rows > chunk_limit(h)) rows = chunk_limit(h);
+  if (rows <= h->cap_rows && (!h->have_rff || h->rffin)) return SIMSTEP_OK;
+  if (rows < h->cap_rows) rows = h->cap_rows;
+  CU_TRY(h, cudaDeviceSynchronize());
+  free_workspace(h);
+  const int prec = h->cfg.precision;
+  if (h->have_ensemble || h->S > 0) {
+    CU_TRY(h, cudaMalloc(&h->xbuf, size_t(rows) * h->XP * h->esize));
+    if (h->HT > 0) CU_TRY(h, cudaMalloc(&h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
+    CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->SP * sizeof(float)));
+    CU_TRY(h, cudaMemset(h->xbuf, 0, size_t(rows) * h->XP * h->esize));
+    if (h->HT > 0) CU_TRY(h, cudaMemset(h->hbuf, 0, size_t(h->N) * rows * h->HT * h->esize));
+    int rc = encode_operand(h, &h->tmap_x, prec, h->xbuf, h->XP, rows, h->XP, kBlockM);
+    if (rc) return rc;
+    if (h->HT > 0) {
+      rc = encode_operand(h, &h->tmap_h, prec, h->hbuf, h->HT, static_cast<long long>(h->N) * rows, h->HT, kBlockM);
+      if (rc) return rc;
+    } else {
+      h->tmap_h = h->tmap_x;
+    }
+  }
+  if (h->have_rff) {
+    CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * h->RKT * h->esize));
+    CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * h->RKT * h->esize));
+    CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));
+    int rc = encode_operand(h, &h->tmap_rffin, prec, h->rffin, h->RKT, rows, h->RKT, kBlockM);
+    if (rc) return rc;
+  }
+  h->cap_rows = rows;
+  return SIMSTEP_OK;
+}
+
+template <typename E>
+void launch_prep(simstep_handle* h, const float* s, const float* a, long long n, long long rows_pad,
+                 cudaStream_t st) {
+  const long long total = rows_pad * h->XP;
+  prep_input_kernel<E><<<grid_for(total, 256, h->sm_count), 256, 0, st>>>(
+      s, a, h->S, h->A, h->XP, n, rows_pad, h->cfg.transform ? h->tf_dev : nullptr,
+      static_cast<typename E::storage*>(h->xbuf));
+  g_launches++;
+}
+
+// prep + all layer GEMMs for rows [0, n) of a chunk; leaves un-normalised member
+// deltas in h->dws[N][cap_rows][SP].
+int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st) {
+  const long long rows_pad = round_up(n, kBlockM);
+  switch (h->cfg.precision) {
+    case SIMSTEP_PREC_TF32: launch_prep<ElemTF32>(h, s, a, n, rows_pad, st); break;
+    case SIMSTEP_PREC_FP16: launch_prep<ElemF16>(h, s, a, n, rows_pad, st); break;
+    default: launch_prep<ElemBF16>(h, s, a, n, rows_pad, st);
+  }
+  CU_TRY(h, cudaGetLastError());
+  for (int l = 0; l <= h->L; ++l) {
+    const Layer& ly = h->layers[l];
+    GemmArgs ga{};
+    ga.m_tiles = int(rows_pad / kBlockM);
+    ga.n_tiles = ly.o_pad / kBlockN;
+    ga.groups = h->N;
+    ga.kb_x = ly.kb_x;
+    ga.kb_h0 = ly.kb_h0;
+    ga.kb_h = ly.kb_h;
+    ga.a_rows_per_group = int(h->cap_rows);
+    ga.ax_rows_per_group = 0;
+    ga.b_rows_per_group = ly.o_pad;
+    ga.bias = ly.bias;
+    ga.act = h->cfg.activation;
+    int rc;
+    if (l < h->L) {
+      ga.out = h->hbuf;
+      ga.out_pitch = h->HT;
+      ga.out_group_stride = h->cap_rows * static_cast<long long>(h->HT);
+      ga.out_col0 = ly.out_col0;
+      ga.rows_valid = int(h->cap_rows);
+      ga.cols_valid = ly.o_pad;
+      rc = launch_gemm<kEpiHidden>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
+    } else {
+      ga.out = h->dws;
+      ga.out_pitch = h->SP;
+      ga.out_group_stride = h->cap_rows * static_cast<long long>(h->SP);
+      ga.out_col0 = 0;
+      ga.rows_valid = int(h->cap_rows);
+      ga.cols_valid = h->SP;
+      ga.vec_ok = 1;
+      ga.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
+      ga.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
+      rc = launch_gemm<kEpiFinal>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
+    }
+    if (rc) return rc;
+  }
+  return SIMSTEP_OK;
+}
+
+int launch_post(simstep_handle* h, const float* state, const int32_t* member, int32_t* num_steps, long long n,
+                float* next_state, float* disc, uint8_t* done, cudaStream_t st) {
+  if (h->S > 32 * kPostMaxPerLane) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
+  const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, static_cast<long long>(h->sm_count) * 8));
+  const size_t smem = size_t(kPostWarps) * h->S * sizeof(float);
+#define POST_CASE(NM)                                                                                         \
+  case NM:                                                                                                    \
+    post_step_kernel<NM><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member,    \
+                                                                  num_steps, h->S, n, next_state, disc, done,  \
+                                                                  h->term);                                   \
+    break;
+  switch (h->N) {
+    POST_CASE(1) POST_CASE(2) POST_CASE(3) POST_CASE(4) POST_CASE(5) POST_CASE(6) POST_CASE(7) POST_CASE(8)
+    default: return fail(h, SIMSTEP_EINVAL, "n_models must be in [1, 8]");
+  }
+#undef POST_CASE
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStream_t st) {
+  const long long rows_pad = round_up(n, kBlockM);
+  const long long total = rows_pad * h->RK;
+  const int grid = grid_for(total, 256, h->sm_count);
+  switch (h->cfg.precision) {
+    case SIMSTEP_PREC_TF32:
+      rff_pack_kernel<ElemTF32><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+                                                      static_cast<float*>(h->rffin));
+      break;
+    case SIMSTEP_PREC_FP16:
+      rff_pack_kernel<ElemF16><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+                                                     static_cast<__half*>(h->rffin));
+      break;
+    default:
+      rff_pack_kernel<ElemBF16><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+                                                      static_cast<__nv_bfloat16*>(h->rffin));
+  }
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+// RFF GEMM over the packed rows of the chunk.  w_pad == nullptr: features only.
+int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* phi, cudaStream_t st) {
+  GemmArgs ga{};
+  ga.m_tiles = int(round_up(n, kBlockM) / kBlockM);
+  ga.n_tiles = h->D_pad / kBlockN;
+  ga.groups = 1;
+  ga.kb_x = h->RKT / h->bk;
+  ga.kb_h = 0;
+  ga.b_rows_per_group = h->D_pad;
+  ga.bias = h->rff_b;
+  ga.scale = w_pad;
+  ga.out = phi;
+  ga.out_pitch = h->D;
+  ga.rows_valid = int(n);
+  ga.cols_valid = h->D;
+  ga.rff_part = w_pad ? h->rff_part : nullptr;
+  ga.rff_part_stride = h->cap_rows;
+  ga.rff_phi_scale = float(std::sqrt(2.0 / h->D));
+  return launch_gemm<kEpiRff>(h, h->cfg.precision, h->tmap_rffin, h->tmap_rffin, h->tmap_rffw, ga, h->sm_count, st);
+}
+
+int launch_combine(simstep_handle* h, const float* disc, long long n, float lambda_b, float threshold, float c_min,
+                   float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus, cudaStream_t st) {
+  cost_combine_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(
+      h->rff_part, h->cap_rows, h->D_pad / kBlockN, float(std::sqrt(2.0 / h->D)), disc, n, lambda_b, threshold, c_min,
+      c_max, clamp_cost, dot, cost, ipm, bonus);
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+int stage_w(simstep_handle* h, const float* w_dev, cudaStream_t st) {
+  CU_TRY(h, cudaMemcpyAsync(h->rff_wpad, w_dev, size_t(h->D) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SIMSTEP_OK;
+}
+
+int rff_sources(simstep_handle* h, const float* s, const float* a, const float* s2, RffSrc* out) {
+  RffSrc r{};
+  const int S = h->S, A = h->A, in = h->rff_in;
+  if (in == 2 * S && s2) { r.n = 2; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = s2; r.width[1] = S; }
+  else if (in == S) { r.n = 1; r.ptr[0] = s; r.width[0] = S; }
+  else if (in == S + A) { r.n = 2; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = a; r.width[1] = A; }
+  else if (in == 2 * S + A && s2) { r.n = 3; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = a; r.width[1] = A; r.ptr[2] = s2; r.width[2] = S; }
+  else return fail(h, SIMSTEP_EINVAL, "rff in_dim does not match an input_type of s/ss/sa/sas");
+  *out = r;
+  return SIMSTEP_OK;
+}
+
+int check_step_ready(simstep_handle* h, long long n_envs) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (!h->have_ensemble) return fail(h, SIMSTEP_EINVAL, "simstep_load_ensemble has not been called");
+  if (n_envs < 0) return fail(h, SIMSTEP_EINVAL, "n_envs < 0");
+  return SIMSTEP_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+
+extern "C" {
+
+int simstep_abi_version(void) { return SIMSTEP_ABI_VERSION; }
+
+const char* simstep_last_error(const simstep_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t simstep_launch_count(void) { return g_launches.load(); }
+
+int simstep_create(const simstep_config* cfg, simstep_handle** out) {
+  if (!cfg || !out) return fail(nullptr, SIMSTEP_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != SIMSTEP_ABI_VERSION) return fail(nullptr, SIMSTEP_EINVAL, "abi_version mismatch");
+  if (cfg->state_dim < 1 || cfg->action_dim < 0 || cfg->n_models < 1 || cfg->n_models > 8 || cfg->n_hidden < 0 ||
+      cfg->n_hidden > SIMSTEP_MAX_HIDDEN)
+    return fail(nullptr, SIMSTEP_EINVAL, "bad ensemble shape");
+  if (cfg->precision < 0 || cfg->precision > 2) return fail(nullptr, SIMSTEP_EINVAL, "bad precision");
+  for (int i = 0; i < cfg->n_hidden; ++i)
+    if (cfg->hidden[i] < 1) return fail(nullptr, SIMSTEP_EINVAL, "bad hidden size");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(nullptr, SIMSTEP_ENODEV, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(nullptr, SIMSTEP_ENODEV, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, SIMSTEP_ENODEV,
+                "libsimstep is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+
+  simstep_handle* h = new simstep_handle();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  h->esize = cfg->precision == SIMSTEP_PREC_TF32 ? 4 : 2;
+  h->bk = 128 / h->esize;
+  h->S = cfg->state_dim;
+  h->A = cfg->action_dim;
+  h->N = cfg->n_models;
+  h->L = cfg->n_hidden;
+  h->XP = int(round_up(h->S + h->A, 64));
+  h->SP = int(round_up(h->S, kBlockN));
+  std::vector<int> hp(h->L), hcol(h->L);
+  int ht = 0;
+  for (int i = 0; i < h->L; ++i) {
+    hp[i] = int(round_up(cfg->hidden[i], kBlockN));
+    hcol[i] = ht;
+    ht += hp[i];
+  }
+  h->HT = ht;
+  h->layers.resize(h->L + 1);
+  const int X = h->S + h->A;
+  for (int l = 0; l <= h->L; ++l) {
+    Layer& ly = h->layers[l];
+    ly.out = l < h->L ? cfg->hidden[l] : h->S;
+    ly.o_pad = l < h->L ? hp[l] : h->SP;
+    ly.out_col0 = l < h->L ? hcol[l] : 0;
+    PackSegs& sg = ly.segs;
+    sg.n = 0;
+    if (cfg->dense_connect || l == 0) {
+      // K order of BasicMLP's concat: [x, h_1, ..., h_l]  (dynamics.py:414-419, 427-430)
+      ly.kb_x = h->XP / h->bk;
+      sg.src0[0] = 0; sg.width[0] = X; sg.dst0[0] = 0; sg.n = 1;
+      int src = X;
+      for (int j = 0; j < l && cfg->dense_connect; ++j) {
+        sg.src0[sg.n] = src; sg.width[sg.n] = cfg->hidden[j]; sg.dst0[sg.n] = h->XP + hcol[j];
+        src += cfg->hidden[j];
+        sg.n++;
+      }
+      ly.in_ref = src;
+      ly.kb_h0 = 0;
+      ly.kb_h = (cfg->dense_connect && l > 0) ? (hcol[l - 1] + hp[l - 1]) / h->bk : 0;
+      ly.k_pad = h->XP + ly.kb_h * h->bk;
+    } else {
+      ly.kb_x = 0;
+      ly.kb_h0 = hcol[l - 1] / h->bk;
+      ly.kb_h = hp[l - 1] / h->bk;
+      ly.k_pad = hp[l - 1];
+      ly.in_ref = cfg->hidden[l - 1];
+      sg.src0[0] = 0; sg.width[0] = cfg->hidden[l - 1]; sg.dst0[0] = 0; sg.n = 1;
+    }
+  }
+  // default termination model: none (horizon only) until simstep_set_termination
+  h->term.horizon = 300;
+  h->term.vel_inv_divisor = 1.f;
+  h->term.vel_threshold = 100.f;
+  h->term.pos_dim = 3;
+  *out = h;
+  return SIMSTEP_OK;
+}
+
+int simstep_destroy(simstep_handle* h) {
+  if (!h) return SIMSTEP_OK;
+  cudaDeviceSynchronize();
+  free_workspace(h);
+  for (auto& ly : h->layers) {
+    cudaFree(ly.w);
+    cudaFree(ly.bias);
+  }
+  cudaFree(h->tf_dev);
+  cudaFree(h->out_scale_dev);
+  cudaFree(h->out_shift_dev);
+  cudaFree(h->rff_w);
+  cudaFree(h->rff_b);
+  cudaFree(h->rff_wpad);
+  cudaFree(h->colsum_partial);
+  cudaFree(h->imit_dev);
+  delete h;
+  return SIMSTEP_OK;
+}
+
+int simstep_query(const simstep_handle* h, int32_t* n_layers, int32_t* layer_in, int32_t* layer_out,
+                  int64_t* chunk_envs, int64_t* workspace_bytes) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (n_layers) *n_layers = h->L + 1;
+  for (int l = 0; l <= h->L; ++l) {
+    if (layer_in) layer_in[l] = h->layers[l].in_ref;
+    if (layer_out) layer_out[l] = h->layers[l].out;
+  }
+  if (chunk_envs) *chunk_envs = chunk_limit(h);
+  if (workspace_bytes) {
+    const long long r = h->cap_rows;
+    *workspace_bytes = r * h->XP * h->esize + static_cast<long long>(h->N) * r * h->HT * h->esize +
+                       static_cast<long long>(h->N) * r * h->SP * 4 + (h->have_rff ? r * h->RKT * h->esize : 0);
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host, const float* const* biases_host,
+                          const float* const* transforms_host) {
+  if (!h || !weights_host || !biases_host) return fail(h, SIMSTEP_EINVAL, "null argument");
+  if (h->cfg.transform && !transforms_host) return fail(h, SIMSTEP_EINVAL, "transform set but no transforms given");
+  CU_TRY(h, cudaSetDevice(h->device));
+  const int nl = h->L + 1;
+  cudaStream_t st = nullptr;
+  for (int l = 0; l < nl; ++l) {
+    Layer& ly = h->layers[l];
+    const size_t wbytes = size_t(h->N) * ly.o_pad * ly.k_pad * h->esize;
+    if (!ly.w) CU_TRY(h, cudaMalloc(&ly.w, wbytes));
+    if (!ly.bias) CU_TRY(h, cudaMalloc(&ly.bias, size_t(h->N) * ly.o_pad * sizeof(float)));
+    CU_TRY(h, cudaMemsetAsync(ly.w, 0, wbytes, st));
+    CU_TRY(h, cudaMemsetAsync(ly.bias, 0, size_t(h->N) * ly.o_pad * sizeof(float), st));
+    float* tmp = nullptr;
+    CU_TRY(h, cudaMalloc(&tmp, size_t(ly.out) * ly.in_ref * sizeof(float)));
+    for (int m = 0; m < h->N; ++m) {
+      const float* wsrc = weights_host[m * nl + l];
+      const float* bsrc = biases_host[m * nl + l];
+      if (!wsrc || !bsrc) { cudaFree(tmp); return fail(h, SIMSTEP_EINVAL, "null weight or bias pointer"); }
+      CU_TRY(h, cudaMemcpyAsync(tmp, wsrc, size_t(ly.out) * ly.in_ref * sizeof(float), cudaMemcpyHostToDevice, st));
+      void* dst = static_cast<char*>(ly.w) + size_t(m) * ly.o_pad * ly.k_pad * h->esize;
+      int rc = pack_matrix(h, h->cfg.precision, tmp, ly.in_ref, ly.out, dst, ly.k_pad, ly.segs, 0, st);
+      if (rc) { cudaFree(tmp); return rc; }
+      CU_TRY(h, cudaMemcpyAsync(ly.bias + size_t(m) * ly.o_pad, bsrc, size_t(ly.out) * sizeof(float),
+                                cudaMemcpyHostToDevice, st));
+      CU_TRY(h, cudaStreamSynchronize(st));  // tmp and the pageable host source are reused
+    }
+    cudaFree(tmp);
+    int rc = encode_operand(h, &ly.tmap_w, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
+                            ly.k_pad, kBlockN);
+    if (rc) return rc;
+  }
+  // transforms
+  const int S = h->S, A = h->A;
+  if (!h->tf_dev) CU_TRY(h, cudaMalloc(&h->tf_dev, size_t(2 * S + 2 * A + 4) * sizeof(float)));
+  if (!h->out_scale_dev) CU_TRY(h, cudaMalloc(&h->out_scale_dev, size_t(h->SP) * sizeof(float)));
+  if (!h->out_shift_dev) CU_TRY(h, cudaMalloc(&h->out_shift_dev, size_t(h->SP) * sizeof(float)));
+  if (h->cfg.transform) {
+    for (int i = 0; i < 6; ++i)
+      if (!transforms_host[i]) return fail(h, SIMSTEP_EINVAL, "null transform vector");
+    std::vector<float> tf(2 * S + 2 * A), osc(h->SP, 1.f), osh(h->SP, 0.f);
+    std::memcpy(tf.data(), transforms_host[0], S * sizeof(float));
+    std::memcpy(tf.data() + S, transforms_host[1], S * sizeof(float));
+    std::memcpy(tf.data() + 2 * S, transforms_host[2], A * sizeof(float));
+    std::memcpy(tf.data() + 2 * S + A, transforms_host[3], A * sizeof(float));
+    std::memcpy(osh.data(), transforms_host[4], S * sizeof(float));
+    std::memcpy(osc.data(), transforms_host[5], S * sizeof(float));
+    CU_TRY(h, cudaMemcpy(h->tf_dev, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->out_scale_dev, osc.data(), osc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->out_shift_dev, osh.data(), osh.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CU_TRY(h, cudaDeviceSynchronize());
+  h->have_ensemble = true;
+  return SIMSTEP_OK;
+}
+
+int simstep_set_termination(simstep_handle* h, const simstep_termination* t) {
+  if (!h || !t) return fail(h, SIMSTEP_EINVAL, "null argument");
+  if (t->n_bodies < 0 || t->n_bodies > SIMSTEP_MAX_BODIES) return fail(h, SIMSTEP_EINVAL, "bad n_bodies");
+  TermConst& c = h->term;
+  c.horizon = t->horizon;
+  c.enable_velocity_check = t->enable_velocity_check;
+  c.vel_offset = t->vel_offset;
+  c.vel_threshold = t->vel_threshold;
+  c.vel_inv_divisor = t->vel_divisor != 0.f ? 1.f / t->vel_divisor : 1.f;
+  c.record_all_world = t->record_all_world;
+  c.record_world_root_pos = t->record_world_root_pos;
+  c.n_bodies = t->n_bodies;
+  c.pos_dim = t->pos_dim > 0 ? t->pos_dim : 3;
+  for (int i = 0; i < t->n_bodies; ++i) {
+    if (t->body_offset[i] < 0 || t->body_offset[i] + c.pos_dim + 1 >= h->S)
+      return fail(h, SIMSTEP_EINVAL, "body offset outside the state vector");
+    c.body_offset[i] = t->body_offset[i];
+    c.body_shape[i] = t->body_shape[i];
+    c.body_radius[i] = 0.5f * t->body_param0[i];
+    c.body_half_height[i] = 0.5f * t->body_param1[i];
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, const float* weight_host,
+                     const float* bias_host, int32_t split) {
+  if (!h || !weight_host || !bias_host || feature_dim < 1 || in_dim < 1) return fail(h, SIMSTEP_EINVAL, "bad argument");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaDeviceSynchronize());
+  cudaFree(h->rff_w); cudaFree(h->rff_b); cudaFree(h->rff_wpad); cudaFree(h->colsum_partial);
+  cudaFree(h->rffin); cudaFree(h->rff_part);
+  h->rff_w = nullptr; h->rff_b = nullptr; h->rff_wpad = nullptr; h->colsum_partial = nullptr;
+  h->rffin = nullptr; h->rff_part = nullptr;
+  h->have_rff = false;
+  h->D = feature_dim;
+  h->D_pad = int(round_up(feature_dim, kBlockN));
+  h->rff_in = in_dim;
+  h->RK = int(round_up(in_dim, 64));
+  h->rff_split = split ? 1 : 0;
+  h->RKT = h->rff_split ? 3 * h->RK : h->RK;
+  const size_t wbytes = size_t(h->D_pad) * h->RKT * h->esize;
+  CU_TRY(h, cudaMalloc(&h->rff_w, wbytes));
+  CU_TRY(h, cudaMemset(h->rff_w, 0, wbytes));
+  CU_TRY(h, cudaMalloc(&h->rff_b, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMemset(h->rff_b, 0, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->rff_wpad, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMemset(h->rff_wpad, 0, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->colsum_partial, size_t(1024) * h->D_pad * sizeof(double)));
+  float* tmp = nullptr;
+  CU_TRY(h, cudaMalloc(&tmp, size_t(feature_dim) * in_dim * sizeof(float)));
+  CU_TRY(h, cudaMemcpy(tmp, weight_host, size_t(feature_dim) * in_dim * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->rff_b, bias_host, size_t(feature_dim) * sizeof(float), cudaMemcpyHostToDevice));
+  PackSegs sg{};
+  sg.n = 1; sg.src0[0] = 0; sg.width[0] = in_dim;
+  // operand triple on the A side is [hi | lo | hi]; B side is [hi | hi | lo]
+  const int modes[3] = {1, 1, 2};
+  for (int part = 0; part < (h->rff_split ? 3 : 1); ++part) {
+    sg.dst0[0] = part * h->RK;
+    int rc = pack_matrix(h, h->cfg.precision, tmp, in_dim, feature_dim, h->rff_w, h->RKT, sg,
+                         h->rff_split ? modes[part] : 0, nullptr);
+    if (rc) { cudaFree(tmp); return rc; }
+  }
+  CU_TRY(h, cudaDeviceSynchronize());
+  cudaFree(tmp);
+  int rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN);
+  if (rc) return rc;
+  h->have_rff = true;
+  return SIMSTEP_OK;
+}
+
+int simstep_forward(simstep_handle* h, const float* state_dev, const float* action_dev, int64_t n_envs,
+                    float* delta_dev, void* stream) {
+  int rc = check_step_ready(h, n_envs);
+  if (rc) return rc;
+  if (n_envs == 0) return SIMSTEP_OK;
+  if (!state_dev || !action_dev || !delta_dev) return fail(h, SIMSTEP_EINVAL, "null device pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_workspace(h, n_envs))) return rc;
+  for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
+    const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
+    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
+    const long long total = static_cast<long long>(h->N) * n * h->S;
+    extract_delta_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, st>>>(h->dws, h->cap_rows, h->SP, h->N, h->S, n,
+                                                                            delta_dev, n_envs, r0);
+    g_launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_discrepancy(simstep_handle* h, const float* state_dev, const float* action_dev, int64_t n_envs,
+                        float* disc_dev, void* stream) {
+  int rc = check_step_ready(h, n_envs);
+  if (rc) return rc;
+  if (n_envs == 0) return SIMSTEP_OK;
+  if (!state_dev || !action_dev || !disc_dev) return fail(h, SIMSTEP_EINVAL, "null device pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_workspace(h, n_envs))) return rc;
+  for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
+    const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
+    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
+    if ((rc = launch_post(h, nullptr, nullptr, nullptr, n, nullptr, disc_dev + r0, nullptr, st))) return rc;
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_step(simstep_handle* h, const float* state_dev, const float* action_dev, const int32_t* member_dev,
+                 int32_t* num_steps_dev, int64_t n_envs, float* next_state_dev, float* disc_dev, uint8_t* done_dev,
+                 void* stream) {
+  int rc = check_step_ready(h, n_envs);
+  if (rc) return rc;
+  if (n_envs == 0) return SIMSTEP_OK;
+  if (!state_dev || !action_dev || !next_state_dev) return fail(h, SIMSTEP_EINVAL, "null device pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_workspace(h, n_envs))) return rc;
+  for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
+    const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
+    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
+    if ((rc = launch_post(h, state_dev + r0 * h->S, member_dev ? member_dev + r0 : nullptr,
+                          num_steps_dev ? num_steps_dev + r0 : nullptr, n, next_state_dev + r0 * h->S,
+                          disc_dev ? disc_dev + r0 : nullptr, done_dev ? done_dev + r0 : nullptr, st)))
+      return rc;
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_step_cost(simstep_handle* h, const float* state_dev, const float* action_dev, const int32_t* member_dev,
+                      int32_t* num_steps_dev, int64_t n_envs, float* next_state_dev, float* disc_dev,
+                      uint8_t* done_dev, const float* w_dev, float lambda_b, float threshold, float c_min, float c_max,
+                      int32_t clamp_cost, float* cost_dev, float* ipm_dev, float* bonus_dev, void* stream) {
+  int rc = check_step_ready(h, n_envs);
+  if (rc) return rc;
+  if (!h->have_rff) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (n_envs == 0) return SIMSTEP_OK;
+  if (!state_dev || !action_dev || !next_state_dev || !disc_dev || !w_dev)
+    return fail(h, SIMSTEP_EINVAL, "null device pointer (state, action, next_state, disc and w are required)");
+  if (next_state_dev == state_dev) return fail(h, SIMSTEP_EINVAL, "next_state must not alias state in step_cost");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_workspace(h, n_envs))) return rc;
+  if ((rc = stage_w(h, w_dev, st))) return rc;
+  for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
+    const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
+    const float* s = state_dev + r0 * h->S;
+    const float* a = action_dev + r0 * h->A;
+    float* s2 = next_state_dev + r0 * h->S;
+    if ((rc = run_ensemble_chunk(h, s, a, n, st))) return rc;
+    if ((rc = launch_post(h, s, member_dev ? member_dev + r0 : nullptr, num_steps_dev ? num_steps_dev + r0 : nullptr,
+                          n, s2, disc_dev + r0, done_dev ? done_dev + r0 : nullptr, st)))
+      return rc;
+    RffSrc src;
+    if ((rc = rff_sources(h, s, a, s2, &src))) return rc;
+    if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
+    if ((rc = launch_combine(h, disc_dev + r0, n, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
+                             cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
+                             bonus_dev ? bonus_dev + r0 : nullptr, st)))
+      return rc;
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_rff_features(simstep_handle* h, const float* x_dev, int64_t n_rows, float* phi_dev, double* phi_sum_dev,
+                         void* stream) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (!h->have_rff) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (n_rows < 0 || (n_rows > 0 && (!x_dev || !phi_dev))) return fail(h, SIMSTEP_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (n_rows > 0) {
+    if ((rc = ensure_workspace(h, n_rows))) return rc;
+    for (long long r0 = 0; r0 < n_rows; r0 += h->cap_rows) {
+      const long long n = std::min<long long>(h->cap_rows, n_rows - r0);
+      RffSrc src{};
+      src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
+      if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+      if ((rc = launch_rff_gemm(h, n, nullptr, phi_dev + r0 * h->D, st))) return rc;
+    }
+  }
+  if (phi_sum_dev) {
+    const int nb = int(std::min<long long>(1024, std::max<long long>(1, (n_rows + 63) / 64)));
+    const int rpb = int((n_rows + nb - 1) / nb);
+    colsum_partial_kernel<<<nb, 256, 0, st>>>(phi_dev, n_rows, h->D, rpb > 0 ? rpb : 1, h->colsum_partial);
+    colsum_final_kernel<<<(h->D + 255) / 256, 256, 0, st>>>(h->colsum_partial, nb, h->D, phi_sum_dev, 0);
+    g_launches += 2;
+    CU_TRY(h, cudaGetLastError());
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_rff_dot(simstep_handle* h, const float* x_dev, int64_t n_rows, const float* w_dev, float* dot_dev,
+                    void* stream) {
+  return simstep_bonus_cost(h, x_dev, nullptr, n_rows, w_dev, 0.f, 1.f, 0.f, 0.f, 0, dot_dev, nullptr, nullptr,
+                            stream);
+}
+
+int simstep_bonus_cost(simstep_handle* h, const float* x_dev, const float* disc_dev, int64_t n_rows,
+                       const float* w_dev, float lambda_b, float threshold, float c_min, float c_max,
+                       int32_t clamp_cost, float* cost_dev, float* ipm_dev, float* bonus_dev, void* stream) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (!h->have_rff) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (n_rows < 0) return fail(h, SIMSTEP_EINVAL, "n_rows < 0");
+  if (n_rows == 0) return SIMSTEP_OK;
+  if (!x_dev || !w_dev) return fail(h, SIMSTEP_EINVAL, "null device pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = ensure_workspace(h, n_rows))) return rc;
+  if ((rc = stage_w(h, w_dev, st))) return rc;
+  for (long long r0 = 0; r0 < n_rows; r0 += h->cap_rows) {
+    const long long n = std::min<long long>(h->cap_rows, n_rows - r0);
+    RffSrc src{};
+    src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
+    if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
+    if (disc_dev == nullptr) {
+      // raw dot only (simstep_rff_dot): cost_dev receives phi.w
+      rc = launch_combine(h, nullptr, n, 0.f, 1.f, 0.f, 0.f, 0, cost_dev ? cost_dev + r0 : nullptr, nullptr, nullptr,
+                          nullptr, st);
+    } else {
+      rc = launch_combine(h, disc_dev + r0, n, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
+                          cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
+                          bonus_dev ? bonus_dev + r0 : nullptr, st);
+    }
+    if (rc) return rc;
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, double* out_dev, void* stream) {
+  if (!h || !out_dev || n < 0 || (n > 0 && !x_dev)) return fail(h, SIMSTEP_EINVAL, "bad argument");
+  reduce_max_sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, n, out_dev);
+  g_launches++;
+  CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, int32_t k, const float* a_dev,
+                       const float* b_dev, const float* bias_dev, float* d_dev, void* stream) {
+  if (precision < 0 || precision > 2 || groups < 1 || m < 1 || n < 1 || k < 1 || !a_dev || !b_dev || !d_dev)
+    return fail(nullptr, SIMSTEP_EINVAL, "bad argument");
+  simstep_handle* h = nullptr;  // errors go to the create-error slot
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int es = precision == SIMSTEP_PREC_TF32 ? 4 : 2;
+  const int bk = 128 / es;
+  const long long m_pad = round_up(m, kBlockM), n_pad = round_up(n, kBlockN), k_pad = round_up(k, 64);
+  cudaDeviceProp prop;
+  int dev = 0;
+  CU_TRY(h, cudaGetDevice(&dev));
+  CU_TRY(h, cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(nullptr, SIMSTEP_ENODEV, "libsimstep is built for sm_100a only");
+  void *ap = nullptr, *bp = nullptr;
+  float* biasp = nullptr;
+  CU_TRY(h, cudaMalloc(&ap, size_t(groups) * m_pad * k_pad * es));
+  CU_TRY(h, cudaMalloc(&bp, size_t(groups) * n_pad * k_pad * es));
+  CU_TRY(h, cudaMalloc(&biasp, size_t(groups) * n_pad * sizeof(float)));
+  CU_TRY(h, cudaMemsetAsync(ap, 0, size_t(groups) * m_pad * k_pad * es, st));
+  CU_TRY(h, cudaMemsetAsync(bp, 0, size_t(groups) * n_pad * k_pad * es, st));
+  CU_TRY(h, cudaMemsetAsync(biasp, 0, size_t(groups) * n_pad * sizeof(float), st));
+  PackSegs sg{};
+  sg.n = 1; sg.src0[0] = 0; sg.width[0] = k; sg.dst0[0] = 0;
+  int rc = SIMSTEP_OK;
+  for (int g = 0; g < groups && !rc; ++g) {
+    rc = pack_matrix(h, precision, a_dev + size_t(g) * m * k, k, int(m), static_cast<char*>(ap) + size_t(g) * m_pad * k_pad * es,
+                     k_pad, sg, 0, st);
+    if (!rc)
+      rc = pack_matrix(h, precision, b_dev + size_t(g) * n * k, k, n, static_cast<char*>(bp) + size_t(g) * n_pad * k_pad * es,
+                       k_pad, sg, 0, st);
+    if (!rc && bias_dev)
+      if (cudaMemcpyAsync(biasp + size_t(g) * n_pad, bias_dev + size_t(g) * n, size_t(n) * sizeof(float),
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = fail(nullptr, SIMSTEP_ECUDA, "bias copy failed");
+  }
+  CUtensorMap ta, tb;
+  if (!rc) rc = encode_operand(h, &ta, precision, ap, k_pad, groups * m_pad, k_pad, kBlockM);
+  if (!rc) rc = encode_operand(h, &tb, precision, bp, k_pad, groups * n_pad, k_pad, kBlockN);
+  if (!rc) {
+    GemmArgs ga{};
+    ga.m_tiles = int(m_pad / kBlockM);
+    ga.n_tiles = int(n_pad / kBlockN);
+    ga.groups = groups;
+    ga.kb_x = 0;
+    ga.kb_h0 = 0;
+    ga.kb_h = int(k_pad / bk);
+    ga.a_rows_per_group = int(m_pad);
+    ga.b_rows_per_group = int(n_pad);
+    ga.bias = biasp;
+    ga.out = d_dev;
+    ga.out_pitch = n;
+    ga.out_group_stride = m * static_cast<long long>(n);
+    ga.rows_valid = int(m);
+    ga.cols_valid = n;
+    ga.vec_ok = (n % 4 == 0) ? 1 : 0;
+    rc = launch_gemm<kEpiFinal>(h, precision, ta, ta, tb, ga, prop.multiProcessorCount, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(ap);
+  cudaFree(bp);
+  cudaFree(biasp);
+  if (!rc && e != cudaSuccess) return fail(nullptr, SIMSTEP_ECUDA, std::string("debug gemm: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+}  // extern "C"
+
+#include "imitation_api.inc"

@@ -1,0 +1,345 @@
+// HBM-bound kernels around the ensemble GEMMs: input normalisation, the fused
+// next-state / discrepancy / termination kernel, RFF operand packing, the
+// cost combine and small reductions.  All row-parallel, coalesced, no atomics
+// on the data path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gemm_tcgen05.cuh"
+#include "../../include/simstep.h"
+
+namespace simstep {
+
+// ---- operand packing -----------------------------------------------------
+
+struct PackSegs {
+  int n;
+  int src0[SIMSTEP_MAX_HIDDEN + 2];
+  int width[SIMSTEP_MAX_HIDDEN + 2];
+  int dst0[SIMSTEP_MAX_HIDDEN + 2];
+};
+
+// dst[o][dst0+i] = cvt(src[o][src0+i]) for every segment, dst pre-zeroed.
+// One block row per output feature; used once at load time.
+template <typename E>
+__global__ void pack_weight_kernel(const float* __restrict__ src, int src_pitch, int rows,
+                                   typename E::storage* __restrict__ dst, long long dst_pitch, PackSegs segs,
+                                   int mode /*0 value, 1 hi, 2 lo*/) {
+  const int o = blockIdx.x;
+  if (o >= rows) return;
+  for (int s = 0; s < segs.n; ++s) {
+    for (int i = threadIdx.x; i < segs.width[s]; i += blockDim.x) {
+      const float v = src[size_t(o) * src_pitch + segs.src0[s] + i];
+      float out = v;
+      if (mode == 2) out = v - static_cast<float>(E::cvt(v));
+      dst[size_t(o) * dst_pitch + segs.dst0[s] + i] = E::cvt(out);
+    }
+  }
+}
+
+// x = [(s - mean_s)/scale_s, (a - mean_a)/scale_a, 0...]  (reference
+// milo/milo/dynamics.py:225-230) written in the GEMM operand format.  Rows in
+// [n_rows, rows_pad) are zero-filled so padded tiles stay finite.
+template <typename E>
+__global__ void prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A,
+                                  int XP, long long n_rows, long long rows_pad,
+                                  const float* __restrict__ tf /* mean_s|scale_s|mean_a|scale_a or null */,
+                                  typename E::storage* __restrict__ x) {
+  const long long total = rows_pad * XP;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / XP;
+    const int col = static_cast<int>(idx - row * XP);
+    float v = 0.f;
+    if (row < n_rows) {
+      if (col < S) {
+        v = state[row * S + col];
+        if (tf) v = (v - tf[col]) / tf[S + col];
+      } else if (col < S + A) {
+        const int c = col - S;
+        v = action[row * A + c];
+        if (tf) v = (v - tf[2 * S + c]) / tf[2 * S + A + c];
+      }
+    }
+    x[idx] = E::cvt(v);
+  }
+}
+
+// RFF operand rows: concatenation of up to three fp32 sources, optionally as
+// [hi | lo | hi] operand triple (see simstep_load_rff).
+struct RffSrc {
+  int n;
+  const float* ptr[3];
+  int width[3];
+};
+
+template <typename E>
+__global__ void rff_pack_kernel(RffSrc src, int in_dim, int RK, int split, long long n_rows, long long rows_pad,
+                                typename E::storage* __restrict__ out) {
+  const int RKT = split ? 3 * RK : RK;
+  const long long total = rows_pad * RK;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / RK;
+    int col = static_cast<int>(idx - row * RK);
+    float v = 0.f;
+    if (row < n_rows && col < in_dim) {
+      int c = col;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (s < src.n) {
+          if (c >= 0 && c < src.width[s]) v = src.ptr[s][row * src.width[s] + c];
+          c -= src.width[s];
+        }
+      }
+    }
+    typename E::storage* orow = out + row * RKT;
+    const typename E::storage hi = E::cvt(v);
+    orow[col] = hi;
+    if (split) {
+      orow[RK + col] = E::cvt(v - static_cast<float>(hi));
+      orow[2 * RK + col] = hi;
+    }
+  }
+}
+
+// ---- fused next-state / discrepancy / termination kernel -------------------
+
+struct TermConst {
+  int horizon;
+  int enable_velocity_check;
+  int vel_offset;
+  float vel_threshold;
+  float vel_inv_divisor;
+  int record_all_world;
+  int record_world_root_pos;
+  int n_bodies;
+  int pos_dim;
+  int body_offset[SIMSTEP_MAX_BODIES];
+  int body_shape[SIMSTEP_MAX_BODIES];
+  float body_radius[SIMSTEP_MAX_BODIES];      // 0.5*Param0
+  float body_half_height[SIMSTEP_MAX_BODIES]; // 0.5*Param1
+};
+
+constexpr int kPostWarps = 8;
+constexpr int kPostMaxPerLane = 8;  // supports S <= 256
+
+// One warp per env row (reference: sim_env.py:140-173 for the step and the
+// termination test, dynamics.py:134-143 for the discrepancy).
+//   delta  [NM][delta_rows][SP] fp32 workspace of the final GEMM, row = chunk-local
+//   state  [E][S], next_state [E][S] (may alias state)
+template <int NM>
+__global__ void __launch_bounds__(kPostWarps * 32)
+post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, const float* state,
+                 const int32_t* __restrict__ member, int32_t* num_steps, int S, long long n_rows,
+                 float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done, const TermConst tc) {
+  extern __shared__ float sm_rows[];  // [kPostWarps][S]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* srow = sm_rows + size_t(wib) * S;
+  const long long warp_global = blockIdx.x * static_cast<long long>(kPostWarps) + wib;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kPostWarps;
+  constexpr int NP = NM * (NM - 1) / 2;
+
+  for (long long row = warp_global; row < n_rows; row += n_warps) {
+    float d[NM][kPostMaxPerLane];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const float* drow = delta + (static_cast<long long>(m) * delta_rows + row) * SP;
+#pragma unroll
+      for (int i = 0; i < kPostMaxPerLane; ++i) {
+        const int j = lane + 32 * i;
+        d[m][i] = (j < S) ? __ldg(drow + j) : 0.f;
+      }
+    }
+
+    if (disc != nullptr) {
+      float acc[NP > 0 ? NP : 1];
+      int p = 0;
+#pragma unroll
+      for (int a = 0; a < NM; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < NM; ++b) {
+          float s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < kPostMaxPerLane; ++i) {
+            const float t = d[a][i] - d[b][i];
+            s2 = fmaf(t, t, s2);
+          }
+          acc[p++] = s2;
+        }
+      }
+      float best = 0.f;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        float s2 = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        // NaN must propagate like torch.max does
+        if (s2 != s2) best = s2;
+        else if (best == best && s2 > best) best = s2;
+      }
+      if (lane == 0) disc[row] = sqrtf(best);
+    }
+
+    if (next_state != nullptr) {
+      const int mem = member ? member[row] : 0;
+      float nxt[kPostMaxPerLane];
+#pragma unroll
+      for (int i = 0; i < kPostMaxPerLane; ++i) {
+        const int j = lane + 32 * i;
+        float dm = 0.f;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) dm = (m == mem) ? d[m][i] : dm;
+        nxt[i] = 0.f;
+        if (j < S) {
+          nxt[i] = state[row * S + j] + dm;
+          next_state[row * S + j] = nxt[i];
+          srow[j] = nxt[i];
+        }
+      }
+      int steps = 0;
+      if (num_steps != nullptr) {
+        steps = num_steps[row] + 1;
+        if (lane == 0) num_steps[row] = steps;
+      }
+      if (done != nullptr) {
+        __syncwarp();
+        bool flag = false;
+        if (lane < tc.n_bodies) {
+          const int off = tc.body_offset[lane];
+          const int shape = tc.body_shape[lane];
+          float y = srow[off + 1];
+          if (!(tc.record_all_world || (lane == 0 && tc.record_world_root_pos))) y += srow[0];
+          const float lim = tc.body_radius[lane] + 0.0001f;
+          if (shape == SIMSTEP_SHAPE_SPHERE) {
+            flag = y <= lim;
+          } else if (shape == SIMSTEP_SHAPE_CAPSULE) {
+            const float cap = tc.body_half_height[lane] * srow[off + tc.pos_dim + 1];
+            flag = (y + cap <= lim) || (y - cap <= lim);
+          }
+        }
+        if (tc.enable_velocity_check) {
+#pragma unroll
+          for (int i = 0; i < kPostMaxPerLane; ++i) {
+            const int j = lane + 32 * i;
+            if (j >= tc.vel_offset && j < S) flag = flag || (fabsf(nxt[i] * tc.vel_inv_divisor) > tc.vel_threshold);
+          }
+        }
+        const bool any = __any_sync(0xffffffffu, flag);
+        if (lane == 0) done[row] = (any || (num_steps != nullptr && steps >= tc.horizon)) ? 1 : 0;
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// delta workspace -> dense [NM][E][S] rows (DynamicsModel.forward's return value)
+__global__ void extract_delta_kernel(const float* __restrict__ ws, long long ws_rows, int SP, int NM, int S,
+                                     long long n_rows, float* __restrict__ out, long long out_rows,
+                                     long long out_row0) {
+  const long long total = static_cast<long long>(NM) * n_rows * S;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx % S);
+    const long long t = idx / S;
+    const long long row = t % n_rows;
+    const int m = static_cast<int>(t / n_rows);
+    out[(static_cast<long long>(m) * out_rows + out_row0 + row) * S + j] =
+        ws[(static_cast<long long>(m) * ws_rows + row) * SP + j];
+  }
+}
+
+// ---- cost combine (reference milo/milo/linear_cost.py:96-103, 130-147) ------
+
+__global__ void cost_combine_kernel(const float* __restrict__ part, long long part_stride, int n_parts,
+                                    float phi_scale, const float* __restrict__ disc, long long n_rows, float lambda_b,
+                                    float threshold, float c_min, float c_max, int clamp_cost,
+                                    float* __restrict__ dot_out, float* __restrict__ cost, float* __restrict__ ipm,
+                                    float* __restrict__ bonus) {
+  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
+       row += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float dot = 0.f;
+    for (int t = 0; t < n_parts; ++t) dot += part[t * part_stride + row];
+    dot *= phi_scale;
+    if (dot_out) dot_out[row] = dot;
+    if (disc == nullptr) continue;
+    float c = dot;
+    float b;
+    if (clamp_cost) {
+      c = fminf(fmaxf(c, c_min), c_max);
+      if (dot != dot) c = dot;  // torch.clamp keeps NaN
+      float dh = disc[row] / threshold;
+      if (dh > 1.0f) dh = 1.0f;
+      b = dh * c_min;
+    } else {
+      b = disc[row];
+    }
+    const float i_ = (1.f - lambda_b) * c;
+    const float wb = lambda_b * b;
+    if (ipm) ipm[row] = i_;
+    if (bonus) bonus[row] = wb;
+    if (cost) cost[row] = i_ - wb;
+  }
+}
+
+// ---- reductions ------------------------------------------------------------
+
+// column sums of a [n_rows][D] fp32 matrix, fp64 accumulate, two passes so the
+// result does not depend on scheduling: partial[b][d] then final.
+__global__ void colsum_partial_kernel(const float* __restrict__ x, long long n_rows, int D, int rows_per_block,
+                                      double* __restrict__ partial) {
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, n_rows);
+  for (int dcol = threadIdx.x; dcol < D; dcol += blockDim.x) {
+    double s = 0.0;
+    for (long long r = r0; r < r1; ++r) s += static_cast<double>(x[r * D + dcol]);
+    partial[static_cast<long long>(blockIdx.x) * D + dcol] = s;
+  }
+}
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int n_blocks, int D, double* __restrict__ out,
+                                    int accumulate) {
+  for (int dcol = blockIdx.x * blockDim.x + threadIdx.x; dcol < D; dcol += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partial[static_cast<long long>(b) * D + dcol];
+    out[dcol] = accumulate ? out[dcol] + s : s;
+  }
+}
+
+// out[0] = max, out[1] = sum; single block, deterministic.
+__global__ void reduce_max_sum_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  __shared__ double s_sum[32];
+  __shared__ float s_max[32];
+  double sum = 0.0;
+  float mx = -INFINITY;
+  bool nan = false;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    sum += v;
+    nan = nan || (v != v);
+    mx = fmaxf(mx, v);
+  }
+  if (nan) mx = NAN;
+  for (int off = 16; off > 0; off >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float o = __shfl_xor_sync(0xffffffffu, mx, off);
+    mx = (mx != mx || o != o) ? NAN : fmaxf(mx, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[threadIdx.x >> 5] = sum;
+    s_max[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0;
+    float tm = -INFINITY;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) {
+      ts += s_sum[w];
+      tm = (tm != tm || s_max[w] != s_max[w]) ? NAN : fmaxf(tm, s_max[w]);
+    }
+    out[0] = tm;
+    out[1] = ts;
+  }
+}
+
+}  // namespace simstep

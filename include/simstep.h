@@ -1,0 +1,244 @@
+/*
+ * simstep.h — C ABI of libsimstep.so: the B200 (sm_100a) implementation of the
+ * batched learned-dynamics environment step of gym-simenv / MILO.
+ *
+ * Every entry point below replaces one call on the reference's hot path.  The
+ * citations are paths under the reference tree (file:line):
+ *
+ *   SE  = gym-simenv/gym_simenv/envs/sim_env.py
+ *   DYN = milo/milo/dynamics.py
+ *   LC  = milo/milo/linear_cost.py
+ *   SI  = deepmimic/deepmimic/DeepMimicCore/scenes/SceneImitate.cpp
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller,
+ *     pointers named *_host are host pointers, read during the call only.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued
+ *     on it and the call returns without synchronising unless stated.
+ *   - every function returns 0 on success, a negative SIMSTEP_E* code on
+ *     failure; simstep_last_error() gives the message.  Nothing throws.
+ *   - a handle is bound to the CUDA device that was current at create time and
+ *     is not thread-safe: one handle per GPU per thread.
+ *   - all matrices are row-major fp32 and dense unless a pitch is given.
+ */
+#ifndef SIMSTEP_H_
+#define SIMSTEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMSTEP_ABI_VERSION 1
+
+#define SIMSTEP_OK 0
+#define SIMSTEP_EINVAL (-1)   /* bad argument / wrong call order            */
+#define SIMSTEP_ECUDA (-2)    /* a CUDA runtime or driver call failed        */
+#define SIMSTEP_ENODEV (-3)   /* no sm_100 device                           */
+#define SIMSTEP_ENOMEM (-4)   /* workspace allocation failed                */
+
+#define SIMSTEP_MAX_HIDDEN 8
+#define SIMSTEP_MAX_BODIES 32
+#define SIMSTEP_MAX_JOINTS 32
+
+/* operand formats of the tensor-core GEMMs (fp32 accumulate in TMEM) */
+#define SIMSTEP_PREC_TF32 0   /* 10-bit mantissa, 8-bit exponent (default)  */
+#define SIMSTEP_PREC_FP16 1   /* 10-bit mantissa, 5-bit exponent, saturating */
+#define SIMSTEP_PREC_BF16 2   /* 7-bit mantissa, 8-bit exponent              */
+
+#define SIMSTEP_ACT_RELU 0
+#define SIMSTEP_ACT_TANH 1
+
+#define SIMSTEP_SHAPE_SPHERE 0
+#define SIMSTEP_SHAPE_CAPSULE 1
+#define SIMSTEP_SHAPE_BOX 2   /* ignored, as SE:238-244 does */
+
+typedef struct simstep_handle simstep_handle;
+
+/* Shape of the dynamics ensemble: the ctor arguments of DynamicsEnsemble
+ * (DYN:19-80) and BasicMLP (DYN:394-420) that matter for inference. */
+typedef struct simstep_config {
+  int32_t abi_version;      /* SIMSTEP_ABI_VERSION                           */
+  int32_t state_dim;        /* S, 226 for humanoid3d                         */
+  int32_t action_dim;       /* A, 28                                         */
+  int32_t n_models;         /* N ensemble members (DYN:26)                   */
+  int32_t n_hidden;         /* number of hidden layers                       */
+  int32_t hidden[SIMSTEP_MAX_HIDDEN]; /* hidden_sizes (DYN:28)               */
+  int32_t dense_connect;    /* DYN:30, DYN:414-419                           */
+  int32_t activation;       /* SIMSTEP_ACT_* (DYN:31, DYN:410)               */
+  int32_t transform;        /* DYN:32: normalise in / un-normalise out       */
+  int32_t precision;        /* SIMSTEP_PREC_*                                */
+  int32_t max_chunk_envs;   /* workspace rows per pass; 0 = default          */
+  int32_t reserved[7];
+} simstep_config;
+
+/* Termination model of SimEnv.is_done (SE:164-268). */
+typedef struct simstep_termination {
+  int32_t horizon;               /* SE:28, SE:170                            */
+  int32_t enable_velocity_check; /* SE:27, SE:172                            */
+  int32_t vel_offset;            /* deepmimic.get_vel_offset(), 136          */
+  float vel_threshold;           /* SE:259, 100                              */
+  float vel_divisor;             /* sampling_rate if RecordVelAsPos else 1   */
+  int32_t record_all_world;      /* SE:181, SE:227                           */
+  int32_t record_world_root_pos; /* SE:181, SE:227                           */
+  int32_t n_bodies;              /* len(fall_contact_bodies), SE:102         */
+  int32_t body_offset[SIMSTEP_MAX_BODIES]; /* (pos+rot dim)*id + 1, SE:103   */
+  int32_t body_shape[SIMSTEP_MAX_BODIES];  /* SIMSTEP_SHAPE_*                */
+  float body_param0[SIMSTEP_MAX_BODIES];   /* diameter, SE:188, SE:201       */
+  float body_param1[SIMSTEP_MAX_BODIES];   /* cylinder height, SE:202        */
+  int32_t pos_dim;               /* 3, SE:99                                 */
+} simstep_termination;
+
+/* ---- lifetime ----------------------------------------------------------- */
+
+int simstep_abi_version(void);
+/* Message of the last failure on this handle (or of the last failed create
+ * when h is NULL).  The pointer stays valid until the next call. */
+const char* simstep_last_error(const simstep_handle* h);
+
+int simstep_create(const simstep_config* cfg, simstep_handle** out);
+int simstep_destroy(simstep_handle* h);
+
+/* Packed-operand geometry, for callers that size buffers and for tests. */
+int simstep_query(const simstep_handle* h, int32_t* n_layers, int32_t* layer_in /*[n_layers]*/,
+                  int32_t* layer_out /*[n_layers]*/, int64_t* chunk_envs, int64_t* workspace_bytes);
+
+/* ---- parameters --------------------------------------------------------- */
+
+/* Replaces DynamicsEnsemble.load_ensemble / DynamicsModel.load (DYN:118-131,
+ * DYN:380-386): weights_host[m*n_layers+l] is fc_layers.l.weight of member m
+ * ([out,in] row-major, in = BasicMLP's concat width), biases_host likewise.
+ * transforms_host = {state_mean, state_scale, action_mean, action_scale,
+ * diff_mean, diff_scale} (DS:23-43), ignored when cfg.transform == 0. */
+int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host,
+                          const float* const* biases_host, const float* const* transforms_host);
+
+int simstep_set_termination(simstep_handle* h, const simstep_termination* t);
+
+/* Replaces the rff layer of RBFLinearCost (LC:53-55): weight_host [D,in_dim],
+ * bias_host [D].  in_dim must be S (input_type 's'), 2S ('ss'), S+A ('sa') or
+ * 2S+A ('sas').  split != 0 keeps ~21 mantissa bits of the pre-activation by
+ * running the GEMM on hi/lo operand pairs. */
+int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim,
+                     const float* weight_host, const float* bias_host, int32_t split);
+
+/* ---- ensemble forward --------------------------------------------------- */
+
+/* DynamicsModel.forward(state, action, unnormalize_out=True) for ALL members
+ * at once (DYN:216-233, DYN:422-433): delta_dev[m][e][:] is member m's
+ * predicted state difference, layout [N][E][S]. */
+int simstep_forward(simstep_handle* h, const float* state_dev, const float* action_dev, int64_t n_envs,
+                    float* delta_dev, void* stream);
+
+/* DynamicsEnsemble.compute_discrepancy (DYN:134-143): disc_dev[e] =
+ * max_{i<j} ||delta_i - delta_j||_2. */
+int simstep_discrepancy(simstep_handle* h, const float* state_dev, const float* action_dev, int64_t n_envs,
+                        float* disc_dev, void* stream);
+
+/* ---- the env step ------------------------------------------------------- */
+
+/* Batched SimEnv.step + is_done (SE:140-173) with the discrepancy of
+ * DYN:134-143 taken from the same forward pass.
+ *   member_dev[e]    active member of env e (SE:282-283), int32
+ *   num_steps_dev[e] step counter (SE:153), incremented in place, int32
+ *   next_state_dev   [E][S]; may alias state_dev (SE:158 is in place)
+ *   disc_dev         [E] or NULL
+ *   done_dev         [E] uint8 or NULL
+ */
+int simstep_step(simstep_handle* h, const float* state_dev, const float* action_dev, const int32_t* member_dev,
+                 int32_t* num_steps_dev, int64_t n_envs, float* next_state_dev, float* disc_dev, uint8_t* done_dev,
+                 void* stream);
+
+/* simstep_step followed by RBFLinearCost.get_bonus_costs (LC:111-152) on the
+ * same rows, input_type taken from simstep_load_rff:
+ *   w_dev [D]       cost weights (LC:91)
+ *   cost = (1-lambda_b)*clamp(phi.w, c_min, c_max) - lambda_b*min(disc/threshold,1)*c_min
+ *   cost_dev, ipm_dev, bonus_dev: [E] each, any may be NULL (bonus is the
+ *   weighted bonus, LC:144).  clamp_cost == 0 reproduces cost_range=None
+ *   (LC:137-138, LC:103). */
+int simstep_step_cost(simstep_handle* h, const float* state_dev, const float* action_dev,
+                      const int32_t* member_dev, int32_t* num_steps_dev, int64_t n_envs, float* next_state_dev,
+                      float* disc_dev, uint8_t* done_dev, const float* w_dev, float lambda_b, float threshold,
+                      float c_min, float c_max, int32_t clamp_cost, float* cost_dev, float* ipm_dev,
+                      float* bonus_dev, void* stream);
+
+/* ---- MILO cost on explicit rows ---------------------------------------- */
+
+/* RBFLinearCost.get_rep (LC:64-71): phi_dev [E][D] = cos(x W^T + b)*sqrt(2/D),
+ * x_dev [E][in_dim].  phi_sum_dev [D] (may be NULL) receives sum_e phi, the
+ * numerator of fit_cost's mean (LC:88). */
+int simstep_rff_features(simstep_handle* h, const float* x_dev, int64_t n_rows, float* phi_dev,
+                         double* phi_sum_dev, void* stream);
+
+/* RBFLinearCost.get_costs (LC:96-103) before the clamp: dot_dev[e] = phi(x_e).w */
+int simstep_rff_dot(simstep_handle* h, const float* x_dev, int64_t n_rows, const float* w_dev, float* dot_dev,
+                    void* stream);
+
+/* RBFLinearCost.get_bonus_costs (LC:111-152) given rows and their discrepancy. */
+int simstep_bonus_cost(simstep_handle* h, const float* x_dev, const float* disc_dev, int64_t n_rows,
+                       const float* w_dev, float lambda_b, float threshold, float c_min, float c_max,
+                       int32_t clamp_cost, float* cost_dev, float* ipm_dev, float* bonus_dev, void* stream);
+
+/* ---- DeepMimic imitation reward ----------------------------------------- */
+
+/* Articulated character of the reward (humanoid3d.txt Skeleton/BodyDefs):
+ * joints are topologically ordered, joint 0 is the root. */
+typedef struct simstep_character {
+  int32_t n_joints;
+  int32_t joint_type[SIMSTEP_MAX_JOINTS];   /* 0 root(none) 1 spherical 2 revolute 3 fixed */
+  int32_t parent[SIMSTEP_MAX_JOINTS];
+  float attach[SIMSTEP_MAX_JOINTS][3];      /* joint AttachX/Y/Z                */
+  int32_t param_offset[SIMSTEP_MAX_JOINTS]; /* offset in pose/vel (KT:1053-1062) */
+  int32_t is_end_eff[SIMSTEP_MAX_JOINTS];
+  float diff_weight[SIMSTEP_MAX_JOINTS];    /* DiffWeight (SI:300-312 normalises) */
+  float body_mass[SIMSTEP_MAX_JOINTS];
+  float body_attach[SIMSTEP_MAX_JOINTS][3]; /* BodyDefs AttachX/Y/Z             */
+  int32_t dof;                              /* pose/vel length, 43              */
+} simstep_character;
+
+/* Reference clip after cMotion::Load post-processing (Motion.cpp:356-442) and
+ * the first-frame centring of KinController.cpp:144-160: frames_host
+ * [n_frames][dof] poses, frame_vel_host [n_frames][dof] (Motion.cpp:170-191),
+ * frame_time_host [n_frames] start times, loop_wrap != 0 for "Loop":"wrap",
+ * cycle_delta = root translation of one cycle (KinController.cpp:162-175). */
+int simstep_load_clip(simstep_handle* h, const simstep_character* ch, int32_t n_frames,
+                      const float* frames_host, const float* frame_vel_host, const float* frame_time_host,
+                      float duration, int32_t loop_wrap, const float* cycle_delta_host);
+
+/* Batched cSceneImitate::CalcRewardImitate (SI:7-127) against the loaded clip.
+ *   pose_dev, vel_dev [E][dof]   simulated character (KT pose/vel layout)
+ *   kin_time_dev [E]             clip time of env e's kinematic character
+ *   kin_origin_dev [E][3] or NULL world offset of the kin character's origin
+ *   reward_dev [E]; terms_dev [E][5] (pose, vel, end_eff, root, com rewards) or NULL */
+int simstep_imitation_reward(simstep_handle* h, const float* pose_dev, const float* vel_dev,
+                             const float* kin_time_dev, const float* kin_origin_dev, int64_t n_envs,
+                             float* reward_dev, float* terms_dev, void* stream);
+
+/* cKinCharacter pose/vel at a clip time (KinCharacter.cpp:573-640 via
+ * Motion.cpp:267-305): out_pose_dev, out_vel_dev [E][dof]. */
+int simstep_clip_sample(simstep_handle* h, const float* kin_time_dev, const float* kin_origin_dev, int64_t n_envs,
+                        float* out_pose_dev, float* out_vel_dev, void* stream);
+
+/* ---- reductions used by the multi-GPU host code ------------------------- */
+
+/* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */
+int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, double* out_dev, void* stream);
+
+/* ---- debugging / unit tests -------------------------------------------- */
+
+/* One grouped GEMM through the production tcgen05 kernel:
+ * d[g][m][n] = sum_k a[g][m][k]*b[g][n][k] (+bias[g][n]) for g < groups,
+ * a_dev [groups][m][k], b_dev [groups][n][k], d_dev [groups][m][n] fp32.
+ * Operands are rounded to `precision` exactly as the ensemble path does. */
+int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, int32_t k, const float* a_dev,
+                       const float* b_dev, const float* bias_dev, float* d_dev, void* stream);
+
+/* Number of kernels this library has launched on the calling process. */
+int64_t simstep_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMSTEP_H_ */
