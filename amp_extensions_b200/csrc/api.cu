@@ -853,6 +853,10 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
                           cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         rc = fail(nullptr, SIMSTEP_ECUDA, "bias copy failed");
   }
+  if (!rc) {
+    cudaError_t pe = cudaStreamSynchronize(st);
+    if (pe != cudaSuccess) rc = fail(nullptr, SIMSTEP_ECUDA, std::string("debug gemm pack stage: ") + cudaGetErrorString(pe));
+  }
   CUtensorMap ta, tb;
   if (!rc) rc = encode_operand(h, &ta, precision, ap, k_pad, groups * m_pad, k_pad, kBlockM);
   if (!rc) rc = encode_operand(h, &tb, precision, bp, k_pad, groups * n_pad, k_pad, kBlockN);
