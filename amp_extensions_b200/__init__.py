@@ -11,3 +11,9 @@ Host-side mirror of the reference's plugin surface for this one hot path:
 All compute goes through libsimstep.so (include/simstep.h); there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from .datasets import AmpDataset  # noqa: F401
+from .dynamics import DynamicsEnsemble, DynamicsModel  # noqa: F401
+from .engine import Engine, HumanoidTermination  # noqa: F401
+from .linear_cost import RBFLinearCost  # noqa: F401
+from .sim_env import SimEnv, VecSimEnv  # noqa: F401

@@ -1,0 +1,277 @@
+"""Thin object wrapper over a libsimstep handle: device tensors in, device tensors out.
+
+torch is used for device memory and streams only; every computation is a call into the C ABI
+(include/simstep.h).  A missing library or GPU raises — nothing here computes on the CPU.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+DEFAULT_PRECISION = "fp16"
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_f32(x, device):
+    """Contiguous fp32 CUDA tensor (no copy when it already is one)."""
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(x)
+    return x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class HumanoidTermination:
+    """Fall-contact model of SimEnv (reference gym-simenv/gym_simenv/envs/sim_env.py:100-116, 164-268).
+
+    body_defs: list of dicts with 'Shape', 'Param0', 'Param1' (humanoid3d.txt BodyDefs) indexed by body id.
+    """
+
+    # humanoid3d.txt BodyDefs (shape, Param0, Param1), see SURVEY.md appendix B
+    HUMANOID3D = [
+        ("sphere", 0.18, 0.18), ("sphere", 0.22, 0.22), ("sphere", 0.205, 0.205), ("capsule", 0.11, 0.30),
+        ("capsule", 0.10, 0.31), ("box", 0.177, 0.055), ("capsule", 0.09, 0.18), ("capsule", 0.08, 0.135),
+        ("sphere", 0.08, 0.08), ("capsule", 0.11, 0.30), ("capsule", 0.10, 0.31), ("box", 0.177, 0.055),
+        ("capsule", 0.09, 0.18), ("capsule", 0.08, 0.135), ("sphere", 0.08, 0.08),
+    ]
+    FALL_CONTACT_BODIES = (0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 12, 13, 14)
+
+    def __init__(self, horizon=300, enable_velocity_check=False, body_defs=None, fall_contact_bodies=None,
+                 pos_dim=3, rot_dim=6, vel_offset=136, vel_threshold=100.0, vel_divisor=1.0,
+                 record_all_world=False, record_world_root_pos=False):
+        self.horizon = int(horizon)
+        self.enable_velocity_check = bool(enable_velocity_check)
+        self.body_defs = list(body_defs) if body_defs is not None else list(self.HUMANOID3D)
+        self.fall_contact_bodies = tuple(fall_contact_bodies if fall_contact_bodies is not None
+                                         else self.FALL_CONTACT_BODIES)
+        self.pos_dim, self.rot_dim = int(pos_dim), int(rot_dim)
+        self.vel_offset = int(vel_offset)
+        self.vel_threshold = float(vel_threshold)
+        self.vel_divisor = float(vel_divisor)
+        self.record_all_world = bool(record_all_world)
+        self.record_world_root_pos = bool(record_world_root_pos)
+
+    def to_struct(self):
+        t = _lib.SimstepTermination()
+        t.horizon = self.horizon
+        t.enable_velocity_check = int(self.enable_velocity_check)
+        t.vel_offset = self.vel_offset
+        t.vel_threshold = self.vel_threshold
+        t.vel_divisor = self.vel_divisor
+        t.record_all_world = int(self.record_all_world)
+        t.record_world_root_pos = int(self.record_world_root_pos)
+        t.n_bodies = len(self.fall_contact_bodies)
+        t.pos_dim = self.pos_dim
+        for i, b in enumerate(self.fall_contact_bodies):
+            d = self.body_defs[b]
+            if isinstance(d, dict):
+                shape, p0, p1 = d["Shape"], d["Param0"], d["Param1"]
+            else:
+                shape, p0, p1 = d
+            t.body_offset[i] = (self.pos_dim + self.rot_dim) * b + 1
+            t.body_shape[i] = _lib.SHAPE.get(shape, _lib.SHAPE["box"])
+            t.body_param0[i] = float(p0)
+            t.body_param1[i] = float(p1)
+        return t
+
+
+class Engine:
+    """One libsimstep handle on one CUDA device."""
+
+    def __init__(self, state_dim, action_dim, num_models, hidden_sizes, dense_connect=True, activation="relu",
+                 transform=True, precision=None, device=None, max_chunk_envs=0):
+        if not torch.cuda.is_available():
+            raise _lib.SimstepError("amp_extensions_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _lib.SimstepError(f"device must be a CUDA device, got {self.device}")
+        self.S, self.A, self.N = int(state_dim), int(action_dim), int(num_models)
+        self.hidden = [int(h) for h in hidden_sizes]
+        self.precision = precision or DEFAULT_PRECISION
+        cfg = _lib.SimstepConfig()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.state_dim, cfg.action_dim, cfg.n_models, cfg.n_hidden = self.S, self.A, self.N, len(self.hidden)
+        for i, h in enumerate(self.hidden):
+            cfg.hidden[i] = h
+        cfg.dense_connect = int(bool(dense_connect))
+        cfg.activation = _lib.ACT[activation if activation in _lib.ACT else "tanh"]
+        cfg.transform = int(bool(transform))
+        cfg.precision = _lib.PREC[self.precision]
+        cfg.max_chunk_envs = int(max_chunk_envs)
+        self.transform = bool(transform)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.simstep_create(C.byref(cfg), C.byref(self._h)))
+        self.rff_dim = 0
+        self.rff_in = 0
+
+    # -- lifetime -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.simstep_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(rc, self._h)
+
+    # -- parameters ---------------------------------------------------------------------
+    def load_ensemble(self, weights, biases, transforms=None):
+        """weights[m][l], biases[m][l]: CPU fp32 tensors in nn.Linear layout; transforms: 6 vectors or None."""
+        nl = len(self.hidden) + 1
+        keep = []
+        wp = (C.c_void_p * (self.N * nl))()
+        bp = (C.c_void_p * (self.N * nl))()
+        for m in range(self.N):
+            for l in range(nl):
+                w = weights[m][l].detach().to("cpu", torch.float32).contiguous()
+                b = biases[m][l].detach().to("cpu", torch.float32).contiguous()
+                keep += [w, b]
+                wp[m * nl + l] = w.data_ptr()
+                bp[m * nl + l] = b.data_ptr()
+        tp = None
+        if self.transform:
+            if transforms is None:
+                raise ValueError("transform=True needs the six transformation vectors")
+            tfs = [t.detach().to("cpu", torch.float32).contiguous() for t in transforms]
+            keep += tfs
+            tp = (C.c_void_p * 6)(*[t.data_ptr() for t in tfs])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_load_ensemble(self._h, wp, bp, tp))
+
+    def set_termination(self, term):
+        t = term.to_struct()
+        self._check(self.lib.simstep_set_termination(self._h, C.byref(t)))
+
+    def load_rff(self, weight, bias, split=True):
+        w = weight.detach().to("cpu", torch.float32).contiguous()
+        b = bias.detach().to("cpu", torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_load_rff(self._h, w.shape[0], w.shape[1], _ptr(w), _ptr(b), int(bool(split))))
+        self.rff_dim, self.rff_in = int(w.shape[0]), int(w.shape[1])
+
+    # -- ensemble -----------------------------------------------------------------------
+    def forward(self, state, action):
+        """All members' un-normalised predictions, CUDA tensor [N, E, S]."""
+        s, a = _dev_f32(state, self.device), _dev_f32(action, self.device)
+        E = s.shape[0]
+        out = torch.empty((self.N, E, self.S), device=self.device, dtype=torch.float32)
+        self._check(self.lib.simstep_forward(self._h, _ptr(s), _ptr(a), E, _ptr(out), _stream(self.device)))
+        return out
+
+    def discrepancy(self, state, action):
+        s, a = _dev_f32(state, self.device), _dev_f32(action, self.device)
+        E = s.shape[0]
+        out = torch.empty((E,), device=self.device, dtype=torch.float32)
+        self._check(self.lib.simstep_discrepancy(self._h, _ptr(s), _ptr(a), E, _ptr(out), _stream(self.device)))
+        return out
+
+    def step(self, state, action, member, num_steps, next_state=None, disc=None, done=None, want_disc=True,
+             want_done=True):
+        """In-place batched env step on device tensors. Returns (next_state, disc, done)."""
+        E = state.shape[0]
+        if next_state is None:
+            next_state = torch.empty_like(state)
+        if disc is None and want_disc:
+            disc = torch.empty((E,), device=self.device, dtype=torch.float32)
+        if done is None and want_done:
+            done = torch.empty((E,), device=self.device, dtype=torch.uint8)
+        self._check(self.lib.simstep_step(self._h, _ptr(state), _ptr(action), _ptr(member), _ptr(num_steps), E,
+                                          _ptr(next_state), _ptr(disc), _ptr(done), _stream(self.device)))
+        return next_state, disc, done
+
+    def step_cost(self, state, action, member, num_steps, w, lambda_b, threshold, c_min=-1.0, c_max=0.0,
+                  clamp_cost=True, next_state=None, disc=None, done=None, cost=None, ipm=None, bonus=None):
+        E = state.shape[0]
+        f32 = dict(device=self.device, dtype=torch.float32)
+        next_state = torch.empty_like(state) if next_state is None else next_state
+        disc = torch.empty((E,), **f32) if disc is None else disc
+        done = torch.empty((E,), device=self.device, dtype=torch.uint8) if done is None else done
+        cost = torch.empty((E,), **f32) if cost is None else cost
+        ipm = torch.empty((E,), **f32) if ipm is None else ipm
+        bonus = torch.empty((E,), **f32) if bonus is None else bonus
+        self._check(self.lib.simstep_step_cost(
+            self._h, _ptr(state), _ptr(action), _ptr(member), _ptr(num_steps), E, _ptr(next_state), _ptr(disc),
+            _ptr(done), _ptr(w), float(lambda_b), float(threshold), float(c_min), float(c_max), int(bool(clamp_cost)),
+            _ptr(cost), _ptr(ipm), _ptr(bonus), _stream(self.device)))
+        return next_state, disc, done, cost, ipm, bonus
+
+    # -- cost ---------------------------------------------------------------------------
+    def rff_features(self, x, want_sum=False):
+        x = _dev_f32(x, self.device)
+        n = x.shape[0]
+        phi = torch.empty((n, self.rff_dim), device=self.device, dtype=torch.float32)
+        psum = torch.empty((self.rff_dim,), device=self.device, dtype=torch.float64) if want_sum else None
+        self._check(self.lib.simstep_rff_features(self._h, _ptr(x), n, _ptr(phi), _ptr(psum), _stream(self.device)))
+        return (phi, psum) if want_sum else phi
+
+    def rff_dot(self, x, w):
+        x, w = _dev_f32(x, self.device), _dev_f32(w, self.device)
+        n = x.shape[0]
+        out = torch.empty((n,), device=self.device, dtype=torch.float32)
+        self._check(self.lib.simstep_rff_dot(self._h, _ptr(x), n, _ptr(w), _ptr(out), _stream(self.device)))
+        return out
+
+    def bonus_cost(self, x, disc, w, lambda_b, threshold, c_min=-1.0, c_max=0.0, clamp_cost=True):
+        x, w, disc = _dev_f32(x, self.device), _dev_f32(w, self.device), _dev_f32(disc, self.device)
+        n = x.shape[0]
+        cost, ipm, bonus = (torch.empty((n,), device=self.device, dtype=torch.float32) for _ in range(3))
+        self._check(self.lib.simstep_bonus_cost(self._h, _ptr(x), _ptr(disc), n, _ptr(w), float(lambda_b),
+                                                float(threshold), float(c_min), float(c_max), int(bool(clamp_cost)),
+                                                _ptr(cost), _ptr(ipm), _ptr(bonus), _stream(self.device)))
+        return cost, ipm, bonus
+
+    def reduce_max_sum(self, x):
+        x = _dev_f32(x, self.device)
+        out = torch.empty((2,), device=self.device, dtype=torch.float64)
+        self._check(self.lib.simstep_reduce_max_sum(self._h, _ptr(x), x.numel(), _ptr(out), _stream(self.device)))
+        return out
+
+    # -- imitation reward ---------------------------------------------------------------
+    def load_clip(self, character, clip):
+        ch = character.to_struct()
+        fr = torch.as_tensor(clip.frames, dtype=torch.float32).contiguous()
+        fv = torch.as_tensor(clip.frame_vels, dtype=torch.float32).contiguous()
+        ft = torch.as_tensor(clip.frame_times, dtype=torch.float32).contiguous()
+        cd = torch.as_tensor(clip.cycle_delta, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_load_clip(self._h, C.byref(ch), fr.shape[0], _ptr(fr), _ptr(fv), _ptr(ft),
+                                                   float(clip.duration), int(bool(clip.loop_wrap)), _ptr(cd)))
+        self.dof = int(fr.shape[1])
+
+    def imitation_reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False):
+        pose, vel = _dev_f32(pose, self.device), _dev_f32(vel, self.device)
+        kin_time = _dev_f32(kin_time, self.device)
+        kin_origin = _dev_f32(kin_origin, self.device) if kin_origin is not None else None
+        E = pose.shape[0]
+        reward = torch.empty((E,), device=self.device, dtype=torch.float32)
+        terms = torch.empty((E, 5), device=self.device, dtype=torch.float32) if want_terms else None
+        self._check(self.lib.simstep_imitation_reward(self._h, _ptr(pose), _ptr(vel), _ptr(kin_time),
+                                                      _ptr(kin_origin), E, _ptr(reward), _ptr(terms),
+                                                      _stream(self.device)))
+        return (reward, terms) if want_terms else reward
+
+    def clip_sample(self, kin_time, kin_origin=None):
+        kin_time = _dev_f32(kin_time, self.device)
+        kin_origin = _dev_f32(kin_origin, self.device) if kin_origin is not None else None
+        E = kin_time.shape[0]
+        pose = torch.empty((E, self.dof), device=self.device, dtype=torch.float32)
+        vel = torch.empty((E, self.dof), device=self.device, dtype=torch.float32)
+        self._check(self.lib.simstep_clip_sample(self._h, _ptr(kin_time), _ptr(kin_origin), E, _ptr(pose), _ptr(vel),
+                                                 _stream(self.device)))
+        return pose, vel

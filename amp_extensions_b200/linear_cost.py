@@ -1,0 +1,121 @@
+"""MILO's IPM / random-Fourier-feature cost with the reference's surface, evaluated on B200.
+
+Mirrors reference milo/milo/linear_cost.py:6-152 (RBFLinearCost): same constructor arguments, the same
+host-side RNG consumption (so bandwidth, rff weights and bias are bit-identical to the reference's for a
+given seed and torch build), same return shapes (CPU tensors [B,1], info dict keys).  Feature
+evaluation, the cost dot product and the bonus combine run through libsimstep's tcgen05 GEMM.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+
+
+class RBFLinearCost:
+    def __init__(self, expert_data, feature_dim=1024, input_type="ss", cost_range=[-1.0, 0.0], bw_quantile=0.1,
+                 bw_samples=100000, lambda_b=1.0, lr=0.0, seed=100, precision=None, device=None, split=True):
+        torch.manual_seed(seed)  # linear_cost.py:33-35
+        np.random.seed(seed)
+        self.expert_data = expert_data
+        input_dim = expert_data.size(1)
+        self.input_type = input_type
+        self.feature_dim = feature_dim
+        self.cost_range = cost_range
+        if cost_range is not None:
+            self.c_min, self.c_max = cost_range
+        self.lambda_b = lambda_b
+        self.lr = lr
+        self.quantile = bw_quantile
+        self.bw_samples = bw_samples
+        self._precision = precision
+        self._device = device
+        self._split = split
+        self._eng = None
+        self.bw = self.fit_bandwidth(expert_data)
+        # linear_cost.py:53-55 (the nn.Linear default init consumes RNG before rand_like, as in the reference)
+        self.rff = nn.Linear(input_dim, feature_dim)
+        self.rff.bias.data = (torch.rand_like(self.rff.bias.data) - 0.5) * 2.0 * np.pi
+        self.rff.weight.data = torch.rand_like(self.rff.weight.data) / (self.bw + 1e-8)
+        self.w = None
+        self.expert_rep = self.get_rep(expert_data)  # linear_cost.py:61-62
+        self.phi_e = self.expert_rep.mean(dim=0)
+
+    # -- host-side fitting (same arithmetic and RNG stream as the reference) --------------------
+    def fit_bandwidth(self, data):
+        """linear_cost.py:73-82: quantile of the distance between random pairs."""
+        num_data = data.shape[0]
+        idxs_0 = torch.randint(low=0, high=num_data, size=(self.bw_samples,))
+        idxs_1 = torch.randint(low=0, high=num_data, size=(self.bw_samples,))
+        norm = torch.norm(data[idxs_0, :] - data[idxs_1, :], dim=1)
+        return torch.quantile(norm, q=self.quantile).item()
+
+    # -- device side --------------------------------------------------------------------------
+    def engine(self):
+        if self._eng is None:
+            d = self.rff.weight.shape[1]
+            self._eng = _engine.Engine(state_dim=d, action_dim=0, num_models=1, hidden_sizes=[], dense_connect=True,
+                                       transform=False, precision=self._precision, device=self._device)
+            self._rff_stamp = None
+        stamp = (self.rff.weight._version, self.rff.bias._version, id(self.rff.weight.data), id(self.rff.bias.data))
+        if stamp != self._rff_stamp:
+            self._eng.load_rff(self.rff.weight.data, self.rff.bias.data, split=self._split)
+            self._rff_stamp = stamp
+        return self._eng
+
+    def get_rep(self, x):
+        """linear_cost.py:64-71: cos(rff(x)) * sqrt(2/D), returned on the CPU like the reference."""
+        with torch.no_grad():
+            return self.engine().rff_features(x).cpu()
+
+    def fit_cost(self, data_pi):
+        """linear_cost.py:84-94: w = mean phi(pi) - mean phi(expert); returns w.w."""
+        _, psum = self.engine().rff_features(data_pi, want_sum=True)
+        phi = (psum / max(int(data_pi.shape[0]), 1)).float().cpu()
+        feat_diff = phi - self.phi_e
+        self.w = feat_diff
+        return torch.dot(self.w, feat_diff).item()
+
+    def get_costs(self, x):
+        """linear_cost.py:96-103."""
+        dot = self.engine().rff_dot(x, self.w).cpu().unsqueeze(1)
+        if self.cost_range is not None:
+            return torch.clamp(dot, self.c_min, self.c_max)
+        return dot
+
+    def get_expert_cost(self):
+        """linear_cost.py:105-109."""
+        return (1 - self.lambda_b) * torch.clamp(torch.mm(self.expert_rep, self.w.unsqueeze(1)), self.c_min,
+                                                 self.c_max).mean()
+
+    def rff_input(self, states, actions, next_states=None):
+        """linear_cost.py:115-126."""
+        if self.input_type == "sa":
+            return torch.cat([states, actions], dim=1)
+        if self.input_type == "ss":
+            assert next_states is not None
+            return torch.cat([states, next_states], dim=1)
+        if self.input_type == "sas":
+            return torch.cat([states, actions, next_states], dim=1)
+        if self.input_type == "s":
+            return states
+        raise NotImplementedError("Input type not implemented")
+
+    def get_bonus_costs(self, states, actions, ensemble, next_states=None):
+        """linear_cost.py:111-152. `ensemble` needs get_action_discrepancy(states, actions) and .threshold."""
+        eng = self.engine()
+        rff_in = self.rff_input(states.float(), actions.float(), None if next_states is None else next_states.float())
+        disc = ensemble.get_action_discrepancy(states, actions)
+        clamp = self.cost_range is not None
+        c_min, c_max = (self.c_min, self.c_max) if clamp else (0.0, 0.0)
+        cost, ipm, bonus = eng.bonus_cost(rff_in, disc, self.w, self.lambda_b, ensemble.threshold if clamp else 1.0,
+                                          c_min, c_max, clamp)
+        cost, ipm, bonus = cost.cpu().unsqueeze(1), ipm.cpu().unsqueeze(1), bonus.cpu().unsqueeze(1)
+        v_targ = ipm / (1 - self.lambda_b) if self.lambda_b != 1 else self.get_costs(rff_in)
+        info = {"bonus": bonus, "ipm": ipm, "v_targ": v_targ, "cost": cost}
+        return cost, info
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_eng"] = None
+        return d

@@ -1,0 +1,81 @@
+"""Shared fixtures: golden vectors and seeded synthetic inputs."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "milo_golden.npz")
+_cache = {}
+
+
+def golden():
+    if "g" not in _cache:
+        _cache["g"] = np.load(GOLDEN, allow_pickle=False)
+    return _cache["g"]
+
+
+def t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def tiny_case(tag):
+    """Returns dict with dims, weights/biases per member, transforms, inputs and the reference outputs."""
+    g = golden()
+    dims = g[f"{tag}/dims"].tolist()
+    S, A, N, dense = dims[:4]
+    hidden = dims[4:]
+    nl = len(hidden) + 1
+    ws = [[t(g[f"{tag}/m{k}/fc_layers.{l}.weight"]) for l in range(nl)] for k in range(N)]
+    bs = [[t(g[f"{tag}/m{k}/fc_layers.{l}.bias"]) for l in range(nl)] for k in range(N)]
+    tf = tuple(t(g[f"{tag}/tf{i}"]) for i in range(6))
+    return dict(S=S, A=A, N=N, dense=bool(dense), hidden=hidden, act=str(g[f"{tag}/act"]), ws=ws, bs=bs, tf=tf,
+                xs=t(g[f"{tag}/xs"]), xa=t(g[f"{tag}/xa"]), preds=t(g[f"{tag}/preds"]),
+                preds_norm=t(g[f"{tag}/preds_norm"]), disc=t(g[f"{tag}/disc"]), threshold=float(g[f"{tag}/threshold"]),
+                ds=(t(g[f"{tag}/ds_s"]), t(g[f"{tag}/ds_a"]), t(g[f"{tag}/ds_s2"])))
+
+
+def synth_dataset(M, S, A, seed):
+    """Same generator as tests/golden/make_golden.py::synth_dataset."""
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(M, S, generator=g)
+    a = torch.randn(M, A, generator=g)
+    s2 = s + 0.05 * torch.randn(M, S, generator=g)
+    return s, a, s2
+
+
+def ns_case():
+    """North-star ensemble: weights regenerated from the seed by the oracle, pinned by stored checksums."""
+    if "ns" in _cache:
+        return _cache["ns"]
+    from oracle import milo_oracle as mo
+    g = golden()
+    S, A, N = 226, 28, 4
+    hidden = [512] * 4
+    ws, bs = mo.init_ensemble(S, A, hidden, N, dense_connect=True, base_seed=100)
+    tf = tuple(t(g[f"ns/tf{i}"]) for i in range(6))
+    case = dict(S=S, A=A, N=N, dense=True, hidden=hidden, act="relu", ws=ws, bs=bs, tf=tf, xs=t(g["ns/xs"]),
+                xa=t(g["ns/xa"]), preds=t(g["ns/preds"]), disc=t(g["ns/disc"]), threshold=float(g["ns/threshold"]),
+                threshold_rows=int(g["ns/threshold_rows"]), wsum=g["ns/wsum"], wabs=g["ns/wabs"])
+    _cache["ns"] = case
+    return case
+
+
+def ns_expert():
+    g = torch.Generator().manual_seed(2)
+    es = torch.randn(256, 226, generator=g)
+    return torch.cat([es, es + 0.05 * torch.randn(256, 226, generator=g)], dim=1)
+
+
+def humanoid_like_states(E, seed, fall_fraction=0.3):
+    """States in the 226-d humanoid3d layout whose collision test has both outcomes: root height in
+    s[0], body positions (relative to root) at 9b+1.., rotation normal at 9b+4.., velocities from 136."""
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(E, 226, generator=g) * 0.3
+    s[:, 0] = 0.7 + 0.4 * torch.rand(E, generator=g)
+    for b in range(15):
+        s[:, 9 * b + 2] = (torch.rand(E, generator=g) - 0.5) * 0.8  # relative y of body b
+        s[:, 9 * b + 5] = torch.rand(E, generator=g) * 2 - 1        # normal.y
+    low = torch.rand(E, generator=g) < fall_fraction
+    s[low, 0] = 0.05 + 0.3 * torch.rand(int(low.sum()), generator=g)
+    s[:, 136:] = torch.randn(E, 90, generator=g) * 3.0
+    return s

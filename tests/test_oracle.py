@@ -1,0 +1,132 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference's own code."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import milo_oracle as mo
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("tag", ["tiny_dense", "tiny_plain_tanh"])
+def test_forward_and_discrepancy_match_reference(tag):
+    c = H.tiny_case(tag)
+    preds = mo.ensemble_forward(c["ws"], c["bs"], c["tf"], c["xs"], c["xa"], c["dense"], c["act"])
+    assert torch.equal(preds, c["preds"])  # same ops, same order: bit-exact
+    pn = torch.stack([mo.dynamics_forward(w, b, c["tf"], c["xs"], c["xa"], c["dense"], c["act"], unnormalize_out=False)
+                      for w, b in zip(c["ws"], c["bs"])])
+    assert torch.equal(pn, c["preds_norm"])
+    assert torch.equal(mo.discrepancy_from_preds(preds), c["disc"])
+
+
+@pytest.mark.parametrize("tag", ["tiny_dense", "tiny_plain_tanh"])
+def test_transformations_and_threshold_match_reference(tag):
+    c = H.tiny_case(tag)
+    tf = mo.get_transformations(*c["ds"])
+    for a, b in zip(tf, c["tf"]):
+        assert torch.equal(a, b)
+    thr = mo.compute_threshold(c["ws"], c["bs"], c["tf"], c["ds"][0], c["ds"][1], 256, c["dense"]) \
+        if c["act"] == "relu" else None
+    if thr is not None:
+        assert thr == pytest.approx(c["threshold"], rel=1e-6)
+
+
+def test_layer_shapes_of_north_star_config():
+    fan_in, fan_out = mo.layer_input_sizes(254, 226, [512] * 4, True)
+    assert fan_in == [254, 766, 1278, 1790, 2302]  # SURVEY.md section 0, dynamics.py:412-420
+    assert fan_out == [512, 512, 512, 512, 226]
+    fan_in, _ = mo.layer_input_sizes(254, 226, [1024] * 4, True)
+    assert fan_in == [254, 1278, 2302, 3326, 4350]
+
+
+def test_north_star_init_is_the_reference_init():
+    c = H.ns_case()
+    for k in range(c["N"]):
+        flat = [x for pair in zip(c["ws"][k], c["bs"][k]) for x in pair]
+        np.testing.assert_allclose([float(v.double().sum()) for v in flat], c["wsum"][k], rtol=0, atol=1e-9)
+        np.testing.assert_allclose([float(v.double().abs().sum()) for v in flat], c["wabs"][k], rtol=1e-12)
+
+
+def test_north_star_forward_matches_reference():
+    c = H.ns_case()
+    preds = mo.ensemble_forward(c["ws"], c["bs"], c["tf"], c["xs"], c["xa"])
+    assert torch.equal(preds, c["preds"])
+    assert torch.equal(mo.discrepancy_from_preds(preds), c["disc"])
+    s, a, _ = H.synth_dataset(8192, 226, 28, 0)
+    n = c["threshold_rows"]
+    assert mo.compute_threshold(c["ws"], c["bs"], c["tf"], s[:n], a[:n]) == pytest.approx(c["threshold"], rel=1e-6)
+
+
+@pytest.mark.parametrize("tag,D", [("cost64", 64), ("cost512", 512)])
+def test_rff_cost_matches_reference(tag, D):
+    g = H.golden()
+    c = H.ns_case()
+    expert = H.ns_expert()
+    if tag == "cost64":
+        assert torch.equal(expert, H.t(g["cost64/expert"]))
+    cost = mo.RffCostOracle(expert, feature_dim=D, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100)
+    assert cost.bw == pytest.approx(float(g[f"{tag}/bw"]), rel=0, abs=0)
+    if D == 64:
+        assert torch.equal(cost.rff_weight, H.t(g["cost64/rff_w"]))
+        assert torch.equal(cost.rff_bias, H.t(g["cost64/rff_b"]))
+    assert torch.equal(cost.phi_e, H.t(g[f"{tag}/phi_e"]))
+    nxt = H.t(g[f"{tag}/next"])
+    pi = torch.cat([c["xs"], nxt], dim=1)
+    assert torch.equal(cost.get_rep(pi), H.t(g[f"{tag}/rep"]))
+    assert cost.fit_cost(pi) == pytest.approx(float(g[f"{tag}/mmd"]), rel=1e-7)
+    assert torch.equal(cost.w, H.t(g[f"{tag}/w"]))
+    assert torch.equal(cost.get_costs(pi), H.t(g[f"{tag}/costs"]))
+    assert float(cost.get_expert_cost()) == pytest.approx(float(g[f"{tag}/expert_cost"]), rel=1e-7)
+    total, info = cost.get_bonus_costs(c["xs"], c["xa"], c["disc"], c["threshold"], next_states=nxt)
+    assert torch.equal(total, H.t(g[f"{tag}/total"]))
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        assert torch.equal(info[k], H.t(g[f"{tag}/info_{k}"]))
+
+
+# ---- SimEnv restatement: no reference vectors exist (gym + SWIG simulator), hand-built known answers ----
+
+def _standing_state():
+    s = np.zeros((1, 226))
+    s[0, 0] = 0.9          # root height
+    for b in range(15):
+        s[0, 9 * b + 5] = 1.0  # normals point up
+    return s
+
+
+def test_simenv_no_collision_when_standing():
+    s = _standing_state()
+    assert not mo.simenv_collided(s)[0]
+
+
+def test_simenv_sphere_threshold_is_radius_plus_1e_4():
+    # neck (body 2, diameter 0.205): world y = s[0] + s[9*2+2]; sim_env.py:188-189
+    for dy, want in ((0.1025 + 0.0001 + 1e-6, False), (0.1025 + 0.0001 - 1e-6, True)):
+        s = _standing_state()
+        s[0, 9 * 2 + 2] = dy - s[0, 0]
+        assert bool(mo.simenv_collided(s)[0]) is want
+
+
+def test_simenv_capsule_uses_both_end_caps():
+    # right knee (body 4: diameter .10, height .31): centre at y=0.2, tilted so that one cap reaches the ground
+    s = _standing_state()
+    s[0, 9 * 4 + 2] = 0.2 - s[0, 0]
+    s[0, 9 * 4 + 5] = 0.5
+    assert not mo.simenv_collided(s)[0]           # 0.2 - 0.155*0.5 = 0.1225 > 0.0501
+    s[0, 9 * 4 + 5] = -1.0
+    assert mo.simenv_collided(s)[0]               # 0.2 - 0.155 = 0.045 <= 0.0501 (top cap, normal flipped)
+    # ankles (bodies 5, 11) are boxes and never count (sim_env.py:238-244)
+    s = _standing_state()
+    s[0, 9 * 5 + 2] = -5.0
+    assert not mo.simenv_collided(s)[0]
+
+
+def test_simenv_step_horizon_and_velocity():
+    s = _standing_state()
+    nxt, steps, done = mo.simenv_step(s, np.zeros((1, 226), np.float32), np.array([298]))
+    assert steps[0] == 299 and not done[0]
+    nxt, steps, done = mo.simenv_step(s, np.zeros((1, 226), np.float32), np.array([299]))
+    assert done[0]
+    d = np.zeros((1, 226), np.float32)
+    d[0, 200] = 101.0
+    assert not mo.simenv_step(s, d, np.array([0]))[2][0]
+    assert mo.simenv_step(s, d, np.array([0]), enable_velocity_check=True)[2][0]
+    assert nxt.dtype == np.float64

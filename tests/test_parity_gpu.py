@@ -1,0 +1,326 @@
+"""GPU parity of the CUDA path (through the C ABI) against the reference's golden vectors and the oracle.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative for next-state and reward against the fp32 reference,
+tensor-core operands with >= 10 mantissa bits (tf32 or fp16) and fp32 accumulation.  "Relative" is taken
+per element against max(|ref|, scale) where scale is the typical magnitude of that output (element-wise
+relative error is ill-posed at zero crossings); each test states its scale.  Termination masks must be
+identical except for rows whose margin to a threshold is inside that tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import milo_oracle as mo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3
+PRECISIONS = ["tf32", "fp16"]
+
+
+def assert_close(x, ref, scale, rel=REL, what=""):
+    x, ref = x.detach().double().cpu(), ref.detach().double().cpu()
+    tol = rel * torch.maximum(ref.abs(), torch.as_tensor(scale, dtype=torch.float64).expand_as(ref))
+    bad = (x - ref).abs() > tol
+    assert torch.isfinite(x).all(), f"{what}: non-finite output"
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.numel()} outside {rel:g} relative; worst abs err "
+                           f"{float((x - ref).abs().max()):.3e} at ref {float(ref.flatten()[(x - ref).abs().argmax()]):.3e}")
+
+
+def make_engine(case, precision, **kw):
+    from amp_extensions_b200.engine import Engine
+    eng = Engine(case["S"], case["A"], case["N"], case["hidden"], dense_connect=case["dense"],
+                 activation=case["act"], transform=True, precision=precision, **kw)
+    eng.load_ensemble(case["ws"], case["bs"], case["tf"])
+    return eng
+
+
+# ---------------------------------------------------------------------------------------------------
+# the GEMM kernel alone
+
+@pytest.mark.parametrize("prec", ["tf32", "fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 1, 8, 8), (1, 128, 256, 64), (2, 129, 257, 100), (4, 1000, 226, 2302),
+                                   (3, 5000, 512, 1278)])
+def test_debug_gemm_matches_fp64(prec, shape):
+    from amp_extensions_b200 import _lib
+    lib = _lib.load()
+    groups, m, n, k = shape
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    a = torch.randn(groups, m, k, device="cuda", generator=g)
+    b = torch.randn(groups, n, k, device="cuda", generator=g) / k ** 0.5
+    bias = torch.randn(groups, n, device="cuda", generator=g)
+    d = torch.full((groups, m, n), float("nan"), device="cuda")
+    rc = lib.simstep_debug_gemm(_lib.PREC[prec], groups, m, n, k, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                C.c_void_p(bias.data_ptr()), C.c_void_p(d.data_ptr()), None)
+    _lib.check(rc)
+
+    def rnd(x):
+        if prec == "tf32":
+            return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        return x.half().float() if prec == "fp16" else x.bfloat16().float()
+
+    ref = torch.einsum("gmk,gnk->gmn", rnd(a).double(), rnd(b).double()) + bias.double()[:, None, :]
+    # operands are rounded identically on both sides, so only the fp32 accumulation order differs
+    assert (d.double() - ref).abs().max().item() <= 3e-5 * max(1.0, (k / 256) ** 0.5) * ref.abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# ensemble forward / discrepancy against the reference's own outputs
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("tag", ["tiny_dense", "tiny_plain_tanh"])
+def test_tiny_forward_matches_reference(tag, prec):
+    c = H.tiny_case(tag)
+    eng = make_engine(c, prec)
+    preds = eng.forward(c["xs"], c["xa"])
+    scale = c["tf"][5].abs().max().item()  # diff_scale: the unit the network's output is expressed in
+    assert_close(preds, c["preds"], scale, what="delta")
+    disc = eng.discrepancy(c["xs"], c["xa"])
+    assert_close(disc, c["disc"], c["disc"].mean().item(), what="disc")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_north_star_forward_matches_reference(prec):
+    c = H.ns_case()
+    eng = make_engine(c, prec)
+    preds = eng.forward(c["xs"], c["xa"])
+    assert_close(preds, c["preds"], c["tf"][5].abs().max().item(), what="delta")
+    rel_l2 = ((preds.cpu() - c["preds"]).norm() / c["preds"].norm()).item()
+    assert rel_l2 < REL
+    assert_close(eng.discrepancy(c["xs"], c["xa"]), c["disc"], c["disc"].mean().item(), what="disc")
+
+
+def test_bf16_operands_miss_the_tolerance_budget():
+    """Why the default operand format is fp16 and not bf16: measured, not assumed."""
+    c = H.ns_case()
+    e16, eb = make_engine(c, "fp16"), make_engine(c, "bf16")
+    err16 = ((e16.forward(c["xs"], c["xa"]).cpu() - c["preds"]).norm() / c["preds"].norm()).item()
+    errb = ((eb.forward(c["xs"], c["xa"]).cpu() - c["preds"]).norm() / c["preds"].norm()).item()
+    assert err16 < REL and errb > 3 * err16
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_threshold_matches_reference(prec):
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble
+    c = H.ns_case()
+    s, a, s2 = H.synth_dataset(8192, 226, 28, 0)
+    n = c["threshold_rows"]
+    full = AmpDataset(s, a, s2)
+    ens = DynamicsEnsemble(226, 28, full, None, num_models=4, hidden_sizes=[512] * 4, dense_connect=True,
+                           transform=True, base_seed=100, precision=prec)
+    for tf_mine, tf_ref in zip(ens.transformations, c["tf"]):
+        assert torch.equal(tf_mine, tf_ref)
+    for k in range(4):  # same seed, same init order as the reference (dynamics.py:184-196)
+        for l, lin in enumerate(ens.models[k].model.fc_layers):
+            assert torch.equal(lin.weight.data, c["ws"][k][l]) and torch.equal(lin.bias.data, c["bs"][k][l])
+    ens.train_dataset = AmpDataset(s[:n], a[:n], s2[:n])
+    ens.compute_threshold()
+    assert ens.threshold == pytest.approx(c["threshold"], rel=REL)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the env step: next state, discrepancy, termination, counters
+
+def oracle_step(c, s, a, member, steps, **kw):
+    preds = mo.ensemble_forward(c["ws"], c["bs"], c["tf"], s, a, c["dense"], c["act"])
+    active = preds[member.long(), torch.arange(s.shape[0])]
+    nxt, st, done = mo.simenv_step(s.double().numpy(), active.numpy(), steps.numpy(), **kw)
+    return preds, torch.from_numpy(nxt), torch.from_numpy(st), torch.from_numpy(done), mo.discrepancy_from_preds(preds)
+
+
+def collision_margin(ob):
+    """Smallest distance of any tested quantity to its threshold (sim_env.py:188, 236), per row."""
+    ob = np.asarray(ob, dtype=np.float64)
+    m = np.full(ob.shape[0], np.inf)
+    for body in mo.HUMANOID3D_FALL_BODIES:
+        shape, p0, p1 = mo.HUMANOID3D_BODY_DEFS[body]
+        off = 9 * body + 1
+        y = ob[:, 0] + ob[:, off + 1]
+        lim = 0.5 * p0 + 1e-4
+        if shape == "sphere":
+            m = np.minimum(m, np.abs(y - lim))
+        else:
+            cap = 0.5 * p1 * ob[:, off + 4]
+            m = np.minimum(m, np.minimum(np.abs(y + cap - lim), np.abs(y - cap - lim)))
+    return m
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("E", [1, 127, 128, 129, 1024])
+def test_step_matches_oracle(prec, E):
+    from amp_extensions_b200.engine import HumanoidTermination
+    c = H.ns_case()
+    eng = make_engine(c, prec)
+    eng.set_termination(HumanoidTermination(horizon=300, enable_velocity_check=True))
+    s = H.humanoid_like_states(E, seed=11)
+    g = torch.Generator().manual_seed(12)
+    a = torch.randn(E, 28, generator=g)
+    member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32)
+    steps = torch.randint(0, 300, (E,), generator=g, dtype=torch.int32)
+    steps[: max(1, E // 8)] = 299
+    _, nxt_ref, steps_ref, done_ref, disc_ref = oracle_step(c, s, a, member, steps, horizon=300,
+                                                            enable_velocity_check=True)
+    sd, ad = s.cuda(), a.cuda()
+    md, std = member.cuda(), steps.clone().cuda()
+    nxt, disc, done = eng.step(sd, ad, md, std)
+    # scale of a state element: the dataset's per-dimension spread (state_scale of the transforms)
+    assert_close(nxt, nxt_ref, c["tf"][1].mean().item(), what="next_state")
+    assert_close(disc, disc_ref, disc_ref.mean().item(), what="disc")
+    assert torch.equal(std.cpu(), steps_ref.to(torch.int32))
+    mism = done.cpu().bool() != done_ref
+    if mism.any():
+        margin = np.minimum(collision_margin(nxt_ref.numpy()), np.abs(np.abs(nxt_ref.numpy()[:, 136:]) - 100).min(1))
+        assert (margin[mism.numpy()] < REL * 1.0).all(), "termination mask differs away from any threshold"
+    assert 0 < int(done_ref.sum()) < E or E == 1  # the inputs exercise both outcomes
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_step_in_place_and_optional_outputs(prec):
+    c = H.tiny_case("tiny_dense")
+    eng = make_engine(c, prec)
+    g = torch.Generator().manual_seed(3)
+    s, a = torch.randn(300, 20, generator=g).cuda(), torch.randn(300, 6, generator=g).cuda()
+    member = torch.zeros(300, dtype=torch.int32, device="cuda")
+    steps = torch.zeros(300, dtype=torch.int32, device="cuda")
+    ref_next, ref_disc, _ = eng.step(s, a, member, steps.clone())
+    s2 = s.clone()
+    out, disc, done = eng.step(s2, a, member, steps, next_state=s2, want_disc=False, want_done=False)
+    assert out.data_ptr() == s2.data_ptr() and disc is None and done is None
+    assert torch.equal(s2, ref_next)  # aliasing next_state with state is allowed (sim_env.py:158 is in place)
+    assert int(steps.min()) == 1 and int(steps.max()) == 1
+
+
+def test_empty_batch_is_a_no_op():
+    c = H.tiny_case("tiny_dense")
+    eng = make_engine(c, "tf32")
+    assert eng.forward(torch.zeros(0, 20), torch.zeros(0, 6)).shape == (3, 0, 20)
+    assert eng.discrepancy(torch.zeros(0, 20), torch.zeros(0, 6)).shape == (0,)
+
+
+def test_identical_members_have_zero_discrepancy():
+    c = dict(H.tiny_case("tiny_dense"))
+    c["ws"] = [c["ws"][0]] * c["N"]
+    c["bs"] = [c["bs"][0]] * c["N"]
+    eng = make_engine(c, "fp16")
+    assert float(eng.discrepancy(c["xs"], c["xa"]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_rows_are_independent_and_chunking_is_invisible(prec):
+    """Full-size properties (40 000 rows, BASELINE.json config 2): a row's result does not depend on the
+    batch around it, on its position, or on how the library chunks the batch."""
+    c = H.ns_case()
+    E = 40000
+    g = torch.Generator().manual_seed(21)
+    s, a = torch.randn(E, 226, generator=g).cuda(), torch.randn(E, 28, generator=g).cuda()
+    big = make_engine(c, prec)
+    d_all = big.discrepancy(s, a)
+    assert torch.isfinite(d_all).all()
+    perm = torch.randperm(E, generator=g).cuda()
+    assert torch.equal(big.discrepancy(s[perm], a[perm]), d_all[perm])
+    assert torch.equal(big.discrepancy(s[1000:1777], a[1000:1777]), d_all[1000:1777])
+    small = make_engine(c, prec, max_chunk_envs=4096)
+    assert torch.equal(small.discrepancy(s, a), d_all)
+    # forward and discrepancy come from the same pass: recompute the norm from the returned deltas
+    f = big.forward(s[:4096], a[:4096]).double()
+    pair = torch.stack([(f[i] - f[j]).norm(dim=1) for i in range(4) for j in range(i + 1, 4)]).max(0).values
+    assert_close(d_all[:4096], pair, pair.mean().item(), rel=1e-5, what="disc vs forward")
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_extreme_inputs_stay_finite_or_propagate_nan(prec):
+    c = H.tiny_case("tiny_dense")
+    eng = make_engine(c, prec)
+    s, a = c["xs"].clone(), c["xa"].clone()
+    s[0] = 1e6   # an exploded state: fp16 operands saturate instead of overflowing
+    s[1, 3] = float("nan")
+    out = eng.forward(s, a).cpu()
+    assert torch.isfinite(out[:, 0]).all()
+    assert torch.isnan(out[:, 1]).any()
+    assert torch.isfinite(out[:, 2:]).all()
+    assert torch.isnan(eng.discrepancy(s, a).cpu()[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# MILO cost
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("tag,D", [("cost64", 64), ("cost512", 512)])
+def test_rbf_linear_cost_matches_reference(tag, D, prec):
+    from amp_extensions_b200 import RBFLinearCost
+    g = H.golden()
+    c = H.ns_case()
+    cost = RBFLinearCost(H.ns_expert(), feature_dim=D, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100,
+                         precision=prec)
+    assert cost.bw == float(g[f"{tag}/bw"])  # host-side fit: same RNG stream, same arithmetic
+    wsum = g[f"{tag}/rff_wsum"]
+    assert float(cost.rff.weight.data.double().sum()) == wsum[0] and float(cost.rff.bias.data.double().sum()) == wsum[1]
+    phi_scale = (2.0 / D) ** 0.5
+    assert_close(cost.phi_e, H.t(g[f"{tag}/phi_e"]), phi_scale, what="phi_e")
+    nxt = H.t(g[f"{tag}/next"])
+    pi = torch.cat([c["xs"], nxt], dim=1)
+    assert_close(cost.get_rep(pi), H.t(g[f"{tag}/rep"]), phi_scale, what="rep")
+    mmd = cost.fit_cost(pi)
+    assert mmd == pytest.approx(float(g[f"{tag}/mmd"]), rel=REL)
+    w_ref = H.t(g[f"{tag}/w"])
+    assert_close(cost.w, w_ref, w_ref.abs().max().item(), what="w")
+    cost.w = w_ref.clone()  # isolate the remaining checks from the fit
+    costs_ref = H.t(g[f"{tag}/costs"])
+    cscale = max(costs_ref.abs().max().item(), 1e-6)
+    assert_close(cost.get_costs(pi), costs_ref, cscale, what="costs")
+
+    class Ens:  # the reference passes the ensemble object (linear_cost.py:132)
+        threshold = c["threshold"]
+
+        @staticmethod
+        def get_action_discrepancy(s, a):
+            return c["disc"]
+
+    total, info = cost.get_bonus_costs(c["xs"], c["xa"], Ens, next_states=nxt)
+    assert total.shape == (48, 1)
+    tot_ref = H.t(g[f"{tag}/total"])
+    assert_close(total, tot_ref, tot_ref.abs().max().item(), what="total cost")
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        ref = H.t(g[f"{tag}/info_{k}"])
+        assert_close(info[k], ref, max(ref.abs().max().item(), 1e-6), what=k)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_fused_step_cost_matches_oracle(prec):
+    """BASELINE.json config 2 path: step + discrepancy bonus + IPM cost in one call."""
+    from amp_extensions_b200 import RBFLinearCost
+    from amp_extensions_b200.engine import HumanoidTermination
+    c = H.ns_case()
+    E = 2000
+    s = H.humanoid_like_states(E, seed=31)
+    g = torch.Generator().manual_seed(32)
+    a = torch.randn(E, 28, generator=g)
+    member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32)
+    steps = torch.zeros(E, dtype=torch.int32)
+    lam, thr = 0.0025, c["threshold"]
+    oc = mo.RffCostOracle(H.ns_expert(), feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=lam, seed=100)
+    _, nxt_ref, _, done_ref, disc_ref = oracle_step(c, s, a, member, steps)
+    oc.fit_cost(torch.cat([s, nxt_ref.float()], dim=1)[:1024])
+    cost_ref, info_ref = oc.get_bonus_costs(s, a, disc_ref, thr, next_states=nxt_ref.float())
+
+    eng = make_engine(c, prec)
+    eng.set_termination(HumanoidTermination())
+    eng.load_rff(oc.rff_weight, oc.rff_bias, split=True)
+    nxt, disc, done, cost, ipm, bonus = eng.step_cost(s.cuda(), a.cuda(), member.cuda(), steps.cuda(), oc.w.cuda(),
+                                                       lam, thr)
+    assert_close(nxt, nxt_ref, c["tf"][1].mean().item(), what="next_state")
+    assert_close(disc, disc_ref, disc_ref.mean().item(), what="disc")
+    cs = cost_ref.abs().max().item()
+    assert_close(cost, cost_ref[:, 0], cs, what="cost")
+    assert_close(ipm, info_ref["ipm"][:, 0], cs, what="ipm")
+    assert_close(bonus, info_ref["bonus"][:, 0], info_ref["bonus"].abs().max().item(), what="bonus")
+    # reward = -cost (batch_reinforce.py:144) at 1e-3 of the reward scale
+    assert_close(-cost, -cost_ref[:, 0], cs, what="reward")
+    # cost_range=None variant (linear_cost.py:103, 137-138)
+    oc.cost_range = None
+    cost_ref2, _ = oc.get_bonus_costs(s, a, disc_ref, thr, next_states=nxt_ref.float())
+    out = eng.step_cost(s.cuda(), a.cuda(), member.cuda(), steps.cuda(), oc.w.cuda(), lam, 1.0, 0.0, 0.0, False)
+    assert_close(out[3], cost_ref2[:, 0], cost_ref2.abs().max().item(), what="unclamped cost")
