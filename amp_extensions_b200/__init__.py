@@ -17,3 +17,6 @@ from .dynamics import DynamicsEnsemble, DynamicsModel  # noqa: F401
 from .engine import Engine, HumanoidTermination  # noqa: F401
 from .linear_cost import RBFLinearCost  # noqa: F401
 from .sim_env import SimEnv, VecSimEnv  # noqa: F401
+from .character import Character, humanoid3d  # noqa: F401
+from .imitation import ImitationReward  # noqa: F401
+from .motion import MotionClip  # noqa: F401

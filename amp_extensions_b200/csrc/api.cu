@@ -388,6 +388,8 @@ int rff_sources(simstep_handle* h, const float* s, const float* a, const float* 
   return SIMSTEP_OK;
 }
 
+void free_clip(simstep_handle* h);
+
 int check_step_ready(simstep_handle* h, long long n_envs) {
   if (!h) return SIMSTEP_EINVAL;
   if (!h->have_ensemble) return fail(h, SIMSTEP_EINVAL, "simstep_load_ensemble has not been called");
@@ -503,7 +505,7 @@ int simstep_destroy(simstep_handle* h) {
   cudaFree(h->rff_b);
   cudaFree(h->rff_wpad);
   cudaFree(h->colsum_partial);
-  cudaFree(h->imit_dev);
+  free_clip(h);
   delete h;
   return SIMSTEP_OK;
 }

@@ -42,8 +42,9 @@ struct ElemF16 {
   static constexpr int kKind = 1;
   static constexpr uint32_t kFmt = 0;
   __device__ static __forceinline__ storage cvt(float x) {
-    // saturate instead of overflowing to inf: an exploded state stays finite
-    return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    // saturate instead of overflowing to inf: an exploded state stays finite; NaN stays NaN
+    const float c = fminf(fmaxf(x, -65504.f), 65504.f);
+    return __float2half_rn(x != x ? x : c);
   }
 };
 struct ElemBF16 {

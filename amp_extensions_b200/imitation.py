@@ -1,0 +1,41 @@
+"""DeepMimic / AMP motion-imitation reward against a reference clip, batched on B200.
+
+`ImitationReward(character, clip)` evaluates reference DeepMimicCore
+scenes/SceneImitate.cpp:7-127 (cSceneImitate::CalcRewardImitate) for E environments per call: the
+simulated character is given by its generalized pose/velocity (the layout of cKinTree, e.g. 43 numbers
+for humanoid3d: root pos 3 + root quat 4 (w,x,y,z) + per-joint parameters), the kinematic character is the
+clip evaluated at each env's own time (Motion.cpp:267-305 with slerp, MotionController.cpp:25-41 cycle
+offset, KinCharacter.cpp:573-640) plus an optional world offset of its origin.
+"""
+import torch
+
+from . import engine as _engine
+from .character import Character, humanoid3d
+from .motion import MotionClip
+
+
+class ImitationReward:
+    def __init__(self, character=None, clip=None, device=None, engine=None):
+        self.character = character if character is not None else humanoid3d()
+        self.clip = clip if clip is not None else MotionClip.spinkick(self.character)
+        if engine is None:
+            # a handle needs an ensemble shape; the reward itself uses none of it
+            engine = _engine.Engine(state_dim=self.character.dof, action_dim=0, num_models=1, hidden_sizes=[],
+                                    transform=False, device=device)
+        self.engine = engine
+        self.engine.load_clip(self.character, self.clip)
+        self.dof = self.character.dof
+
+    def reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False):
+        """pose, vel: [E, dof]; kin_time: [E] seconds; kin_origin: [E, 3] or None.
+        Returns reward [E] (and the five sub-rewards pose, vel, end-effector, root, com as [E, 5])."""
+        return self.engine.imitation_reward(pose, vel, kin_time, kin_origin, want_terms=want_terms)
+
+    def sample(self, kin_time, kin_origin=None):
+        """Pose and velocity of the kinematic character at the given clip times: ([E, dof], [E, dof])."""
+        return self.engine.clip_sample(kin_time, kin_origin)
+
+    @staticmethod
+    def advance_time(kin_time, num_steps, dt=1.0 / 30.0):
+        """Clip time after num_steps policy steps (20 substeps of 1/600 s, gym_deepmimic.py:106-110)."""
+        return kin_time + torch.as_tensor(num_steps, dtype=torch.float32, device=kin_time.device) * dt

@@ -79,3 +79,40 @@ def humanoid_like_states(E, seed, fall_fraction=0.3):
     s[low, 0] = 0.05 + 0.3 * torch.rand(int(low.sum()), generator=g)
     s[:, 136:] = torch.randn(E, 90, generator=g) * 3.0
     return s
+
+
+def spinkick_raw():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "amp_extensions_b200", "data",
+                             "humanoid3d_spinkick.npz"))
+    return z["frames_raw"]
+
+
+def perturbed_poses(E, seed, clip=None, t_max=None, with_origin=True):
+    """SURVEY.md section 8d generator: pose = clip(t) perturbed (root pos += N(0,.05), every quaternion
+    <- exp(N(0,.2) axis) q, revolute += N(0,.2)), vel = clipvel(t) + N(0,.5), t ~ U(0, t_max)."""
+    from oracle import imitation_oracle as io
+    clip = clip or io.Clip(spinkick_raw(), io.HUMANOID3D, "wrap")
+    rng = np.random.default_rng(seed)
+    offs, _ = io.param_layout(io.HUMANOID3D)
+    t = rng.uniform(0, t_max if t_max is not None else clip.duration, E)
+    origin = rng.normal(0, 0.3, (E, 3)) if with_origin else None
+    pose, vel = np.zeros((E, 43)), np.zeros((E, 43))
+    for e in range(E):
+        p = clip.kin_pose(t[e], origin[e] if with_origin else (0, 0, 0))
+        if with_origin:
+            p[1] -= origin[e, 1]  # the simulated character stands on the real ground
+        v = clip.kin_vel(t[e]) + rng.normal(0, 0.5, 43)
+        p[0:3] += rng.normal(0, 0.05, 3)
+        for j, jt in enumerate(io.HUMANOID3D["joint_type"]):
+            o = offs[j] + (3 if jt == io.ROOT else 0)
+            if jt in (io.ROOT, io.SPHERICAL):
+                ax = rng.normal(0, 1, 3)
+                ang = rng.normal(0, 0.2)
+                dq = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * ax / np.linalg.norm(ax)])
+                q = io.quat_mul(dq, p[o:o + 4])
+                p[o:o + 4] = q / np.linalg.norm(q)
+                v[o + 3] = 0.0  # 4th slot of an angular velocity is unused (KinTree.cpp:1546)
+            elif jt == io.REVOLUTE:
+                p[o] += rng.normal(0, 0.2)
+        pose[e], vel[e] = p, v
+    return pose, vel, t, origin

@@ -1,0 +1,115 @@
+"""GPU parity of the imitation-reward kernel against the float64 oracle (oracle/imitation_oracle.py).
+
+Tolerance: reward and its five exponential sub-rewards within 1e-3 relative (fp32 kernel against a float64
+restatement); "relative" against max(|ref|, 1e-2) because a sub-reward may underflow towards 0.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import imitation_oracle as io
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+REL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from amp_extensions_b200 import ImitationReward
+    clip = io.Clip(H.spinkick_raw(), io.HUMANOID3D, "wrap")
+    return ImitationReward(), clip
+
+
+def close(x, ref, floor=1e-2, rel=REL):
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert np.isfinite(x).all()
+    bad = np.abs(x - ref) > rel * np.maximum(np.abs(ref), floor)
+    assert not bad.any(), f"{bad.sum()} of {bad.size} outside tolerance, worst {np.abs(x - ref).max():.3e}"
+
+
+def test_clip_sampling_matches_oracle(setup):
+    imit, clip = setup
+    rng = np.random.default_rng(5)
+    t = np.concatenate([rng.uniform(0, 5 * clip.duration, 500), clip.times[:-1], [0.0, clip.duration, 2 * clip.duration]])
+    org = rng.normal(0, 0.5, (t.size, 3))
+    pose, vel = imit.sample(torch.from_numpy(t).float(), torch.from_numpy(org).float())
+    pose, vel = pose.cpu().numpy(), vel.cpu().numpy()
+    t32 = t.astype(np.float32).astype(np.float64)
+    # skip samples whose fp32 time lands on the other side of a frame / cycle boundary
+    ok = np.ones(t.size, dtype=bool)
+    for e in range(t.size):
+        i64, _ = clip.index_blend(t[e])
+        i32, _ = clip.index_blend(t32[e])
+        ok[e] = i64 == i32 and clip.cycle_count(t[e]) == clip.cycle_count(t32[e])
+    assert ok.sum() > 480
+    ref_p = np.stack([clip.kin_pose(t32[e], org[e].astype(np.float32).astype(np.float64)) for e in range(t.size)])
+    ref_v = np.stack([clip.kin_vel(t32[e]) for e in range(t.size)])
+    # fp32 time resolution (6e-8 s relative) times the clip velocity bounds the achievable agreement
+    np.testing.assert_allclose(pose[ok], ref_p[ok], atol=2e-5)
+    np.testing.assert_allclose(vel[ok], ref_v[ok], atol=2e-3, rtol=1e-4)
+
+
+def test_reward_is_one_on_the_clip_at_scale(setup):
+    """1M envs (BASELINE.json config 3 size): the kinematic character scores 1 against itself."""
+    imit, clip = setup
+    E = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    t = torch.rand(E, device="cuda", generator=g) * (6 * clip.duration)
+    pose, vel = imit.sample(t)
+    r, terms = imit.reward(pose, vel, t, want_terms=True)
+    assert float((r - 1).abs().max()) < 2e-5
+    assert float((terms - 1).abs().max()) < 1e-4
+    # rewards are bounded and fall when the pose is perturbed
+    r2 = imit.reward(pose + 0.05 * torch.randn(pose.shape, device="cuda", generator=g), vel, t)
+    assert float(r2.max()) <= 1.0 + 1e-6 and float(r2.min()) >= 0.0 and float(r2.mean()) < float(r.mean())
+
+
+@pytest.mark.parametrize("with_origin", [False, True])
+def test_reward_matches_oracle_on_perturbed_poses(setup, with_origin):
+    imit, clip = setup
+    E = 384
+    pose, vel, t, origin = H.perturbed_poses(E, seed=3, clip=clip, t_max=4 * clip.duration, with_origin=with_origin)
+    t32 = t.astype(np.float32).astype(np.float64)
+    p32, v32 = pose.astype(np.float32).astype(np.float64), vel.astype(np.float32).astype(np.float64)
+    o32 = origin.astype(np.float32).astype(np.float64) if with_origin else None
+    ref_r, ref_terms = io.imitation_reward_batch(io.HUMANOID3D, clip, p32, v32, t32, o32)
+    r, terms = imit.reward(torch.from_numpy(pose).float(), torch.from_numpy(vel).float(), torch.from_numpy(t).float(),
+                           torch.from_numpy(origin).float() if with_origin else None, want_terms=True)
+    close(terms.cpu().numpy(), ref_terms)
+    close(r.cpu().numpy(), ref_r)
+    assert ref_terms.min() < 0.5 < ref_terms.max()  # the inputs exercise the exponentials' range
+
+
+def test_closed_form_terms_on_gpu(setup):
+    imit, clip = setup
+    t = 0.45
+    p1, v1 = clip.kin_pose(t), clip.kin_vel(t)
+    theta = 0.3
+    ax = np.array([0.2, 1.0, -0.4])
+    dq = np.concatenate([[np.cos(theta / 2)], np.sin(theta / 2) * ax / np.linalg.norm(ax)])
+    rows_p, rows_v, want = [], [], []
+    p0 = p1.copy(); p0[7:11] = io.quat_mul(p1[7:11], dq)
+    rows_p.append(p0); rows_v.append(v1); want.append((0, np.exp(-2.0 * (0.5 / 4.8) * theta ** 2)))
+    p0 = p1.copy(); p0[19] += 0.2
+    rows_p.append(p0); rows_v.append(v1); want.append((0, np.exp(-2.0 * (0.3 / 4.8) * 0.04)))
+    v0 = v1.copy(); v0[11:14] += [0.5, -0.25, 1.0]
+    rows_p.append(p1); rows_v.append(v0); want.append((1, np.exp(-0.1 * (0.3 / 4.8) * 1.3125)))
+    p0 = p1.copy(); p0[0] += 0.1; p0[2] -= 0.2
+    rows_p.append(p0); rows_v.append(v1); want.append((3, np.exp(-5.0 * 0.05)))
+    _, terms = imit.reward(torch.tensor(np.stack(rows_p)).float(), torch.tensor(np.stack(rows_v)).float(),
+                           torch.full((4,), t), want_terms=True)
+    terms = terms.cpu().numpy()
+    for row, (k, val) in enumerate(want):
+        assert terms[row, k] == pytest.approx(val, rel=REL)
+
+
+def test_rows_are_independent(setup):
+    imit, clip = setup
+    pose, vel, t, origin = H.perturbed_poses(300, seed=9, clip=clip)
+    args = [torch.from_numpy(a).float().cuda() for a in (pose, vel, t, origin)]
+    r = imit.reward(*args)
+    perm = torch.randperm(300, device="cuda")
+    assert torch.equal(imit.reward(*[a[perm] for a in args]), r[perm])
+    assert torch.equal(imit.reward(*[a[100:133] for a in args]), r[100:133])
+    assert imit.reward(*[a[:0] for a in args]).shape == (0,)
