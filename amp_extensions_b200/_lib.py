@@ -99,6 +99,8 @@ _SIGNATURES = {
                                            _c_void_p, _c_void_p, _c_void_p]),
     "simstep_clip_sample": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p, _c_void_p]),
     "simstep_reduce_max_sum": (C.c_int, [_c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
+    "simstep_profile_enable": (C.c_int, [_c_void_p, C.c_int32]),
+    "simstep_profile_read": (C.c_int, [_c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "simstep_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _c_void_p, _c_void_p,
                                      _c_void_p, _c_void_p, _c_void_p]),
     "simstep_launch_count": (C.c_int64, []),
@@ -143,6 +145,9 @@ def check(rc, handle=None):
     if rc != 0:
         msg = load().simstep_last_error(handle)
         raise SimstepError(f"libsimstep error {rc}: {msg.decode() if msg else '?'}")
+
+
+PROF_CATEGORIES = ("prep", "ensemble_gemm", "post", "rff_pack", "rff_gemm", "combine", "imitation", "reserved")
 
 
 def launch_count():

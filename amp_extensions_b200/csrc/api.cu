@@ -75,10 +75,38 @@ struct simstep_handle {
   bool have_clip = false;
   int dof = 0;
 
+  // optional per-category device timing (simstep_profile_*)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;   // begin/end pairs
+  std::vector<int> prof_cat;
+  int prof_open = -1;
+  double prof_ms[SIMSTEP_PROF_CATEGORIES] = {0};
+  long long prof_n[SIMSTEP_PROF_CATEGORIES] = {0};
+
   std::string err;
 };
 
 namespace {
+
+// Brackets the launches issued while it is alive with two events on the launch stream.
+struct ProfScope {
+  simstep_handle* h;
+  cudaStream_t st;
+  bool on;
+  ProfScope(simstep_handle* h_, int cat, cudaStream_t st_) : h(h_), st(st_), on(h_ && h_->prof_on) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->prof_ev.push_back(a);
+    h->prof_ev.push_back(b);
+    h->prof_cat.push_back(cat);
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(h->prof_ev.back(), st);
+  }
+};
 
 int fail(simstep_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -251,12 +279,16 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
 // deltas in h->dws[N][cap_rows][SP].
 int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st) {
   const long long rows_pad = round_up(n, kBlockM);
+  {
+  ProfScope ps(h, SIMSTEP_PROF_PREP, st);
   switch (h->cfg.precision) {
     case SIMSTEP_PREC_TF32: launch_prep<ElemTF32>(h, s, a, n, rows_pad, st); break;
     case SIMSTEP_PREC_FP16: launch_prep<ElemF16>(h, s, a, n, rows_pad, st); break;
     default: launch_prep<ElemBF16>(h, s, a, n, rows_pad, st);
   }
+  }
   CU_TRY(h, cudaGetLastError());
+  ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
   for (int l = 0; l <= h->L; ++l) {
     const Layer& ly = h->layers[l];
     GemmArgs ga{};
@@ -300,6 +332,7 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
 int launch_post(simstep_handle* h, const float* state, const int32_t* member, int32_t* num_steps, long long n,
                 float* next_state, float* disc, uint8_t* done, cudaStream_t st) {
   if (h->S > 32 * kPostMaxPerLane) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
+  ProfScope ps(h, SIMSTEP_PROF_POST, st);
   const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, static_cast<long long>(h->sm_count) * 8));
   const size_t smem = size_t(kPostWarps) * h->S * sizeof(float);
 #define POST_CASE(NM)                                                                                         \
@@ -319,6 +352,7 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
 }
 
 int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStream_t st) {
+  ProfScope ps(h, SIMSTEP_PROF_RFF_PACK, st);
   const long long rows_pad = round_up(n, kBlockM);
   const long long total = rows_pad * h->RK;
   const int grid = grid_for(total, 256, h->sm_count);
@@ -342,6 +376,7 @@ int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStrea
 
 // RFF GEMM over the packed rows of the chunk.  w_pad == nullptr: features only.
 int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* phi, cudaStream_t st) {
+  ProfScope ps(h, SIMSTEP_PROF_RFF_GEMM, st);
   GemmArgs ga{};
   ga.m_tiles = int(round_up(n, kBlockM) / kBlockM);
   ga.n_tiles = h->D_pad / kBlockN;
@@ -363,6 +398,7 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
 
 int launch_combine(simstep_handle* h, const float* disc, long long n, float lambda_b, float threshold, float c_min,
                    float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus, cudaStream_t st) {
+  ProfScope ps(h, SIMSTEP_PROF_COMBINE, st);
   cost_combine_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(
       h->rff_part, h->cap_rows, h->D_pad / kBlockN, float(std::sqrt(2.0 / h->D)), disc, n, lambda_b, threshold, c_min,
       c_max, clamp_cost, dot, cost, ipm, bonus);
@@ -816,6 +852,34 @@ int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, dou
   reduce_max_sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, n, out_dev);
   g_launches++;
   CU_TRY(h, cudaGetLastError());
+  return SIMSTEP_OK;
+}
+
+int simstep_profile_enable(simstep_handle* h, int32_t enable) {
+  if (!h) return SIMSTEP_EINVAL;
+  h->prof_on = enable != 0;
+  return SIMSTEP_OK;
+}
+
+int simstep_profile_read(simstep_handle* h, double* ms_out, int64_t* count_out, int32_t reset) {
+  if (!h) return SIMSTEP_EINVAL;
+  CU_TRY(h, cudaDeviceSynchronize());
+  for (size_t i = 0; i < h->prof_cat.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) {
+      h->prof_ms[h->prof_cat[i]] += ms;
+      h->prof_n[h->prof_cat[i]] += 1;
+    }
+    cudaEventDestroy(h->prof_ev[2 * i]);
+    cudaEventDestroy(h->prof_ev[2 * i + 1]);
+  }
+  h->prof_ev.clear();
+  h->prof_cat.clear();
+  for (int c = 0; c < SIMSTEP_PROF_CATEGORIES; ++c) {
+    if (ms_out) ms_out[c] = h->prof_ms[c];
+    if (count_out) count_out[c] = h->prof_n[c];
+    if (reset) { h->prof_ms[c] = 0; h->prof_n[c] = 0; }
+  }
   return SIMSTEP_OK;
 }
 

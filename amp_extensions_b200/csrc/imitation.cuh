@@ -203,7 +203,8 @@ __device__ __forceinline__ KinSampler make_sampler(const ImitConst& c, const Imi
   return k;
 }
 
-// heading frame: rotation by -heading about y (KinTree.cpp:1667-1712), applied to a direction
+// heading frame: rotation by -heading about y (KinTree.cpp:1667-1712), applied to a direction.  The reference
+// rotates the x axis with Eigen's q*v, which does NOT normalise q: pass the raw root quaternion.
 __device__ __forceinline__ void heading_cs(Quat root_q, float& hc, float& hs) {
   const Vec3 d = qrot(root_q, v3(1.f, 0.f, 0.f));
   const float n2 = d.x * d.x + d.z * d.z;
@@ -283,7 +284,7 @@ imitation_reward_kernel(const ImitConst c, const float* __restrict__ g_times, co
         for (int i = 0; i < 7; ++i) kv[i] = k.v0 ? k.vel(i) : 0.f;
         B[0].v = v3(kv[0], kv[1], kv[2]);
         B[0].w = v3(kv[3], kv[4], kv[5]);
-        heading_cs(A[0].Q, hc0, hs0);
+        heading_cs(rq0_raw, hc0, hs0);
         heading_cs(B[0].Q, hc1, hs1);
         // SceneImitate.cpp:66-68: root rotation and root angular velocity (4 stored components)
         pose_err += jw * quat_theta_sq(rq0_raw, rq1);

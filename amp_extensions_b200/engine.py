@@ -236,11 +236,25 @@ class Engine:
                                                 _ptr(cost), _ptr(ipm), _ptr(bonus), _stream(self.device)))
         return cost, ipm, bonus
 
-    def reduce_max_sum(self, x):
+    def reduce_max_sum(self, x, out=None):
+        """[max, sum] of a device vector as fp64 (written into `out` when given)."""
         x = _dev_f32(x, self.device)
-        out = torch.empty((2,), device=self.device, dtype=torch.float64)
+        if out is None:
+            out = torch.empty((2,), device=self.device, dtype=torch.float64)
         self._check(self.lib.simstep_reduce_max_sum(self._h, _ptr(x), x.numel(), _ptr(out), _stream(self.device)))
         return out
+
+    # -- measurement --------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(self.lib.simstep_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        """{category: (milliseconds, regions)} of device time measured with CUDA events inside the library."""
+        n = len(_lib.PROF_CATEGORIES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.simstep_profile_read(self._h, ms, cnt, int(bool(reset))))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROF_CATEGORIES)}
 
     # -- imitation reward ---------------------------------------------------------------
     def load_clip(self, character, clip):

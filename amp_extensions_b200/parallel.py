@@ -1,0 +1,156 @@
+"""Multi-GPU plumbing: envs shard by index, one process per GPU, full ensemble replica per GPU.
+
+The env step itself needs no data-path collective (every env is independent).
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) carries only small reductions:
+
+  * the discrepancy threshold = dataset maximum (reference milo/milo/dynamics.py:145-152) -> all-reduce MAX,
+    or, as an extension, a global quantile of the per-row discrepancies via a two-pass histogram all-reduce;
+  * fit_cost's feature mean (reference milo/milo/linear_cost.py:84-94) -> all-reduce SUM of [D] sums + count;
+  * rollout cost / return statistics (reference mjrl/mjrl/algos/batch_reinforce.py:135-141, 288-295).
+
+Every function works un-initialised (world size 1) and on CPU tensors (gloo) as well as CUDA tensors (NCCL).
+"""
+import torch
+import torch.distributed as dist
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size():
+    return dist.get_world_size() if is_dist() else 1
+
+
+def rank():
+    return dist.get_rank() if is_dist() else 0
+
+
+def shard_range(n, rank_=None, world=None):
+    """Contiguous env-index range [start, stop) owned by a rank; sizes differ by at most one."""
+    r = rank() if rank_ is None else rank_
+    w = world_size() if world is None else world
+    base, rem = divmod(int(n), w)
+    start = r * base + min(r, rem)
+    return start, start + base + (1 if r < rem else 0)
+
+
+def _all_reduce(t, op):
+    if is_dist():
+        dist.all_reduce(t, op=op)
+    return t
+
+
+def all_reduce_max(x):
+    """Global maximum of a scalar / tensor (element-wise), NaN-propagating like torch.max."""
+    x = torch.as_tensor(x).clone()
+    nan = torch.isnan(x).to(x.dtype)
+    _all_reduce(nan, dist.ReduceOp.MAX)
+    x = torch.nan_to_num(x, nan=-float("inf"))
+    _all_reduce(x, dist.ReduceOp.MAX)
+    return torch.where(nan > 0, torch.full_like(x, float("nan")), x)
+
+
+def all_reduce_sum(x):
+    return _all_reduce(torch.as_tensor(x).clone(), dist.ReduceOp.SUM)
+
+
+def global_threshold(ensemble):
+    """DynamicsEnsemble.compute_threshold over a dataset sharded across ranks: each rank takes the maximum
+    over its own train_dataset on its GPU, one all-reduce(MAX) of a single float makes it global."""
+    local = ensemble.dataset_discrepancy_max()
+    ensemble.threshold = float(all_reduce_max(local).item())
+    return ensemble.threshold
+
+
+def global_fit_cost(cost, data_pi_local):
+    """RBFLinearCost.fit_cost with the rollout rows sharded across ranks: w = global mean phi - phi_e."""
+    eng = cost.engine()
+    n_local = int(data_pi_local.shape[0])
+    if n_local > 0:
+        _, psum = eng.rff_features(data_pi_local, want_sum=True)
+    else:
+        psum = torch.zeros(cost.feature_dim, device=eng.device, dtype=torch.float64)
+    packed = torch.cat([psum, torch.tensor([float(n_local)], device=psum.device, dtype=torch.float64)])
+    packed = all_reduce_sum(packed)
+    phi = (packed[:-1] / packed[-1].clamp_min(1.0)).float().cpu()
+    cost.w = phi - cost.phi_e
+    return cost.w
+
+
+def global_mean(sum_local, count_local):
+    """Mean of a quantity whose per-rank sums and counts are given (fp64)."""
+    packed = torch.cat([torch.as_tensor(sum_local, dtype=torch.float64).reshape(-1),
+                        torch.as_tensor([float(count_local)], dtype=torch.float64).to(torch.as_tensor(sum_local).device)])
+    packed = all_reduce_sum(packed)
+    return packed[:-1] / packed[-1].clamp_min(1.0)
+
+
+def rollout_stats(cost, ipm, bonus, done, num_steps):
+    """Global rollout statistics of one batch of env-steps (batch_reinforce.py:135-141, 288-295):
+    sums / extrema of reward = -cost, int = -bonus, ext = -ipm, finished episodes and their lengths."""
+    f = torch.float64
+    done_b = done.to(torch.bool)
+    n = torch.tensor(float(cost.numel()), device=cost.device, dtype=f)
+    sums = torch.stack([(-cost).to(f).sum(), ((-cost).to(f) ** 2).sum(), (-bonus).to(f).sum(), (-ipm).to(f).sum(),
+                        done_b.to(f).sum(), (num_steps.to(f) * done_b.to(f)).sum(), n])
+    big = float("inf")
+    mx = torch.stack([(-cost).to(f).max() if cost.numel() else torch.tensor(-big, device=cost.device, dtype=f),
+                      cost.to(f).max() if cost.numel() else torch.tensor(-big, device=cost.device, dtype=f)])
+    sums = all_reduce_sum(sums)
+    mx = all_reduce_max(mx)
+    count = sums[6].clamp_min(1.0)
+    mean = sums[0] / count
+    var = (sums[1] / count - mean * mean).clamp_min(0.0)
+    return {
+        "n": int(sums[6].item()), "reward_mean": float(mean), "reward_std": float(var.sqrt()),
+        "reward_max": float(mx[0]), "reward_min": float(-mx[1]), "int": float(sums[2]), "ext": float(sums[3]),
+        "episodes_done": int(sums[4].item()),
+        "ep_len_mean": float(sums[5] / sums[4].clamp_min(1.0)),
+    }
+
+
+def global_quantile(x_local, q, bins=4096, refine=2):
+    """q-quantile (linear interpolation between order statistics, as torch.quantile) of the union of every
+    rank's x_local, without gathering the samples: all-reduce of min/max and of fixed-range histograms, refined
+    `refine` times around the two order statistics that bracket the quantile.  Exact up to the final bin width
+    (range / bins**(refine+1)); used for threshold_mode='quantile', an extension over the reference's dataset
+    maximum."""
+    x = torch.as_tensor(x_local).to(torch.float64).reshape(-1)
+    dev = x.device
+    n = all_reduce_sum(torch.tensor([float(x.numel())], device=dev, dtype=torch.float64))[0]
+    if n.item() == 0:
+        return float("nan")
+    inf = float("inf")
+    lo = -all_reduce_max(torch.tensor([-(x.min().item() if x.numel() else inf)], device=dev, dtype=torch.float64))[0]
+    hi = all_reduce_max(torch.tensor([x.max().item() if x.numel() else -inf], device=dev, dtype=torch.float64))[0]
+    pos = q * (n.item() - 1)
+    k0 = int(pos)
+    frac = pos - k0
+
+    def order_stat(k):
+        a, b = float(lo), float(hi)
+        below = 0  # samples strictly below the current window
+        for _ in range(refine + 1):
+            if b <= a:
+                return a
+            width = (b - a) / bins
+            idx = torch.clamp(((x - a) / width).floor(), 0, bins - 1).long()
+            sel = (x >= a) & (x <= b)
+            hist = torch.bincount(idx[sel], minlength=bins).to(torch.float64)
+            hist = all_reduce_sum(hist)
+            cum = torch.cumsum(hist, 0) + below
+            bin_i = int(torch.searchsorted(cum, torch.tensor([float(k) + 0.5], device=dev, dtype=torch.float64)).item())
+            bin_i = min(bin_i, bins - 1)
+            below = int(cum[bin_i - 1].item()) if bin_i > 0 else below
+            a, b = a + bin_i * width, a + (bin_i + 1) * width
+        # all samples left in the window are within one final bin width: take the window's lower edge + local min
+        in_win = x[(x >= a) & (x <= b)]
+        cand = torch.tensor([-(in_win.min().item() if in_win.numel() else inf)], device=dev, dtype=torch.float64)
+        return float(-all_reduce_max(cand)[0])
+
+    v0 = order_stat(k0)
+    if frac == 0.0 or k0 + 1 >= int(n.item()):
+        return v0
+    v1 = order_stat(k0 + 1)
+    return v0 + frac * (v1 - v0)

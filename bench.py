@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — learned-dynamics env-steps/sec on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's CPU algorithm
+
+One "step" = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1], the
+MILO rollout batch of samples_per_step = 40 000 learned-dynamics env-steps per GPU with the ensemble
+discrepancy bonus and the IPM (random-feature) cost — N-member ensemble forward, s' = s + delta_active,
+pairwise-max discrepancy, termination mask, cos-feature cost and bonus combine — for the 4 x (512 x 4)
+dense-connect humanoid3d ensemble (S = 226, A = 28) with random-init weights.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM), `e2e` is the
+same work through the host-buffer API with pinned H2D/D2H copies inside the timed region, `roofline` is the
+ensemble layer GEMM against the measured tensor peak, `cpu_baseline` is the oracle port of the reference's
+PyTorch CPU path timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_DIM, A_DIM = 226, 28
+N_MODELS, HIDDEN = 4, [512, 512, 512, 512]
+ENVS_PER_GPU = 40000
+RFF_DIM = 512
+LAMBDA_B = 0.0025
+BW_QUANTILE = 0.1
+METRIC = "learned-dynamics env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def flops_per_env_step(n_models=N_MODELS, hidden=HIDDEN, s=S_DIM, a=A_DIM):
+    """Algorithmic FLOPs of the ensemble layers: N * 2 * sum_l K_l * O_l."""
+    sizes = [s + a] + list(hidden) + [s]
+    per_member = sum(2 * sum(sizes[:i + 1]) * sizes[i + 1] for i in range(len(sizes) - 1))
+    return n_models * per_member
+
+
+def fused_bytes_per_env_step(n_models=N_MODELS, s=S_DIM, a=A_DIM):
+    """Algorithmic bytes of the fused next-state/discrepancy/termination/cost path."""
+    return s * 4 + a * 4 + n_models * s * 4 + s * 4 + 16 + 1 + 4 + 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tensor_tflops=d["bf16_tflops_sustained"], burst_tflops=d["bf16_tflops"],
+                    source="measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS / STREAM copy)")
+    return dict(hbm_gbs=6650.0, tensor_tflops=1400.0, burst_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_dataset(M, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(M, S_DIM, generator=g)
+    a = torch.randn(M, A_DIM, generator=g)
+    return s, a, s + 0.05 * torch.randn(M, S_DIM, generator=g)
+
+
+def synth_expert(M, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    es = torch.randn(M, S_DIM, generator=g)
+    return torch.cat([es, es + 0.05 * torch.randn(M, S_DIM, generator=g)], dim=1)
+
+
+# ======================================================================================================
+# reference arm: the reference's own CPU algorithm (oracle port of its PyTorch path)
+
+
+def cpu_reference_setup():
+    import torch
+    from oracle import milo_oracle as mo
+    ws, bs = mo.init_ensemble(S_DIM, A_DIM, HIDDEN, N_MODELS, dense_connect=True, base_seed=100)
+    ds = synth_dataset(8192, 0)
+    tf = mo.get_transformations(*ds)
+    cost = mo.RffCostOracle(synth_expert(4096, 2), feature_dim=RFF_DIM, input_type="ss", bw_quantile=BW_QUANTILE,
+                            lambda_b=LAMBDA_B, seed=100)
+    thr = mo.compute_threshold(ws, bs, tf, ds[0][:1024], ds[1][:1024])
+    g = torch.Generator().manual_seed(1)
+    cost.w = torch.randn(RFF_DIM, generator=g) * 0.01
+    return mo, ws, bs, tf, cost, thr
+
+
+def cpu_reference_step(ctx, s, a, member, steps):
+    """One batch of env-steps as the reference computes them: active-member
+    forward (sim_env.py:155-158), is_done (sim_env.py:164-173), get_bonus_costs = N-member discrepancy +
+    RFF cost + combine (linear_cost.py:111-152)."""
+    import torch
+    mo, ws, bs, tf, cost, thr = ctx
+    with torch.no_grad():
+        nxt = torch.empty_like(s)
+        for m in range(N_MODELS):  # the reference steps each env with its own active member
+            idx = (member == m).nonzero(as_tuple=False).squeeze(1)
+            if idx.numel():
+                nxt[idx] = s[idx] + mo.dynamics_forward(ws[m], bs[m], tf, s[idx], a[idx])
+        _, st, done = mo.simenv_step(s.double().numpy(), (nxt - s).numpy(), steps.numpy())
+        disc = mo.compute_discrepancy(ws, bs, tf, s, a)
+        c, _ = cost.get_bonus_costs(s, a, disc, thr, next_states=nxt)
+    return nxt, c, done
+
+
+def time_cpu_reference(batch, min_seconds, max_reps, warmup=1):
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ctx = cpu_reference_setup()
+    g = torch.Generator().manual_seed(1)
+    s, a = torch.randn(batch, S_DIM, generator=g), torch.randn(batch, A_DIM, generator=g)
+    member = torch.randint(0, N_MODELS, (batch,), generator=g)
+    steps = torch.zeros(batch, dtype=torch.int64)
+    for _ in range(warmup):
+        cpu_reference_step(ctx, s, a, member, steps)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_reps and (time.perf_counter() - t_start < min_seconds or len(times) < 3):
+        t0 = time.perf_counter()
+        cpu_reference_step(ctx, s, a, member, steps)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return dict(value=batch / med, unit=UNIT, cores=threads, kind="port",
+                sample=f"{len(times)} x {batch} env-steps (median), oracle port of the reference's PyTorch CPU path, "
+                       f"torch {torch.__version__} with {threads} intra-op threads"), med
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and cannot
+    travel to the GPU box) on all host threads.  Each step is a bounded sample of the 40 000-step batch, sized
+    after one probe step so that the whole run stays within a couple of minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ctx = cpu_reference_setup()
+    g = torch.Generator().manual_seed(1)
+    full = 4096
+    s, a = torch.randn(full, S_DIM, generator=g), torch.randn(full, A_DIM, generator=g)
+    member = torch.randint(0, N_MODELS, (full,), generator=g)
+    steps = torch.zeros(full, dtype=torch.int64)
+    cpu_reference_step(ctx, s[:256], a[:256], member[:256], steps[:256])
+    t0 = time.perf_counter()
+    cpu_reference_step(ctx, s, a, member, steps)
+    probe = time.perf_counter() - t0
+    budget = 100.0 / max(args.steps + args.warmup, 1)  # seconds per step
+    batch = int(max(256, min(full, (full * budget / probe) // 256 * 256)))
+    s, a, member, steps = s[:batch], a[:batch], member[:batch], steps[:batch]
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_step(ctx, s, a, member, steps)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(ctx, s, a, member, steps)
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    sample = (f"each step = {batch} env-steps of the {ENVS_PER_GPU}-step batch, oracle port of the reference's "
+              f"PyTorch CPU path, torch {torch.__version__}, {threads} intra-op threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, extra={"cpu_sample": sample}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {
+        "workload": "MILO rollout batch: 40000 learned-dynamics env-steps per GPU per step with ensemble "
+                    "discrepancy bonus + IPM/RFF cost (BASELINE.json configs[1])",
+        "ensemble": "4 x (512 x 4) dense_connect, transform, humanoid3d S=226 A=28, random init base_seed=100",
+        "envs_per_gpu": ENVS_PER_GPU, "global_envs_per_step": ENVS_PER_GPU * n_gpus,
+        "rff": {"feature_dim": RFF_DIM, "input_type": "ss", "lambda_b": LAMBDA_B, "hi_lo_split": True},
+        "sharding": f"envs by index over {n_gpus} GPU(s), full ensemble replica per GPU",
+        "l2_policy": "inputs rotate through a ring of 8 batches (325 MB > 126 MB L2); activations (1.5 GB/step) "
+                     "never fit",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ======================================================================================================
+# this repo's arm
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, RBFLinearCost, _lib
+    from amp_extensions_b200.engine import HumanoidTermination
+    from amp_extensions_b200.host_api import HostStepPipeline
+    from amp_extensions_b200 import parallel
+
+    E = args.envs
+    ds = AmpDataset(*synth_dataset(8192, 0))
+    ens = DynamicsEnsemble(S_DIM, A_DIM, ds, None, num_models=N_MODELS, hidden_sizes=HIDDEN, dense_connect=True,
+                           transform=True, base_seed=100, precision=args.precision, device=device)
+    eng = ens.engine()
+    eng.set_termination(HumanoidTermination(horizon=300))
+    cost = RBFLinearCost(synth_expert(4096, 2), feature_dim=RFF_DIM, input_type="ss", bw_quantile=BW_QUANTILE,
+                         lambda_b=LAMBDA_B, seed=100, precision=args.precision, device=device)
+    eng.load_rff(cost.rff.weight.data, cost.rff.bias.data, split=True)
+    # discrepancy threshold: dataset maximum, global over ranks (dynamics.py:145-152)
+    ens.train_dataset = AmpDataset(ds.states[rank::world][:1024], ds.actions[rank::world][:1024],
+                                   ds.next_states[rank::world][:1024])
+    threshold = parallel.global_threshold(ens)
+
+    ring = 8
+    g = torch.Generator(device=device).manual_seed(1 + rank)
+    states = [torch.randn(E, S_DIM, device=device, generator=g) for _ in range(ring)]
+    actions = [torch.randn(E, A_DIM, device=device, generator=g) for _ in range(ring)]
+    member = torch.randint(0, N_MODELS, (E,), device=device, generator=g, dtype=torch.int32)
+    steps = torch.zeros(E, device=device, dtype=torch.int32)
+    nxt = torch.empty(E, S_DIM, device=device)
+    disc, cst, ipm, bonus = (torch.empty(E, device=device) for _ in range(4))
+    done = torch.empty(E, device=device, dtype=torch.uint8)
+    # cost weights: fit on the first 1024 rollout rows (batch_reinforce.py:113), global mean over ranks
+    eng.step(states[0], actions[0], member, steps.clone(), next_state=nxt, disc=disc, done=done)
+    w = parallel.global_fit_cost(cost, torch.cat([states[0][:1024], nxt[:1024]], dim=1)).to(device)
+    stats = torch.zeros(4, device=device, dtype=torch.float64)
+    gathered = torch.zeros(world * 4, device=device, dtype=torch.float64)
+
+    def one_step(i):
+        k = i % ring
+        steps.zero_()
+        eng.step_cost(states[k], actions[k], member, steps, w, LAMBDA_B, threshold, next_state=nxt, disc=disc,
+                      done=done, cost=cst, ipm=ipm, bonus=bonus)
+        if world > 1:  # rollout statistics (batch_reinforce.py:135-141): one small collective per step
+            eng.reduce_max_sum(cst, out=stats[0:2])
+            eng.reduce_max_sum(disc, out=stats[2:4])
+            dist.all_gather_into_tensor(gathered, stats)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = E * world * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel device time (CUDA events inside the library, same workload, separate pass) ----------
+    prof_steps = min(args.steps, 50)
+    eng.profile_enable(True)
+    for i in range(prof_steps):
+        one_step(i)
+    prof = eng.profile_read(reset=True)
+    eng.profile_enable(False)
+    per_step = {k: v[0] / prof_steps for k, v in prof.items() if v[1] > 0}
+
+    # ---- end to end through the host-buffer API: pinned H2D + step + D2H inside the timed region ----------
+    pipe = HostStepPipeline(eng, E, n_chunks=args.e2e_chunks, with_cost=True)
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
+                              "kernels_ms_per_step": per_step, "note": "profiling run (--skip-e2e), not a bench line"}))
+        return 0
+    hs = [states[k].cpu().pin_memory() for k in range(2)]
+    ha = [actions[k].cpu().pin_memory() for k in range(2)]
+    hm, hst = member.cpu().pin_memory(), torch.zeros(E, dtype=torch.int32).pin_memory()
+    e2e_steps = max(10, min(args.steps, 100))
+    for i in range(3):
+        pipe.step(hs[i % 2], ha[i % 2], hm, hst, w, LAMBDA_B, threshold)
+    barrier()
+    t0 = time.perf_counter()
+    chk = 0.0
+    for i in range(e2e_steps):
+        out = pipe.step(hs[i % 2], ha[i % 2], hm, hst, w, LAMBDA_B, threshold)
+        chk += float(out[1][0])  # the caller reads the step's result on the host
+    torch.cuda.synchronize(device)
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = E * world * e2e_steps / float(e2e_dt.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_ms = per_step.get("ensemble_gemm")
+        achieved = flops_per_env_step() * E / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("ensemble_gemm_dram_bytes_per_step")
+        post_ms = per_step.get("post")
+        cpu = None
+        if not args.skip_cpu_baseline:
+            cpu, _ = time_cpu_reference(1024, min_seconds=12.0, max_reps=200)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(world, extra={"operands": f"{args.precision} in, fp32 accumulate (TMEM)",
+                                                    "threshold": threshold}),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "steps": e2e_steps, "chunks": len(pipe.bounds),
+                    "api": "amp_extensions_b200.host_api.HostStepPipeline.step (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "gemm_tcgen05_kernel (5 ensemble layer launches per step)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["tensor_tflops"]) if achieved else None, "traffic": traffic,
+                "peak_source": peaks["source"], "algorithmic_flop_per_env_step": flops_per_env_step(),
+                "ms_per_step": gemm_ms,
+            },
+            "kernels_ms_per_step": per_step,
+            "roofline_hbm": {
+                "kernel": "post_step_kernel (next state + discrepancy + termination)", "bound": "hbm",
+                "achieved": (S_DIM * 4 * (2 + N_MODELS) + 17) * E / (post_ms * 1e-3) / 1e9 if post_ms else None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ((S_DIM * 4 * (2 + N_MODELS) + 17) * E / (post_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                if post_ms else None,
+            },
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "bf16"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU per step")
+    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: no host-buffer pass")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -226,6 +226,24 @@ int simstep_clip_sample(simstep_handle* h, const float* kin_time_dev, const floa
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */
 int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, double* out_dev, void* stream);
 
+/* ---- measurement ---------------------------------------------------------- */
+
+/* Device time per kernel category, measured with CUDA events recorded on the
+ * launch stream around each launch (bench.py's roofline numbers).  Recording is
+ * off by default; enable, run, then read (read synchronises the device). */
+#define SIMSTEP_PROF_PREP 0          /* input normalisation / operand pack      */
+#define SIMSTEP_PROF_ENSEMBLE_GEMM 1 /* all layer GEMMs of one ensemble pass    */
+#define SIMSTEP_PROF_POST 2          /* next state + discrepancy + termination  */
+#define SIMSTEP_PROF_RFF_PACK 3
+#define SIMSTEP_PROF_RFF_GEMM 4
+#define SIMSTEP_PROF_COMBINE 5
+#define SIMSTEP_PROF_IMITATION 6
+#define SIMSTEP_PROF_CATEGORIES 8
+int simstep_profile_enable(simstep_handle* h, int32_t enable);
+/* ms_out[SIMSTEP_PROF_CATEGORIES] accumulated milliseconds, count_out[...] number
+ * of bracketed regions; reset != 0 clears the accumulators afterwards. */
+int simstep_profile_read(simstep_handle* h, double* ms_out, int64_t* count_out, int32_t reset);
+
 /* ---- debugging / unit tests -------------------------------------------- */
 
 /* One grouped GEMM through the production tcgen05 kernel:
