@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -255,10 +256,11 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     }
   }
   if (h->have_rff) {
-    CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * h->RKT * h->esize));
-    CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * h->RKT * h->esize));
+    const int rka = h->rff_split ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
+    CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * rka * h->esize));
+    CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * rka * h->esize));
     CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));
-    int rc = encode_operand(h, &h->tmap_rffin, prec, h->rffin, h->RKT, rows, h->RKT, kBlockM);
+    int rc = encode_operand(h, &h->tmap_rffin, prec, h->rffin, rka, rows, rka, kBlockM);
     if (rc) return rc;
   }
   h->cap_rows = rows;
@@ -268,8 +270,8 @@ int ensure_workspace(simstep_handle* h, long long rows) {
 template <typename E>
 void launch_prep(simstep_handle* h, const float* s, const float* a, long long n, long long rows_pad,
                  cudaStream_t st) {
-  const long long total = rows_pad * h->XP;
-  prep_input_kernel<E><<<grid_for(total, 256, h->sm_count), 256, 0, st>>>(
+  const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
+  prep_input_kernel<E><<<grid, kPrepThreads, 0, st>>>(
       s, a, h->S, h->A, h->XP, n, rows_pad, h->cfg.transform ? h->tf_dev : nullptr,
       static_cast<typename E::storage*>(h->xbuf));
   g_launches++;
@@ -302,7 +304,6 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
     ga.ax_rows_per_group = 0;
     ga.b_rows_per_group = ly.o_pad;
     ga.bias = ly.bias;
-    ga.act = h->cfg.activation;
     int rc;
     if (l < h->L) {
       ga.out = h->hbuf;
@@ -311,7 +312,9 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
       ga.out_col0 = ly.out_col0;
       ga.rows_valid = int(h->cap_rows);
       ga.cols_valid = ly.o_pad;
-      rc = launch_gemm<kEpiHidden>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
+      rc = h->cfg.activation == SIMSTEP_ACT_RELU
+               ? launch_gemm<kEpiHidden>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st)
+               : launch_gemm<kEpiHiddenTanh>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
     } else {
       ga.out = h->dws;
       ga.out_pitch = h->SP;
@@ -331,15 +334,23 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
 
 int launch_post(simstep_handle* h, const float* state, const int32_t* member, int32_t* num_steps, long long n,
                 float* next_state, float* disc, uint8_t* done, cudaStream_t st) {
-  if (h->S > 32 * kPostMaxPerLane) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
+  if (h->S > kPostMaxElems) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
   ProfScope ps(h, SIMSTEP_PROF_POST, st);
   const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, static_cast<long long>(h->sm_count) * 8));
-  const size_t smem = size_t(kPostWarps) * h->S * sizeof(float);
-#define POST_CASE(NM)                                                                                         \
-  case NM:                                                                                                    \
-    post_step_kernel<NM><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member,    \
-                                                                  num_steps, h->S, n, next_state, disc, done,  \
-                                                                  h->term);                                   \
+  const size_t smem = size_t(kPostWarps) * ((h->S + 3) & ~3) * sizeof(float);
+  // float2 lanes need 8-byte aligned rows: even S and 8-byte aligned base pointers
+  const bool vec2 = (h->S % 2 == 0) && (reinterpret_cast<uintptr_t>(state) % 8 == 0) &&
+                    (reinterpret_cast<uintptr_t>(next_state) % 8 == 0);
+#define POST_CASE(NM)                                                                                          \
+  case NM:                                                                                                     \
+    if (vec2)                                                                                                  \
+      post_step_kernel<NM, 2><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member, \
+                                                                     num_steps, h->S, n, next_state, disc, done, \
+                                                                     h->term);                                 \
+    else                                                                                                       \
+      post_step_kernel<NM, 1><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member, \
+                                                                     num_steps, h->S, n, next_state, disc, done, \
+                                                                     h->term);                                 \
     break;
   switch (h->N) {
     POST_CASE(1) POST_CASE(2) POST_CASE(3) POST_CASE(4) POST_CASE(5) POST_CASE(6) POST_CASE(7) POST_CASE(8)
@@ -354,19 +365,18 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
 int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStream_t st) {
   ProfScope ps(h, SIMSTEP_PROF_RFF_PACK, st);
   const long long rows_pad = round_up(n, kBlockM);
-  const long long total = rows_pad * h->RK;
-  const int grid = grid_for(total, 256, h->sm_count);
+  const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
   switch (h->cfg.precision) {
     case SIMSTEP_PREC_TF32:
-      rff_pack_kernel<ElemTF32><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+      rff_pack_kernel<ElemTF32><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
                                                       static_cast<float*>(h->rffin));
       break;
     case SIMSTEP_PREC_FP16:
-      rff_pack_kernel<ElemF16><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+      rff_pack_kernel<ElemF16><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
                                                      static_cast<__half*>(h->rffin));
       break;
     default:
-      rff_pack_kernel<ElemBF16><<<grid, 256, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
+      rff_pack_kernel<ElemBF16><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
                                                       static_cast<__nv_bfloat16*>(h->rffin));
   }
   g_launches++;
@@ -381,8 +391,11 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
   ga.m_tiles = int(round_up(n, kBlockM) / kBlockM);
   ga.n_tiles = h->D_pad / kBlockN;
   ga.groups = 1;
-  ga.kb_x = h->RKT / h->bk;
-  ga.kb_h = 0;
+  // K loop: [hi | lo] through the first map, then the hi block again (x_hi * W_lo) through the second
+  ga.kb_x = (h->rff_split ? 2 * h->RK : h->RK) / h->bk;
+  ga.kb_h0 = 0;
+  ga.kb_h = h->rff_split ? h->RK / h->bk : 0;
+  ga.a_rows_per_group = 0;
   ga.b_rows_per_group = h->D_pad;
   ga.bias = h->rff_b;
   ga.scale = w_pad;
@@ -558,7 +571,7 @@ int simstep_query(const simstep_handle* h, int32_t* n_layers, int32_t* layer_in,
   if (workspace_bytes) {
     const long long r = h->cap_rows;
     *workspace_bytes = r * h->XP * h->esize + static_cast<long long>(h->N) * r * h->HT * h->esize +
-                       static_cast<long long>(h->N) * r * h->SP * 4 + (h->have_rff ? r * h->RKT * h->esize : 0);
+                       static_cast<long long>(h->N) * r * h->SP * 4 + (h->have_rff ? r * (h->rff_split ? 2 * h->RK : h->RK) * h->esize : 0);
   }
   return SIMSTEP_OK;
 }
@@ -659,7 +672,7 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   h->rff_in = in_dim;
   h->RK = int(round_up(in_dim, 64));
   h->rff_split = split ? 1 : 0;
-  h->RKT = h->rff_split ? 3 * h->RK : h->RK;
+  h->RKT = h->rff_split ? 3 * h->RK : h->RK;  // K of the packed weight; the row operand stores 2*RK
   const size_t wbytes = size_t(h->D_pad) * h->RKT * h->esize;
   CU_TRY(h, cudaMalloc(&h->rff_w, wbytes));
   CU_TRY(h, cudaMemset(h->rff_w, 0, wbytes));

@@ -37,31 +37,59 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int src_pitch,
   }
 }
 
+template <typename T>
+struct Pair;
+template <>
+struct Pair<float> { using type = float2; };
+template <>
+struct Pair<__half> { using type = __half2; };
+template <>
+struct Pair<__nv_bfloat16> { using type = __nv_bfloat162; };
+
+template <typename E>
+__device__ __forceinline__ typename Pair<typename E::storage>::type make_pair_cvt(float a, float b) {
+  typename Pair<typename E::storage>::type p;
+  p.x = E::cvt(a);
+  p.y = E::cvt(b);
+  return p;
+}
+
 // x = [(s - mean_s)/scale_s, (a - mean_a)/scale_a, 0...]  (reference
 // milo/milo/dynamics.py:225-230) written in the GEMM operand format.  Rows in
-// [n_rows, rows_pad) are zero-filled so padded tiles stay finite.
+// [n_rows, rows_pad) are zero-filled so padded tiles stay finite.  One block
+// walks rows; each thread owns two adjacent columns (XP is even) and stores
+// them as one packed pair.
+constexpr int kPrepThreads = 128;
 template <typename E>
-__global__ void prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A,
-                                  int XP, long long n_rows, long long rows_pad,
-                                  const float* __restrict__ tf /* mean_s|scale_s|mean_a|scale_a or null */,
-                                  typename E::storage* __restrict__ x) {
-  const long long total = rows_pad * XP;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = idx / XP;
-    const int col = static_cast<int>(idx - row * XP);
-    float v = 0.f;
-    if (row < n_rows) {
-      if (col < S) {
-        v = state[row * S + col];
-        if (tf) v = (v - tf[col]) / tf[S + col];
-      } else if (col < S + A) {
-        const int c = col - S;
-        v = action[row * A + c];
-        if (tf) v = (v - tf[2 * S + c]) / tf[2 * S + A + c];
-      }
+__global__ void __launch_bounds__(kPrepThreads)
+prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A, int XP,
+                  long long n_rows, long long rows_pad,
+                  const float* __restrict__ tf /* mean_s|scale_s|mean_a|scale_a or null */,
+                  typename E::storage* __restrict__ x) {
+  using P = typename Pair<typename E::storage>::type;
+  for (int c0 = 2 * threadIdx.x; c0 < XP; c0 += 2 * kPrepThreads) {
+    // per-column constants hoisted out of the row loop
+    float mean[2] = {0.f, 0.f}, scale[2] = {1.f, 1.f};
+    int src[2];  // 0: state, 1: action, 2: zero padding
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int col = c0 + i;
+      src[i] = col < S ? 0 : (col < S + A ? 1 : 2);
+      if (tf && src[i] == 0) { mean[i] = tf[col]; scale[i] = tf[S + col]; }
+      if (tf && src[i] == 1) { mean[i] = tf[2 * S + col - S]; scale[i] = tf[2 * S + A + col - S]; }
     }
-    x[idx] = E::cvt(v);
+    for (long long row = blockIdx.x; row < rows_pad; row += gridDim.x) {
+      float v[2] = {0.f, 0.f};
+      if (row < n_rows) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = c0 + i;
+          if (src[i] == 0) v[i] = (state[row * S + col] - mean[i]) / scale[i];
+          else if (src[i] == 1) v[i] = (action[row * A + col - S] - mean[i]) / scale[i];
+        }
+      }
+      *reinterpret_cast<P*>(x + row * XP + c0) = make_pair_cvt<E>(v[0], v[1]);
+    }
   }
 }
 
@@ -73,32 +101,42 @@ struct RffSrc {
   int width[3];
 };
 
+// out row = [hi(x) | lo(x)] (split) or [hi(x)] with x the concatenation of the sources zero-padded to RK; the
+// GEMM re-reads the hi block for the third product (x_hi * W_lo), so it is stored once.
 template <typename E>
-__global__ void rff_pack_kernel(RffSrc src, int in_dim, int RK, int split, long long n_rows, long long rows_pad,
-                                typename E::storage* __restrict__ out) {
-  const int RKT = split ? 3 * RK : RK;
-  const long long total = rows_pad * RK;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = idx / RK;
-    int col = static_cast<int>(idx - row * RK);
-    float v = 0.f;
-    if (row < n_rows && col < in_dim) {
-      int c = col;
+__global__ void __launch_bounds__(kPrepThreads)
+rff_pack_kernel(RffSrc src, int in_dim, int RK, int split, long long n_rows, long long rows_pad,
+                typename E::storage* __restrict__ out) {
+  using P = typename Pair<typename E::storage>::type;
+  const int pitch = split ? 2 * RK : RK;
+  for (int c0 = 2 * threadIdx.x; c0 < RK; c0 += 2 * kPrepThreads) {
+    const float* base[2] = {nullptr, nullptr};
+    int width[2] = {0, 0}, off[2] = {0, 0};
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        if (s < src.n) {
-          if (c >= 0 && c < src.width[s]) v = src.ptr[s][row * src.width[s] + c];
-          c -= src.width[s];
+    for (int i = 0; i < 2; ++i) {
+      int c = c0 + i;
+      if (c < in_dim) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k < src.n && base[i] == nullptr) {
+            if (c < src.width[k]) { base[i] = src.ptr[k]; width[i] = src.width[k]; off[i] = c; }
+            c -= src.width[k];
+          }
         }
       }
     }
-    typename E::storage* orow = out + row * RKT;
-    const typename E::storage hi = E::cvt(v);
-    orow[col] = hi;
-    if (split) {
-      orow[RK + col] = E::cvt(v - static_cast<float>(hi));
-      orow[2 * RK + col] = hi;
+    for (long long row = blockIdx.x; row < rows_pad; row += gridDim.x) {
+      float v[2] = {0.f, 0.f};
+      if (row < n_rows) {
+        if (base[0]) v[0] = base[0][row * width[0] + off[0]];
+        if (base[1]) v[1] = base[1][row * width[1] + off[1]];
+      }
+      const P hi = make_pair_cvt<E>(v[0], v[1]);
+      typename E::storage* orow = out + row * pitch;
+      *reinterpret_cast<P*>(orow + c0) = hi;
+      if (split)
+        *reinterpret_cast<P*>(orow + RK + c0) =
+            make_pair_cvt<E>(v[0] - static_cast<float>(hi.x), v[1] - static_cast<float>(hi.y));
     }
   }
 }
@@ -122,34 +160,73 @@ struct TermConst {
 };
 
 constexpr int kPostWarps = 8;
-constexpr int kPostMaxPerLane = 8;  // supports S <= 256
+constexpr int kPostMaxElems = 256;  // supports S <= 256
+
+template <int VEC>
+struct PostVec;
+template <>
+struct PostVec<1> {
+  using type = float;
+  __device__ static __forceinline__ float zero() { return 0.f; }
+  __device__ static __forceinline__ float sub_sq(float a, float b, float acc) { const float t = a - b; return fmaf(t, t, acc); }
+  __device__ static __forceinline__ float add(float a, float b) { return a + b; }
+  __device__ static __forceinline__ bool vel_over(float v, int j, int off, float inv_div, float thr) {
+    return j >= off && fabsf(v * inv_div) > thr;
+  }
+};
+template <>
+struct PostVec<2> {
+  using type = float2;
+  __device__ static __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+  __device__ static __forceinline__ float sub_sq(float2 a, float2 b, float acc) {
+    const float t0 = a.x - b.x, t1 = a.y - b.y;
+    return fmaf(t1, t1, fmaf(t0, t0, acc));
+  }
+  __device__ static __forceinline__ float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+  __device__ static __forceinline__ bool vel_over(float2 v, int j, int off, float inv_div, float thr) {
+    return (j >= off && fabsf(v.x * inv_div) > thr) || (j + 1 >= off && fabsf(v.y * inv_div) > thr);
+  }
+};
 
 // One warp per env row (reference: sim_env.py:140-173 for the step and the
 // termination test, dynamics.py:134-143 for the discrepancy).
 //   delta  [NM][delta_rows][SP] fp32 workspace of the final GEMM, row = chunk-local
 //   state  [E][S], next_state [E][S] (may alias state)
-template <int NM>
+// VEC = 2 when S is even: every row then starts 8-byte aligned and lanes move float2.
+template <int NM, int VEC>
 __global__ void __launch_bounds__(kPostWarps * 32)
 post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, const float* state,
                  const int32_t* __restrict__ member, int32_t* num_steps, int S, long long n_rows,
                  float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done, const TermConst tc) {
+  using V = typename PostVec<VEC>::type;
+  constexpr int kPerLane = kPostMaxElems / (32 * VEC);
   extern __shared__ float sm_rows[];  // [kPostWarps][S]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  float* srow = sm_rows + size_t(wib) * S;
+  float* srow = sm_rows + size_t(wib) * ((S + 3) & ~3);
   const long long warp_global = blockIdx.x * static_cast<long long>(kPostWarps) + wib;
   const long long n_warps = static_cast<long long>(gridDim.x) * kPostWarps;
   constexpr int NP = NM * (NM - 1) / 2;
+  const int nvec = S / VEC;
 
   for (long long row = warp_global; row < n_rows; row += n_warps) {
-    float d[NM][kPostMaxPerLane];
+    V d[NM][kPerLane];
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-      const float* drow = delta + (static_cast<long long>(m) * delta_rows + row) * SP;
+      const V* drow = reinterpret_cast<const V*>(delta + (static_cast<long long>(m) * delta_rows + row) * SP);
 #pragma unroll
-      for (int i = 0; i < kPostMaxPerLane; ++i) {
+      for (int i = 0; i < kPerLane; ++i) {
         const int j = lane + 32 * i;
-        d[m][i] = (j < S) ? __ldg(drow + j) : 0.f;
+        d[m][i] = (j < nvec) ? __ldg(drow + j) : PostVec<VEC>::zero();
+      }
+    }
+    V sv[kPerLane];
+    if (next_state != nullptr) {
+      const V* srow_g = reinterpret_cast<const V*>(state + row * S);
+#pragma unroll
+      for (int i = 0; i < kPerLane; ++i) {
+        const int j = lane + 32 * i;
+        sv[i] = (j < nvec) ? srow_g[j] : PostVec<VEC>::zero();
       }
     }
 
@@ -162,10 +239,7 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
         for (int b = a + 1; b < NM; ++b) {
           float s2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < kPostMaxPerLane; ++i) {
-            const float t = d[a][i] - d[b][i];
-            s2 = fmaf(t, t, s2);
-          }
+          for (int i = 0; i < kPerLane; ++i) s2 = PostVec<VEC>::sub_sq(d[a][i], d[b][i], s2);
           acc[p++] = s2;
         }
       }
@@ -184,18 +258,19 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
 
     if (next_state != nullptr) {
       const int mem = member ? member[row] : 0;
-      float nxt[kPostMaxPerLane];
+      V nxt[kPerLane];
+      V* nrow_g = reinterpret_cast<V*>(next_state + row * S);
+      V* srow_v = reinterpret_cast<V*>(srow);
 #pragma unroll
-      for (int i = 0; i < kPostMaxPerLane; ++i) {
+      for (int i = 0; i < kPerLane; ++i) {
         const int j = lane + 32 * i;
-        float dm = 0.f;
+        V dm = PostVec<VEC>::zero();
 #pragma unroll
         for (int m = 0; m < NM; ++m) dm = (m == mem) ? d[m][i] : dm;
-        nxt[i] = 0.f;
-        if (j < S) {
-          nxt[i] = state[row * S + j] + dm;
-          next_state[row * S + j] = nxt[i];
-          srow[j] = nxt[i];
+        nxt[i] = PostVec<VEC>::add(sv[i], dm);
+        if (j < nvec) {
+          nrow_g[j] = nxt[i];
+          srow_v[j] = nxt[i];
         }
       }
       int steps = 0;
@@ -221,9 +296,9 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
         }
         if (tc.enable_velocity_check) {
 #pragma unroll
-          for (int i = 0; i < kPostMaxPerLane; ++i) {
-            const int j = lane + 32 * i;
-            if (j >= tc.vel_offset && j < S) flag = flag || (fabsf(nxt[i] * tc.vel_inv_divisor) > tc.vel_threshold);
+          for (int i = 0; i < kPerLane; ++i) {
+            const int j = (lane + 32 * i) * VEC;  // first element of this lane's slot
+            if (j < S) flag = flag || PostVec<VEC>::vel_over(nxt[i], j, tc.vel_offset, tc.vel_inv_divisor, tc.vel_threshold);
           }
         }
         const bool any = __any_sync(0xffffffffu, flag);

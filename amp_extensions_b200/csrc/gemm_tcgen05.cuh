@@ -31,20 +31,55 @@ constexpr int kABytes = kBlockM * 128;             // one swizzle atom (128 B) p
 constexpr int kBBytes = kBlockN * 128;
 constexpr int kStageBytes = kABytes + kBBytes;
 
+// Operand formats.  cvt() is the scalar round-to-operand used by the pack kernels; store32<RELU>() converts
+// 32 fp32 accumulator values (optionally through max(x, 0)) and writes them as one contiguous row chunk.
+// NaN propagates through every variant (torch.relu(NaN) is NaN); fp16 saturates instead of overflowing.
 struct ElemTF32 {
   using storage = float;
   static constexpr int kKind = 0;
   static constexpr uint32_t kFmt = 2;
   __device__ static __forceinline__ storage cvt(float x) { return ptx::round_tf32(x); }
+  template <bool RELU>
+  __device__ static __forceinline__ void store32(storage* dst, const float (&v)[32]) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x = v[4 * j + i];
+        if (RELU) asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(x) : "f"(x));
+        r[i] = ptx::round_tf32(x);
+      }
+      d4[j] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
 };
 struct ElemF16 {
   using storage = __half;
   static constexpr int kKind = 1;
   static constexpr uint32_t kFmt = 0;
   __device__ static __forceinline__ storage cvt(float x) {
-    // saturate instead of overflowing to inf: an exploded state stays finite; NaN stays NaN
-    const float c = fminf(fmaxf(x, -65504.f), 65504.f);
-    return __float2half_rn(x != x ? x : c);
+    uint32_t r;  // saturate instead of overflowing to inf: an exploded state stays finite; NaN stays NaN
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(x));
+    return __ushort_as_half(static_cast<unsigned short>(r & 0xFFFFu));
+  }
+  template <bool RELU>
+  __device__ static __forceinline__ void store32(storage* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // d = {a -> upper half, b -> lower half}
+        if (RELU)
+          asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p[i]) : "f"(v[8 * j + 2 * i + 1]), "f"(v[8 * j + 2 * i]));
+        else
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p[i]) : "f"(v[8 * j + 2 * i + 1]), "f"(v[8 * j + 2 * i]));
+      }
+      d4[j] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
   }
 };
 struct ElemBF16 {
@@ -52,6 +87,22 @@ struct ElemBF16 {
   static constexpr int kKind = 1;
   static constexpr uint32_t kFmt = 1;
   __device__ static __forceinline__ storage cvt(float x) { return __float2bfloat16_rn(x); }
+  template <bool RELU>
+  __device__ static __forceinline__ void store32(storage* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (RELU)
+          asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p[i]) : "f"(v[8 * j + 2 * i + 1]), "f"(v[8 * j + 2 * i]));
+        else
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p[i]) : "f"(v[8 * j + 2 * i + 1]), "f"(v[8 * j + 2 * i]));
+      }
+      d4[j] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
 };
 
 template <typename E>
@@ -60,7 +111,7 @@ struct ElemDims {
   static constexpr int kUmmaK = 32 / sizeof(typename E::storage);    // K of one tcgen05.mma
 };
 
-enum EpiMode : int { kEpiHidden = 0, kEpiFinal = 1, kEpiRff = 2 };
+enum EpiMode : int { kEpiHidden = 0, kEpiFinal = 1, kEpiRff = 2, kEpiHiddenTanh = 3 };
 
 struct GemmArgs {
   // tile space: tile -> (group, m_tile, n_tile), n fastest
@@ -84,7 +135,6 @@ struct GemmArgs {
   int out_col0;
   int rows_valid;         // rows of the M axis (per group) that exist in `out`
   int cols_valid;
-  int act;                // 0 relu, 1 tanh
   int vec_ok;             // final: 16-byte aligned rows -> float4 stores
   float* rff_part;        // kEpiRff: [n_tiles][rff_part_stride] partial dots
   long long rff_part_stride;
@@ -101,6 +151,15 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 
 constexpr size_t gemm_smem_bytes() {
   return 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 3 * kBlockN * sizeof(float) + 256;
+}
+
+// cos(x) for the random-feature epilogue: two-constant Cody-Waite reduction to [-pi, pi] then the SFU
+// approximation (abs error < 1e-6 for |x| up to ~1e4, far inside the 1e-3 budget of the cost).
+__device__ __forceinline__ float fast_cos(float x) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.28318548202514648f, x);   // 2*pi rounded to fp32
+  r = fmaf(k, 1.74845553e-7f, r);                // 2*pi_fp32 - 2*pi
+  return __cosf(r);
 }
 
 template <typename E, int MODE>
@@ -245,75 +304,101 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
       const long long row = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
+      constexpr int kChunks = kBlockN / 32;
 
-      if constexpr (MODE == kEpiHidden) {
-        T* orow = static_cast<T*>(args.out) + size_t(g) * args.out_group_stride + row * args.out_pitch +
-                  args.out_col0 + n0;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          T v[32];
+      // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is processed, and the
+      // accumulator is handed back to the MMA warp as soon as the last chunk sits in registers.
+      uint32_t ra[32], rb[32];
+      ptx::tmem_ld_32x32(taddr, ra);
+
+      float dot = 0.f;  // kEpiRff
+      auto process = [&](const uint32_t (&r)[32], int c) {
+        const float4* b4 = reinterpret_cast<const float4*>(sm_bias + c * 32);
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + sm_bias[c * 32 + j];
-            x = args.act == 0 ? fmaxf(x, 0.f) : tanhf(x);
-            v[j] = E::cvt(x);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-          const uint4* src = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-          for (int j = 0; j < int(32 * sizeof(T) / 16); ++j) dst[j] = src[j];
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = b4[j];
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
         }
-      } else if constexpr (MODE == kEpiFinal) {
-        float* orow = static_cast<float*>(args.out) + size_t(g) * args.out_group_stride + row * args.out_pitch +
-                      args.out_col0 + n0;
-        const bool row_ok = row < args.rows_valid;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          float v[32];
+        if constexpr (MODE == kEpiHidden || MODE == kEpiHiddenTanh) {
+          T* orow = static_cast<T*>(args.out) + size_t(g) * args.out_group_stride + row * args.out_pitch +
+                    args.out_col0 + n0 + c * 32;
+          if constexpr (MODE == kEpiHiddenTanh) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaf(__uint_as_float(r[j]) + sm_bias[c * 32 + j], sm_scale[c * 32 + j], sm_shift[c * 32 + j]);
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            E::template store32<false>(orow, v);
+          } else {
+            E::template store32<true>(orow, v);
+          }
+        } else if constexpr (MODE == kEpiFinal) {
+          float* orow = static_cast<float*>(args.out) + size_t(g) * args.out_group_stride + row * args.out_pitch +
+                        args.out_col0 + n0 + c * 32;
+          const float4* s4 = reinterpret_cast<const float4*>(sm_scale + c * 32);
+          const float4* h4 = reinterpret_cast<const float4*>(sm_shift + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = s4[j], sh = h4[j];
+            v[4 * j + 0] = fmaf(v[4 * j + 0], sc.x, sh.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
+          }
           const int col = n0 + c * 32;
-          if (row_ok) {
+          if (row < args.rows_valid) {
             if (args.vec_ok && col + 32 <= args.cols_valid) {
-              float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+              float4* dst = reinterpret_cast<float4*>(orow);
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col + j < args.cols_valid) orow[c * 32 + j] = v[j];
+                if (col + j < args.cols_valid) orow[j] = v[j];
             }
           }
-        }
-      } else {  // kEpiRff
-        float* prow = args.out ? static_cast<float*>(args.out) + row * args.out_pitch + n0 : nullptr;
-        const bool row_ok = row < args.rows_valid;
-        float dot = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          const int col = n0 + c * 32;
+        } else {  // kEpiRff: phi = cos(pre-activation); dot with w (padded columns carry w == 0)
+          const float4* w4 = reinterpret_cast<const float4*>(sm_scale + c * 32);
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float f = cosf(__uint_as_float(r[j]) + sm_bias[c * 32 + j]);
-            dot = fmaf(f, sm_scale[c * 32 + j], dot);  // padded columns carry w == 0
-            if (prow != nullptr && row_ok && col + j < args.cols_valid) prow[c * 32 + j] = f * args.rff_phi_scale;
+          for (int j = 0; j < 32; ++j) f[j] = fast_cos(v[j]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = w4[j];
+            dot = fmaf(f[4 * j + 0], w.x, dot);
+            dot = fmaf(f[4 * j + 1], w.y, dot);
+            dot = fmaf(f[4 * j + 2], w.z, dot);
+            dot = fmaf(f[4 * j + 3], w.w, dot);
+          }
+          if (args.out != nullptr && row < args.rows_valid) {
+            float* prow = static_cast<float*>(args.out) + row * args.out_pitch + n0 + c * 32;
+            const int col = n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < args.cols_valid) prow[j] = f[j] * args.rff_phi_scale;
           }
         }
-        if (args.rff_part != nullptr && row_ok) args.rff_part[size_t(n_tile) * args.rff_part_stride + row] = dot;
-      }
+      };
 
-      ptx::tcgen05_fence_before();
-      ptx::mbar_arrive(&tmem_empty_bar[acc]);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+        process(ra, c);
+        ptx::tmem_ld_wait();
+        if (c + 2 < kChunks) {
+          ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+        } else {
+          ptx::tcgen05_fence_before();
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may overwrite it
+        }
+        process(rb, c + 1);
+      }
+      if constexpr (MODE == kEpiRff) {
+        if (args.rff_part != nullptr && row < args.rows_valid)
+          args.rff_part[size_t(n_tile) * args.rff_part_stride + row] = dot;
+      }
     }
   }
 

@@ -295,7 +295,6 @@ def run_ours(args):
 
     def one_step(i):
         k = i % ring
-        steps.zero_()
         eng.step_cost(states[k], actions[k], member, steps, w, LAMBDA_B, threshold, next_state=nxt, disc=disc,
                       done=done, cost=cst, ipm=ipm, bonus=bonus)
         if world > 1:  # rollout statistics (batch_reinforce.py:135-141): one small collective per step
