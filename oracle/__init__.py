@@ -8,8 +8,6 @@ oracle/ holds restatements of the reference's algorithms used to check the CUDA 
   imitation_oracle.py  numpy float64 restatement of DeepMimicCore's CalcRewardImitate and the kinematic
                        pipeline under it.  The reference C++ needs Eigen 3.3.7 + Bullet 2.88 + SWIG and
                        cannot be built here: PARITY UNPINNED, anchored on closed-form known answers.
-  imitation_c/         the same in plain C (gcc), used as the fast checker at full sizes and as the
-                       CPU baseline leg of bench.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
 package.  The product (amp_extensions_b200) never does.

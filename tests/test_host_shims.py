@@ -1,0 +1,152 @@
+"""Host-side mirror of the reference's plugin surface, without a GPU: the ensemble.pt save format
+(reference milo/milo/dynamics.py:110-131), constructor / attribute compatibility, SimEnv's reset protocol and
+pickling (gym-simenv/gym_simenv/envs/sim_env.py:48, 118-132, 270-285), termination tables (sim_env.py:100-116)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, HumanoidTermination, SimEnv
+from amp_extensions_b200 import _lib
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF_PT = os.path.join(GOLDEN_DIR, "ref_ensemble_tiny_dense.pt")
+
+
+def tiny_ensemble():
+    c = H.tiny_case("tiny_dense")
+    ds = AmpDataset(*c["ds"])
+    ens = DynamicsEnsemble(c["S"], c["A"], ds, None, num_models=c["N"], hidden_sizes=c["hidden"],
+                           dense_connect=True, activation="relu", transform=True, base_seed=100)
+    return c, ens
+
+
+def test_constructor_reproduces_the_reference_init_and_transforms():
+    """Same seeds, same layer construction order => bit-identical random init (dynamics.py:79, 184-196)."""
+    c, ens = tiny_ensemble()
+    for k, m in enumerate(ens.models):
+        for l, lin in enumerate(m.model.fc_layers):
+            assert torch.equal(lin.weight.data, c["ws"][k][l])
+            assert torch.equal(lin.bias.data, c["bs"][k][l])
+    for mine, ref in zip(ens.transformations, c["tf"]):
+        assert torch.equal(mine, ref)
+    m0 = ens.models[0]
+    assert torch.equal(m0.state_mean, c["tf"][0]) and torch.equal(m0.diff_scale, c["tf"][5])  # dynamics.py:128-131
+
+
+def test_loads_an_ensemble_pt_written_by_the_reference():
+    c, ens = tiny_ensemble()
+    for m in ens.models:  # scramble, then load the reference's file
+        for p in m.model.parameters():
+            p.data.zero_()
+    ens.load_ensemble(REF_PT)
+    for k, m in enumerate(ens.models):
+        for l, lin in enumerate(m.model.fc_layers):
+            assert torch.equal(lin.weight.data, c["ws"][k][l]) and torch.equal(lin.bias.data, c["bs"][k][l])
+    # optimizer state is carried through untouched so a later save keeps it (dynamics.py:385-392)
+    ref_sd = torch.load(REF_PT, map_location="cpu")
+    assert ens.models[0].get_state_dicts()["optim"].keys() == ref_sd[0]["optim"].keys()
+
+
+def test_save_ensemble_writes_the_reference_format(tmp_path):
+    c, ens = tiny_ensemble()
+    path = str(tmp_path / "ensemble.pt")
+    ens.save_ensemble(path)
+    mine = torch.load(path, map_location="cpu")
+    ref = torch.load(REF_PT, map_location="cpu")
+    assert isinstance(mine, list) and len(mine) == len(ref) == c["N"]
+    for a, b in zip(mine, ref):
+        assert set(a.keys()) == set(b.keys()) == {"model", "optim"}
+        assert list(a["model"].keys()) == list(b["model"].keys())
+        for k in a["model"]:
+            assert a["model"][k].dtype == b["model"][k].dtype and torch.equal(a["model"][k], b["model"][k])
+    with pytest.raises(AssertionError):  # dynamics.py:123
+        small = DynamicsEnsemble(c["S"], c["A"], AmpDataset(*c["ds"]), None, num_models=2, hidden_sizes=c["hidden"])
+        small.load_ensemble(path)
+
+
+def test_ensemble_pickles_without_its_device_handle():
+    _, ens = tiny_ensemble()
+    ens.threshold = 1.25
+    clone = pickle.loads(pickle.dumps(ens))
+    assert clone._eng is None and clone.threshold == 1.25 and len(clone.models) == len(ens.models)
+    assert all(m._ensemble is clone and m._index == k for k, m in enumerate(clone.models))
+    assert torch.equal(clone.models[1].model.fc_layers[0].weight, ens.models[1].model.fc_layers[0].weight)
+
+
+def test_training_is_left_to_the_reference_class():
+    _, ens = tiny_ensemble()
+    with pytest.raises(NotImplementedError):
+        ens.train()
+    with pytest.raises(NotImplementedError):
+        DynamicsEnsemble(4, 2, None, None, transform=False, use_resnet=True)
+
+
+def test_simenv_reset_protocol_and_member_round_robin():
+    """sim_env.py:118-119: first episode = member 0; every reset advances (c+1) % N (sim_env.py:282-283);
+    observations are float64 copies (sim_env.py:285)."""
+    c, ens = tiny_ensemble()
+    pool = np.arange(5 * c["S"], dtype=np.float32).reshape(5, c["S"])
+    env = SimEnv(ens, reset_states=pool, horizon=7, seed=3)
+    assert env.horizon == 7 and env.state_size == c["S"] and env.action_size == c["A"]
+    assert env.observation_space.shape == (c["S"],) and env.action_space.shape == (c["A"],)
+    assert env.dynamics is ens.models[0] and env.reset_counter == 0
+    seen = []
+    for i in range(5):
+        ob = env.reset()
+        assert ob.dtype == np.float64 and ob.shape == (c["S"],) and env.num_steps == 0
+        assert any(np.array_equal(ob, pool[j].astype(np.float64)) for j in range(5))
+        ob[0] = -1.0  # a copy: mutating it must not touch the env's state
+        assert env.get_observation()[0] != -1.0
+        seen.append(env.reset_counter)
+        assert env.dynamics is ens.models[env.reset_counter]
+    assert seen == [1, 2, 0, 1, 2]
+    assert env.seed_env(11) == 11
+    a = env.np_random.uniform()
+    env.seed_env(11)
+    assert env.np_random.uniform() == a
+    with pytest.raises(AssertionError):  # sim_env.py:152
+        fresh = SimEnv(ens, reset_states=pool)
+        fresh.step(np.zeros(c["A"]))
+
+
+def test_simenv_is_picklable_for_worker_pools():
+    """sampler.py:116-121 ships the env (and through it the ensemble) to Pool workers."""
+    c, ens = tiny_ensemble()
+    pool = np.zeros((2, c["S"]), dtype=np.float32)
+    env = SimEnv(ens, reset_states=pool, horizon=9, enable_velocity_check=True, seed=5)
+    clone = pickle.loads(pickle.dumps(env))
+    assert clone.horizon == 9 and clone.enable_velocity_check and clone._vec is None
+    assert clone.dynamic_ensemble._eng is None
+    assert clone.reset().shape == (c["S"],)
+    with pytest.raises(RuntimeError):
+        SimEnv(ens).reset()  # no simulator, no reset_fn, no reset_states
+
+
+def test_termination_tables_follow_sim_env():
+    """sim_env.py:102-104: offsets (pos_dim+rot_dim)*body + 1 over the fall-contact bodies; shapes and
+    diameters / heights from humanoid3d.txt BodyDefs."""
+    t = HumanoidTermination(horizon=300, enable_velocity_check=True).to_struct()
+    bodies = [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 12, 13, 14]
+    assert t.n_bodies == 13 and t.horizon == 300 and t.enable_velocity_check == 1 and t.vel_offset == 136
+    assert list(t.body_offset[:13]) == [9 * b + 1 for b in bodies]
+    shapes = [t.body_shape[i] for i in range(13)]
+    assert shapes == [0, 0, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0]
+    assert t.body_param0[0] == pytest.approx(0.18) and t.body_param0[3] == pytest.approx(0.11)
+    assert t.body_param1[3] == pytest.approx(0.30) and t.body_param1[6] == pytest.approx(0.135)
+    assert abs(t.vel_threshold - 100.0) < 1e-6 and t.pos_dim == 3
+    # dict-style BodyDefs as parsed from the character file work as well
+    defs = [dict(Shape="sphere", Param0=0.2, Param1=0.2), dict(Shape="box", Param0=1, Param1=1)]
+    t2 = HumanoidTermination(body_defs=defs, fall_contact_bodies=[0, 1]).to_struct()
+    assert t2.n_bodies == 2 and t2.body_shape[1] == _lib.SHAPE["box"] and t2.body_offset[1] == 10
+
+
+def test_amp_dataset_transformations_match_the_oracle():
+    from oracle import milo_oracle as mo
+    s, a, s2 = H.synth_dataset(300, 11, 3, 4)
+    mine = AmpDataset(s, a, s2).get_transformations(torch.device("cpu"))
+    for x, y in zip(mine, mo.get_transformations(s, a, s2)):
+        assert torch.equal(x, y)
