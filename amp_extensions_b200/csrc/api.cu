@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -15,6 +16,7 @@
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
 #include "imitation.cuh"
+#include "imitation_h3d.cuh"
 
 using namespace simstep;
 

@@ -14,11 +14,23 @@ pytestmark = pytest.mark.gpu
 REL = 1e-3
 
 
-@pytest.fixture(scope="module")
-def setup():
+@pytest.fixture(scope="module", params=["h3d", "generic"])
+def setup(request):
+    """Both reward kernels: the register-resident humanoid3d fast path (csrc/imitation_h3d.cuh, the default for
+    the built-in character) and the generic any-character kernel (csrc/imitation.cuh)."""
+    import os
     from amp_extensions_b200 import ImitationReward
     clip = io.Clip(H.spinkick_raw(), io.HUMANOID3D, "wrap")
-    return ImitationReward(), clip
+    old = os.environ.get("SIMSTEP_IMIT_GENERIC")
+    os.environ["SIMSTEP_IMIT_GENERIC"] = "1" if request.param == "generic" else "0"
+    try:
+        imit = ImitationReward()  # the kernel is chosen when the clip is loaded
+    finally:
+        if old is None:
+            os.environ.pop("SIMSTEP_IMIT_GENERIC", None)
+        else:
+            os.environ["SIMSTEP_IMIT_GENERIC"] = old
+    return imit, clip
 
 
 def close(x, ref, floor=1e-2, rel=REL):
@@ -102,6 +114,30 @@ def test_closed_form_terms_on_gpu(setup):
     terms = terms.cpu().numpy()
     for row, (k, val) in enumerate(want):
         assert terms[row, k] == pytest.approx(val, rel=REL)
+
+
+def test_unaligned_rows_and_ragged_tiles(setup):
+    """Row blocks that are not 16-byte aligned (no TMA bulk copy) and batch sizes that leave ragged tiles."""
+    imit, clip = setup
+    pose, vel, t, origin = H.perturbed_poses(301, seed=11, clip=clip)
+    args = [torch.from_numpy(a).float().cuda() for a in (pose, vel, t, origin)]
+    r = imit.reward(*args)
+    for lo, hi in ((1, 301), (3, 132), (0, 129), (2, 3), (0, 257)):
+        sub = [a[lo:hi].clone() for a in args]                        # aligned copies
+        assert torch.equal(imit.reward(*sub), r[lo:hi])
+    # misaligned base pointers: views into a buffer shifted by one float
+    buf_p = torch.empty(pose.size + 1, device="cuda"); buf_v = torch.empty(vel.size + 1, device="cuda")
+    vp = buf_p[1:].view(301, 43); vv = buf_v[1:].view(301, 43)
+    vp.copy_(args[0]); vv.copy_(args[1])
+    eng = imit.engine
+    import ctypes as C
+    out = torch.empty(301, device="cuda")
+    rc = eng.lib.simstep_imitation_reward(eng._h, C.c_void_p(vp.data_ptr()), C.c_void_p(vv.data_ptr()),
+                                          C.c_void_p(args[2].data_ptr()), C.c_void_p(args[3].data_ptr()), 301,
+                                          C.c_void_p(out.data_ptr()), None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, r)
 
 
 def test_rows_are_independent(setup):
