@@ -48,6 +48,8 @@ struct simstep_handle {
   int sm_count = 148;
   int esize = 4;  // bytes per GEMM operand element
   int bk = 32;    // elements per 128-byte swizzle row
+  int cg = 2;     // CTAs per GEMM tile: 2 = cta_group::2 pairs (256-row tiles), 1 = single-CTA tiles
+  int row_align = 256;  // workspace rows are padded to whole tiles
   int S = 0, A = 0, N = 0, L = 0;
   int XP = 0, HT = 0, SP = 0;
   std::vector<Layer> layers;  // L hidden + 1 final
@@ -60,7 +62,7 @@ struct simstep_handle {
   void* xbuf = nullptr;
   void* hbuf = nullptr;
   float* dws = nullptr;
-  CUtensorMap tmap_x, tmap_h;
+  CUtensorMap tmap_x, tmap_h, tmap_dws;
 
   // RFF cost
   bool have_rff = false;
@@ -161,33 +163,56 @@ int encode_operand(simstep_handle* h, CUtensorMap* map, int prec, void* base, lo
   return SIMSTEP_OK;
 }
 
-template <typename E, int MODE>
+template <typename E, int MODE, int CG>
 int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
-                  const GemmArgs& ga, int sm_count, cudaStream_t st) {
+                  const CUtensorMap& out, const GemmArgs& ga, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<E, MODE>;
+  auto kern = gemm_tcgen05_kernel<E, MODE, CG>;
+  constexpr size_t smem = GemmShape<CG>::smem_bytes();
   if (!attr_set) {
-    CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gemm_smem_bytes())));
+    CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_set = true;
   }
   const int total = ga.m_tiles * ga.n_tiles * ga.groups;
   if (total <= 0) return SIMSTEP_OK;
-  const int grid = total < sm_count ? total : sm_count;
-  kern<<<grid, kGemmThreads, gemm_smem_bytes(), st>>>(ax, ah, b, ga);
+  // persistent: one CTA (CG = 1) or one CTA pair (CG = 2) per tile slot, at most one CTA per SM
+  const int slots = std::min(total, sm_count / CG);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(slots * CG));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, ax, ah, b, out, ga));
   g_launches++;
-  CU_TRY(h, cudaGetLastError());
   return SIMSTEP_OK;
 }
 
 template <int MODE>
-int launch_gemm(simstep_handle* h, int prec, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
-                const GemmArgs& ga, int sm_count, cudaStream_t st) {
+int launch_gemm(simstep_handle* h, int prec, int cg, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
+                const CUtensorMap& out, const GemmArgs& ga, int sm_count, cudaStream_t st) {
+#define SIMSTEP_GEMM_CASE(ELEM)                                                                   \
+  return cg == 2 ? launch_gemm_t<ELEM, MODE, 2>(h, ax, ah, b, out, ga, sm_count, st)               \
+                 : launch_gemm_t<ELEM, MODE, 1>(h, ax, ah, b, out, ga, sm_count, st)
   switch (prec) {
-    case SIMSTEP_PREC_TF32: return launch_gemm_t<ElemTF32, MODE>(h, ax, ah, b, ga, sm_count, st);
-    case SIMSTEP_PREC_FP16: return launch_gemm_t<ElemF16, MODE>(h, ax, ah, b, ga, sm_count, st);
-    case SIMSTEP_PREC_BF16: return launch_gemm_t<ElemBF16, MODE>(h, ax, ah, b, ga, sm_count, st);
+    case SIMSTEP_PREC_TF32: SIMSTEP_GEMM_CASE(ElemTF32);
+    case SIMSTEP_PREC_FP16: SIMSTEP_GEMM_CASE(ElemF16);
+    case SIMSTEP_PREC_BF16: SIMSTEP_GEMM_CASE(ElemBF16);
   }
+#undef SIMSTEP_GEMM_CASE
   return fail(h, SIMSTEP_EINVAL, "unknown precision");
+}
+
+// CTAs per GEMM tile: pairs unless SIMSTEP_GEMM_CG=1 asks for single-CTA tiles (bring-up / A-B comparisons)
+int gemm_cta_group() {
+  const char* e = std::getenv("SIMSTEP_GEMM_CG");
+  return (e && e[0] == '1') ? 1 : 2;
 }
 
 int grid_for(long long work_items, int threads, int sm_count) {
@@ -230,12 +255,12 @@ void free_workspace(simstep_handle* h) {
 
 long long chunk_limit(const simstep_handle* h) {
   long long c = h->cfg.max_chunk_envs > 0 ? h->cfg.max_chunk_envs : 65536;
-  return round_up(c, kBlockM);
+  return round_up(c, h->row_align);
 }
 
 // Workspace for `rows` env rows per pass (grown on demand, never shrunk).
 int ensure_workspace(simstep_handle* h, long long rows) {
-  rows = round_up(rows < 1 ? 1 : rows, kBlockM);
+  rows = round_up(rows < 1 ? 1 : rows, h->row_align);
   if (rows > chunk_limit(h)) rows = chunk_limit(h);
   if (rows <= h->cap_rows && (!h->have_rff || h->rffin)) return SIMSTEP_OK;
   if (rows < h->cap_rows) rows = h->cap_rows;
@@ -256,6 +281,10 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     } else {
       h->tmap_h = h->tmap_x;
     }
+    // fp32 delta workspace, written by the final layer's TMA-store epilogue (32-float x 128-row boxes)
+    rc = encode_operand(h, &h->tmap_dws, SIMSTEP_PREC_TF32, h->dws, h->SP, static_cast<long long>(h->N) * rows, h->SP,
+                        kBlockM);
+    if (rc) return rc;
   }
   if (h->have_rff) {
     const int rka = h->rff_split ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
@@ -282,7 +311,7 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
 // prep + all layer GEMMs for rows [0, n) of a chunk; leaves un-normalised member
 // deltas in h->dws[N][cap_rows][SP].
 int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st) {
-  const long long rows_pad = round_up(n, kBlockM);
+  const long long rows_pad = round_up(n, h->row_align);
   {
   ProfScope ps(h, SIMSTEP_PROF_PREP, st);
   switch (h->cfg.precision) {
@@ -296,7 +325,7 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   for (int l = 0; l <= h->L; ++l) {
     const Layer& ly = h->layers[l];
     GemmArgs ga{};
-    ga.m_tiles = int(rows_pad / kBlockM);
+    ga.m_tiles = int(rows_pad / (kBlockM * h->cg));
     ga.n_tiles = ly.o_pad / kBlockN;
     ga.groups = h->N;
     ga.kb_x = ly.kb_x;
@@ -306,28 +335,22 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
     ga.ax_rows_per_group = 0;
     ga.b_rows_per_group = ly.o_pad;
     ga.bias = ly.bias;
+    ga.out_rows_per_group = int(h->cap_rows);
     int rc;
     if (l < h->L) {
-      ga.out = h->hbuf;
-      ga.out_pitch = h->HT;
-      ga.out_group_stride = h->cap_rows * static_cast<long long>(h->HT);
+      // bias + activation straight into this layer's K-slice of the concat buffer
       ga.out_col0 = ly.out_col0;
-      ga.rows_valid = int(h->cap_rows);
-      ga.cols_valid = ly.o_pad;
       rc = h->cfg.activation == SIMSTEP_ACT_RELU
-               ? launch_gemm<kEpiHidden>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st)
-               : launch_gemm<kEpiHiddenTanh>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
+               ? launch_gemm<kEpiHidden>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_h, ga,
+                                         h->sm_count, st)
+               : launch_gemm<kEpiHiddenTanh>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_h, ga,
+                                             h->sm_count, st);
     } else {
-      ga.out = h->dws;
-      ga.out_pitch = h->SP;
-      ga.out_group_stride = h->cap_rows * static_cast<long long>(h->SP);
       ga.out_col0 = 0;
-      ga.rows_valid = int(h->cap_rows);
-      ga.cols_valid = h->SP;
-      ga.vec_ok = 1;
       ga.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
       ga.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
-      rc = launch_gemm<kEpiFinal>(h, h->cfg.precision, h->tmap_x, h->tmap_h, ly.tmap_w, ga, h->sm_count, st);
+      rc = launch_gemm<kEpiFinal>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_dws, ga,
+                                  h->sm_count, st);
     }
     if (rc) return rc;
   }
@@ -366,7 +389,7 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
 
 int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStream_t st) {
   ProfScope ps(h, SIMSTEP_PROF_RFF_PACK, st);
-  const long long rows_pad = round_up(n, kBlockM);
+  const long long rows_pad = round_up(n, h->row_align);
   const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
   switch (h->cfg.precision) {
     case SIMSTEP_PREC_TF32:
@@ -390,7 +413,7 @@ int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStrea
 int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* phi, cudaStream_t st) {
   ProfScope ps(h, SIMSTEP_PROF_RFF_GEMM, st);
   GemmArgs ga{};
-  ga.m_tiles = int(round_up(n, kBlockM) / kBlockM);
+  ga.m_tiles = int(round_up(n, h->row_align) / (kBlockM * h->cg));
   ga.n_tiles = h->D_pad / kBlockN;
   ga.groups = 1;
   // K loop: [hi | lo] through the first map, then the hi block again (x_hi * W_lo) through the second
@@ -408,7 +431,8 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
   ga.rff_part = w_pad ? h->rff_part : nullptr;
   ga.rff_part_stride = h->cap_rows;
   ga.rff_phi_scale = float(std::sqrt(2.0 / h->D));
-  return launch_gemm<kEpiRff>(h, h->cfg.precision, h->tmap_rffin, h->tmap_rffin, h->tmap_rffw, ga, h->sm_count, st);
+  return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_rffin, h->tmap_rffin, h->tmap_rffw, h->tmap_rffin, ga,
+                              h->sm_count, st);
 }
 
 int launch_combine(simstep_handle* h, const float* disc, long long n, float lambda_b, float threshold, float c_min,
@@ -486,6 +510,8 @@ int simstep_create(const simstep_config* cfg, simstep_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   h->esize = cfg->precision == SIMSTEP_PREC_TF32 ? 4 : 2;
   h->bk = 128 / h->esize;
+  h->cg = gemm_cta_group();
+  h->row_align = kBlockM * h->cg;
   h->S = cfg->state_dim;
   h->A = cfg->action_dim;
   h->N = cfg->n_models;
@@ -608,7 +634,7 @@ int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host, c
     }
     cudaFree(tmp);
     int rc = encode_operand(h, &ly.tmap_w, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
-                            ly.k_pad, kBlockN);
+                            ly.k_pad, kBlockN / h->cg);
     if (rc) return rc;
   }
   // transforms
@@ -699,7 +725,7 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   }
   CU_TRY(h, cudaDeviceSynchronize());
   cudaFree(tmp);
-  int rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN);
+  int rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN / h->cg);
   if (rc) return rc;
   h->have_rff = true;
   return SIMSTEP_OK;
@@ -904,19 +930,21 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
     return fail(nullptr, SIMSTEP_EINVAL, "bad argument");
   simstep_handle* h = nullptr;  // errors go to the create-error slot
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cg = gemm_cta_group();
   const int es = precision == SIMSTEP_PREC_TF32 ? 4 : 2;
   const int bk = 128 / es;
-  const long long m_pad = round_up(m, kBlockM), n_pad = round_up(n, kBlockN), k_pad = round_up(k, 64);
+  const long long m_pad = round_up(m, kBlockM * cg), n_pad = round_up(n, kBlockN), k_pad = round_up(k, 64);
   cudaDeviceProp prop;
   int dev = 0;
   CU_TRY(h, cudaGetDevice(&dev));
   CU_TRY(h, cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail(nullptr, SIMSTEP_ENODEV, "libsimstep is built for sm_100a only");
   void *ap = nullptr, *bp = nullptr;
-  float* biasp = nullptr;
+  float *biasp = nullptr, *dp = nullptr;  // dp: padded fp32 output [groups][m_pad][n_pad] of the TMA-store epilogue
   CU_TRY(h, cudaMalloc(&ap, size_t(groups) * m_pad * k_pad * es));
   CU_TRY(h, cudaMalloc(&bp, size_t(groups) * n_pad * k_pad * es));
   CU_TRY(h, cudaMalloc(&biasp, size_t(groups) * n_pad * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&dp, size_t(groups) * m_pad * n_pad * sizeof(float)));
   CU_TRY(h, cudaMemsetAsync(ap, 0, size_t(groups) * m_pad * k_pad * es, st));
   CU_TRY(h, cudaMemsetAsync(bp, 0, size_t(groups) * n_pad * k_pad * es, st));
   CU_TRY(h, cudaMemsetAsync(biasp, 0, size_t(groups) * n_pad * sizeof(float), st));
@@ -938,12 +966,13 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
     cudaError_t pe = cudaStreamSynchronize(st);
     if (pe != cudaSuccess) rc = fail(nullptr, SIMSTEP_ECUDA, std::string("debug gemm pack stage: ") + cudaGetErrorString(pe));
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, td;
   if (!rc) rc = encode_operand(h, &ta, precision, ap, k_pad, groups * m_pad, k_pad, kBlockM);
-  if (!rc) rc = encode_operand(h, &tb, precision, bp, k_pad, groups * n_pad, k_pad, kBlockN);
+  if (!rc) rc = encode_operand(h, &tb, precision, bp, k_pad, groups * n_pad, k_pad, kBlockN / cg);
+  if (!rc) rc = encode_operand(h, &td, SIMSTEP_PREC_TF32, dp, n_pad, groups * m_pad, n_pad, kBlockM);
   if (!rc) {
     GemmArgs ga{};
-    ga.m_tiles = int(m_pad / kBlockM);
+    ga.m_tiles = int(m_pad / (kBlockM * cg));
     ga.n_tiles = int(n_pad / kBlockN);
     ga.groups = groups;
     ga.kb_x = 0;
@@ -952,18 +981,21 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
     ga.a_rows_per_group = int(m_pad);
     ga.b_rows_per_group = int(n_pad);
     ga.bias = biasp;
-    ga.out = d_dev;
-    ga.out_pitch = n;
-    ga.out_group_stride = m * static_cast<long long>(n);
-    ga.rows_valid = int(m);
-    ga.cols_valid = n;
-    ga.vec_ok = (n % 4 == 0) ? 1 : 0;
-    rc = launch_gemm<kEpiFinal>(h, precision, ta, ta, tb, ga, prop.multiProcessorCount, st);
+    ga.out_rows_per_group = int(m_pad);
+    ga.out_col0 = 0;
+    rc = launch_gemm<kEpiFinal>(h, precision, cg, ta, ta, tb, td, ga, prop.multiProcessorCount, st);
+  }
+  if (!rc) {
+    const long long total = static_cast<long long>(groups) * m * n;
+    extract_delta_kernel<<<grid_for(total, 256, prop.multiProcessorCount), 256, 0, st>>>(dp, m_pad, int(n_pad), groups, n,
+                                                                                         m, d_dev, m, 0);
+    g_launches++;
   }
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(ap);
   cudaFree(bp);
   cudaFree(biasp);
+  cudaFree(dp);
   if (!rc && e != cudaSuccess) return fail(nullptr, SIMSTEP_ECUDA, std::string("debug gemm: ") + cudaGetErrorString(e));
   return rc;
 }
