@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/simstep.h"
@@ -126,6 +127,23 @@ int fail(simstep_handle* h, int code, const std::string& msg) {
                                         std::to_string(__LINE__) + ")");                                 \
   } while (0)
 
+// Launch with programmatic stream serialization (see ptx::grid_dep_wait): the kernel may be scheduled while the
+// previous kernel of the stream drains; every kernel launched this way starts with grid_dep_wait().
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -182,13 +200,15 @@ int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& a
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, ax, ah, b, out, ga));
   g_launches++;
   return SIMSTEP_OK;
@@ -300,24 +320,27 @@ int ensure_workspace(simstep_handle* h, long long rows) {
 
 template <typename E>
 void launch_prep(simstep_handle* h, const float* s, const float* a, long long n, long long rows_pad,
-                 cudaStream_t st) {
+                 const float* w_src, cudaStream_t st) {
   const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
-  prep_input_kernel<E><<<grid, kPrepThreads, 0, st>>>(
-      s, a, h->S, h->A, h->XP, n, rows_pad, h->cfg.transform ? h->tf_dev : nullptr,
-      static_cast<typename E::storage*>(h->xbuf));
+  launch_pdl(prep_input_kernel<E>, dim3(grid), dim3(kPrepThreads), 0, st, s, a, h->S, h->A, h->XP, n, rows_pad,
+             h->cfg.transform ? h->tf_dev : nullptr, static_cast<typename E::storage*>(h->xbuf), w_src,
+             w_src ? h->rff_wpad : nullptr, h->D);
   g_launches++;
 }
 
 // prep + all layer GEMMs for rows [0, n) of a chunk; leaves un-normalised member
 // deltas in h->dws[N][cap_rows][SP].
-int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st) {
+// w_stage != nullptr: the prep kernel also copies the cost weights into h->rff_wpad (no separate memcpy node
+// between the step's kernels).
+int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st,
+                       const float* w_stage = nullptr) {
   const long long rows_pad = round_up(n, h->row_align);
   {
   ProfScope ps(h, SIMSTEP_PROF_PREP, st);
   switch (h->cfg.precision) {
-    case SIMSTEP_PREC_TF32: launch_prep<ElemTF32>(h, s, a, n, rows_pad, st); break;
-    case SIMSTEP_PREC_FP16: launch_prep<ElemF16>(h, s, a, n, rows_pad, st); break;
-    default: launch_prep<ElemBF16>(h, s, a, n, rows_pad, st);
+    case SIMSTEP_PREC_TF32: launch_prep<ElemTF32>(h, s, a, n, rows_pad, w_stage, st); break;
+    case SIMSTEP_PREC_FP16: launch_prep<ElemF16>(h, s, a, n, rows_pad, w_stage, st); break;
+    default: launch_prep<ElemBF16>(h, s, a, n, rows_pad, w_stage, st);
   }
   }
   CU_TRY(h, cudaGetLastError());
@@ -357,25 +380,33 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   return SIMSTEP_OK;
 }
 
+// fuse_rff: also write the RFF operand rows of [s; s'] (input_type 'ss'), replacing rff_pack_kernel
 int launch_post(simstep_handle* h, const float* state, const int32_t* member, int32_t* num_steps, long long n,
-                float* next_state, float* disc, uint8_t* done, cudaStream_t st) {
+                float* next_state, float* disc, uint8_t* done, cudaStream_t st, bool fuse_rff = false) {
   if (h->S > kPostMaxElems) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
   ProfScope ps(h, SIMSTEP_PROF_POST, st);
-  const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, static_cast<long long>(h->sm_count) * 8));
+  // one warp per row and one row per warp: the block scheduler balances the tail, no grid-stride quantisation
+  const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, 1LL << 30));
   const size_t smem = size_t(kPostWarps) * ((h->S + 3) & ~3) * sizeof(float);
   // float2 lanes need 8-byte aligned rows: even S and 8-byte aligned base pointers
   const bool vec2 = (h->S % 2 == 0) && (reinterpret_cast<uintptr_t>(state) % 8 == 0) &&
                     (reinterpret_cast<uintptr_t>(next_state) % 8 == 0);
+  PostRff rff{};
+  if (fuse_rff) {
+    if (!vec2) return fail(h, SIMSTEP_EINVAL, "internal: fused RFF operand needs the float2 path");
+    rff.out = h->rffin;
+    rff.prec = h->cfg.precision;
+    rff.RK = h->RK;
+    rff.split = h->rff_split;
+  }
 #define POST_CASE(NM)                                                                                          \
   case NM:                                                                                                     \
     if (vec2)                                                                                                  \
-      post_step_kernel<NM, 2><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member, \
-                                                                     num_steps, h->S, n, next_state, disc, done, \
-                                                                     h->term);                                 \
+      launch_pdl(post_step_kernel<NM, 2>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->SP, \
+                 state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     else                                                                                                       \
-      post_step_kernel<NM, 1><<<blocks, kPostWarps * 32, smem, st>>>(h->dws, h->cap_rows, h->SP, state, member, \
-                                                                     num_steps, h->S, n, next_state, disc, done, \
-                                                                     h->term);                                 \
+      launch_pdl(post_step_kernel<NM, 1>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->SP, \
+                 state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     break;
   switch (h->N) {
     POST_CASE(1) POST_CASE(2) POST_CASE(3) POST_CASE(4) POST_CASE(5) POST_CASE(6) POST_CASE(7) POST_CASE(8)
@@ -393,16 +424,16 @@ int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStrea
   const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
   switch (h->cfg.precision) {
     case SIMSTEP_PREC_TF32:
-      rff_pack_kernel<ElemTF32><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
-                                                      static_cast<float*>(h->rffin));
+      launch_pdl(rff_pack_kernel<ElemTF32>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+                 rows_pad, static_cast<float*>(h->rffin));
       break;
     case SIMSTEP_PREC_FP16:
-      rff_pack_kernel<ElemF16><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
-                                                     static_cast<__half*>(h->rffin));
+      launch_pdl(rff_pack_kernel<ElemF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+                 rows_pad, static_cast<__half*>(h->rffin));
       break;
     default:
-      rff_pack_kernel<ElemBF16><<<grid, kPrepThreads, 0, st>>>(src, h->rff_in, h->RK, h->rff_split, n, rows_pad,
-                                                      static_cast<__nv_bfloat16*>(h->rffin));
+      launch_pdl(rff_pack_kernel<ElemBF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+                 rows_pad, static_cast<__nv_bfloat16*>(h->rffin));
   }
   g_launches++;
   CU_TRY(h, cudaGetLastError());
@@ -438,9 +469,9 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
 int launch_combine(simstep_handle* h, const float* disc, long long n, float lambda_b, float threshold, float c_min,
                    float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus, cudaStream_t st) {
   ProfScope ps(h, SIMSTEP_PROF_COMBINE, st);
-  cost_combine_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(
-      h->rff_part, h->cap_rows, h->D_pad / kBlockN, float(std::sqrt(2.0 / h->D)), disc, n, lambda_b, threshold, c_min,
-      c_max, clamp_cost, dot, cost, ipm, bonus);
+  launch_pdl(cost_combine_kernel, dim3(grid_for(n, 256, h->sm_count)), dim3(256), 0, st, h->rff_part, h->cap_rows,
+             h->D_pad / kBlockN, float(std::sqrt(2.0 / h->D)), disc, n, lambda_b, threshold, c_min, c_max, clamp_cost, dot,
+             cost, ipm, bonus);
   g_launches++;
   CU_TRY(h, cudaGetLastError());
   return SIMSTEP_OK;
@@ -800,19 +831,23 @@ int simstep_step_cost(simstep_handle* h, const float* state_dev, const float* ac
   if (next_state_dev == state_dev) return fail(h, SIMSTEP_EINVAL, "next_state must not alias state in step_cost");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((rc = ensure_workspace(h, n_envs))) return rc;
-  if ((rc = stage_w(h, w_dev, st))) return rc;
   for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
     const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
     const float* s = state_dev + r0 * h->S;
     const float* a = action_dev + r0 * h->A;
     float* s2 = next_state_dev + r0 * h->S;
-    if ((rc = run_ensemble_chunk(h, s, a, n, st))) return rc;
+    if ((rc = run_ensemble_chunk(h, s, a, n, st, r0 == 0 ? w_dev : nullptr))) return rc;
+    // input_type 'ss' with float2-able rows: the post kernel writes the cost features' operand rows itself
+    const bool fuse = h->rff_in == 2 * h->S && h->S % 2 == 0 && reinterpret_cast<uintptr_t>(s) % 8 == 0 &&
+                      reinterpret_cast<uintptr_t>(s2) % 8 == 0;
     if ((rc = launch_post(h, s, member_dev ? member_dev + r0 : nullptr, num_steps_dev ? num_steps_dev + r0 : nullptr,
-                          n, s2, disc_dev + r0, done_dev ? done_dev + r0 : nullptr, st)))
+                          n, s2, disc_dev + r0, done_dev ? done_dev + r0 : nullptr, st, fuse)))
       return rc;
-    RffSrc src;
-    if ((rc = rff_sources(h, s, a, s2, &src))) return rc;
-    if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    if (!fuse) {
+      RffSrc src;
+      if ((rc = rff_sources(h, s, a, s2, &src))) return rc;
+      if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    }
     if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
     if ((rc = launch_combine(h, disc_dev + r0, n, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
                              cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,

@@ -65,8 +65,14 @@ __global__ void __launch_bounds__(kPrepThreads)
 prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A, int XP,
                   long long n_rows, long long rows_pad,
                   const float* __restrict__ tf /* mean_s|scale_s|mean_a|scale_a or null */,
-                  typename E::storage* __restrict__ x) {
+                  typename E::storage* __restrict__ x, const float* __restrict__ w_src, float* __restrict__ w_dst,
+                  int w_len) {
   using P = typename Pair<typename E::storage>::type;
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  // the step's cost weights ride along: block 0 stages w into the zero-padded vector the RFF epilogue reads
+  if (w_src != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < w_len; i += kPrepThreads) w_dst[i] = w_src[i];
   for (int c0 = 2 * threadIdx.x; c0 < XP; c0 += 2 * kPrepThreads) {
     // per-column constants hoisted out of the row loop
     float mean[2] = {0.f, 0.f}, scale[2] = {1.f, 1.f};
@@ -108,6 +114,8 @@ __global__ void __launch_bounds__(kPrepThreads)
 rff_pack_kernel(RffSrc src, int in_dim, int RK, int split, long long n_rows, long long rows_pad,
                 typename E::storage* __restrict__ out) {
   using P = typename Pair<typename E::storage>::type;
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   const int pitch = split ? 2 * RK : RK;
   for (int c0 = 2 * threadIdx.x; c0 < RK; c0 += 2 * kPrepThreads) {
     const float* base[2] = {nullptr, nullptr};
@@ -188,16 +196,39 @@ struct PostVec<2> {
   }
 };
 
+// RFF operand row of the fused step: [hi(s) | hi(s') | 0][lo(s) | lo(s') | 0] (see rff_pack_kernel), written by
+// the same warp that produced s'.  prec: SIMSTEP_PREC_*; out == nullptr: not fused.
+struct PostRff {
+  void* out;
+  int prec;
+  int RK;
+  int split;
+};
+
+template <typename E>
+__device__ __forceinline__ void post_rff_store(const PostRff& r, long long row, int col, float2 v) {
+  using T = typename E::storage;
+  using P = typename Pair<T>::type;
+  const int pitch = r.split ? 2 * r.RK : r.RK;
+  T* orow = static_cast<T*>(r.out) + row * pitch;
+  const P hi = make_pair_cvt<E>(v.x, v.y);
+  *reinterpret_cast<P*>(orow + col) = hi;
+  if (r.split)
+    *reinterpret_cast<P*>(orow + r.RK + col) =
+        make_pair_cvt<E>(v.x - static_cast<float>(hi.x), v.y - static_cast<float>(hi.y));
+}
+
 // One warp per env row (reference: sim_env.py:140-173 for the step and the
 // termination test, dynamics.py:134-143 for the discrepancy).
 //   delta  [NM][delta_rows][SP] fp32 workspace of the final GEMM, row = chunk-local
 //   state  [E][S], next_state [E][S] (may alias state)
 // VEC = 2 when S is even: every row then starts 8-byte aligned and lanes move float2.
 template <int NM, int VEC>
-__global__ void __launch_bounds__(kPostWarps * 32)
+__global__ void __launch_bounds__(kPostWarps * 32, NM <= 4 ? 3 : 2)
 post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, const float* state,
                  const int32_t* __restrict__ member, int32_t* num_steps, int S, long long n_rows,
-                 float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done, const TermConst tc) {
+                 float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done, const TermConst tc,
+                 const PostRff rff) {
   using V = typename PostVec<VEC>::type;
   constexpr int kPerLane = kPostMaxElems / (32 * VEC);
   extern __shared__ float sm_rows[];  // [kPostWarps][S]
@@ -208,6 +239,8 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
   const long long n_warps = static_cast<long long>(gridDim.x) * kPostWarps;
   constexpr int NP = NM * (NM - 1) / 2;
   const int nvec = S / VEC;
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
 
   for (long long row = warp_global; row < n_rows; row += n_warps) {
     V d[NM][kPerLane];
@@ -273,6 +306,26 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
           srow_v[j] = nxt[i];
         }
       }
+      if constexpr (VEC == 2) {
+        if (rff.out != nullptr) {  // cost features' operand rows for input_type 'ss' (linear_cost.py:119)
+#pragma unroll
+          for (int i = 0; i < kPerLane; ++i) {
+            const int j = lane + 32 * i;
+            if (j < nvec) {
+              if (rff.prec == SIMSTEP_PREC_FP16) {
+                post_rff_store<ElemF16>(rff, row, 2 * j, sv[i]);
+                post_rff_store<ElemF16>(rff, row, S + 2 * j, nxt[i]);
+              } else if (rff.prec == SIMSTEP_PREC_TF32) {
+                post_rff_store<ElemTF32>(rff, row, 2 * j, sv[i]);
+                post_rff_store<ElemTF32>(rff, row, S + 2 * j, nxt[i]);
+              } else {
+                post_rff_store<ElemBF16>(rff, row, 2 * j, sv[i]);
+                post_rff_store<ElemBF16>(rff, row, S + 2 * j, nxt[i]);
+              }
+            }
+          }
+        }
+      }
       int steps = 0;
       if (num_steps != nullptr) {
         steps = num_steps[row] + 1;
@@ -332,6 +385,8 @@ __global__ void cost_combine_kernel(const float* __restrict__ part, long long pa
                                     float threshold, float c_min, float c_max, int clamp_cost,
                                     float* __restrict__ dot_out, float* __restrict__ cost, float* __restrict__ ipm,
                                     float* __restrict__ bonus) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
        row += static_cast<long long>(gridDim.x) * blockDim.x) {
     float dot = 0.f;

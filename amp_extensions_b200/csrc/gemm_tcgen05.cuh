@@ -209,6 +209,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // everything above overlapped the previous kernel's tail; its outputs are read (and ours written) from here on
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
 
   const int total_tiles = args.m_tiles * args.n_tiles * args.groups;
   const int kb_total = args.kb_x + args.kb_h;

@@ -24,6 +24,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- programmatic dependent launch ------------------------------------------
+// Kernels of one env step are launched with programmaticStreamSerialization: a kernel may start while its
+// predecessor drains.  grid_dep_wait() blocks until the predecessor has completed and flushed its writes (it
+// is a no-op for a normal launch); grid_dep_launch() lets the successor's CTAs be scheduled from here on.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier -------------------------------------------------------------
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

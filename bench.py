@@ -49,6 +49,23 @@ def fused_bytes_per_env_step(n_models=N_MODELS, s=S_DIM, a=A_DIM):
     return s * 4 + a * 4 + n_models * s * 4 + s * 4 + 16 + 1 + 4 + 4
 
 
+def post_bytes_per_env_step(precision, n_models=N_MODELS, s=S_DIM, rff_k=512, split=True):
+    """Algorithmic bytes of post_step_kernel per env: read N member deltas + s, write s' (+ disc, done, member,
+    step counter), and - fused since round 1 - write the cost features' operand row [hi | lo] of [s; s']."""
+    esize = 4 if precision == "tf32" else 2
+    return s * 4 * (2 + n_models) + 17 + rff_k * esize * (2 if split else 1)
+
+
+def hbm_roofline(post_ms, envs, precision, peaks):
+    if not post_ms:
+        return None
+    b = post_bytes_per_env_step(precision)
+    gbs = b * envs / (post_ms * 1e-3) / 1e9
+    return {"kernel": "post_step_kernel (next state + discrepancy + termination + RFF operand rows)", "bound": "hbm",
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "algorithmic_bytes_per_env_step": b, "ms_per_step": post_ms}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -397,13 +414,7 @@ def run_ours(args):
                 "ms_per_step": gemm_ms,
             },
             "kernels_ms_per_step": per_step,
-            "roofline_hbm": {
-                "kernel": "post_step_kernel (next state + discrepancy + termination)", "bound": "hbm",
-                "achieved": (S_DIM * 4 * (2 + N_MODELS) + 17) * E / (post_ms * 1e-3) / 1e9 if post_ms else None,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ((S_DIM * 4 * (2 + N_MODELS) + 17) * E / (post_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                if post_ms else None,
-            },
+            "roofline_hbm": hbm_roofline(post_ms, E, args.precision, peaks),
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
