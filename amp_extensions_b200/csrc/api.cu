@@ -18,6 +18,7 @@
 #include "gemm_tcgen05.cuh"
 #include "imitation.cuh"
 #include "imitation_h3d.cuh"
+#include "policy.cuh"
 
 using namespace simstep;
 
@@ -78,6 +79,7 @@ struct simstep_handle {
 
   TermConst term{};
   ImitConst* imit_dev = nullptr;
+  void* policy = nullptr;  // PolicyStore (policy_api.inc)
   bool have_clip = false;
   int dof = 0;
 
@@ -495,6 +497,7 @@ int rff_sources(simstep_handle* h, const float* s, const float* a, const float* 
 }
 
 void free_clip(simstep_handle* h);
+void free_policy(simstep_handle* h);
 
 int check_step_ready(simstep_handle* h, long long n_envs) {
   if (!h) return SIMSTEP_EINVAL;
@@ -614,6 +617,7 @@ int simstep_destroy(simstep_handle* h) {
   cudaFree(h->rff_wpad);
   cudaFree(h->colsum_partial);
   free_clip(h);
+  free_policy(h);
   delete h;
   return SIMSTEP_OK;
 }
@@ -1038,3 +1042,4 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
 }  // extern "C"
 
 #include "imitation_api.inc"
+#include "policy_api.inc"

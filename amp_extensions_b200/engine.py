@@ -289,3 +289,57 @@ class Engine:
         self._check(self.lib.simstep_clip_sample(self._h, _ptr(kin_time), _ptr(kin_origin), E, _ptr(pose), _ptr(vel),
                                                  _stream(self.device)))
         return pose, vel
+
+    # -- rollout helpers ----------------------------------------------------------------
+    def load_policy(self, weights, biases, nonlinearity="tanh", in_shift=None, in_scale=None, out_shift=None,
+                    out_scale=None, log_std=None):
+        """mjrl's Gaussian MLP policy (mjrl/mjrl/policies/gaussian_mlp.py:6-104): nn.Linear weights/biases of
+        FCNetwork.fc_layers, its four transformations and the policy's log_std (CPU tensors / arrays)."""
+        nl = len(weights)
+        ws = [torch.as_tensor(w).detach().to("cpu", torch.float32).contiguous() for w in weights]
+        bs = [torch.as_tensor(b).detach().to("cpu", torch.float32).contiguous() for b in biases]
+        lin = (C.c_int32 * nl)(*[int(w.shape[1]) for w in ws])
+        lout = (C.c_int32 * nl)(*[int(w.shape[0]) for w in ws])
+        wp = (C.c_void_p * nl)(*[w.data_ptr() for w in ws])
+        bp = (C.c_void_p * nl)(*[b.data_ptr() for b in bs])
+
+        def vec(x):
+            return None if x is None else torch.as_tensor(x).detach().to("cpu", torch.float32).contiguous()
+
+        extra = [vec(in_shift), vec(in_scale), vec(out_shift), vec(out_scale), vec(log_std)]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_load_policy(self._h, nl, lin, lout, wp, bp, int(nonlinearity == "tanh"),
+                                                     *[_ptr(x) for x in extra]))
+        self.policy_obs_dim, self.policy_act_dim = int(ws[0].shape[1]), int(ws[-1].shape[0])
+
+    def policy_act(self, obs, noise=None, action=None, mean=None, want_mean=True):
+        """(action, mean) of the loaded policy for a batch of observations; noise [E, act] standard normal draws or
+        None for the evaluation action."""
+        E = obs.shape[0]
+        f32 = dict(device=self.device, dtype=torch.float32)
+        if action is None:
+            action = torch.empty((E, self.policy_act_dim), **f32)
+        if mean is None and want_mean:
+            mean = torch.empty((E, self.policy_act_dim), **f32)
+        self._check(self.lib.simstep_policy_act(self._h, _ptr(obs), _ptr(noise), E, _ptr(action), _ptr(mean),
+                                                _stream(self.device)))
+        return action, mean
+
+    def discount(self, reward, gamma, baseline=None, gae_lambda=1.0, seg_end=None, lengths=None, terminated=None,
+                 want_returns=True, want_advantages=None):
+        """Time-major [T, E] discounted returns and GAE advantages (mjrl/mjrl/utils/process_samples.py:3-45)."""
+        T, E = reward.shape
+        want_advantages = (baseline is not None) if want_advantages is None else want_advantages
+        ret = torch.empty_like(reward) if want_returns else None
+        adv = torch.empty_like(reward) if want_advantages else None
+        self._check(self.lib.simstep_discount(self._h, _ptr(reward), _ptr(baseline), _ptr(seg_end), _ptr(lengths),
+                                              _ptr(terminated), T, E, float(gamma), float(gae_lambda), _ptr(ret),
+                                              _ptr(adv), _stream(self.device)))
+        return ret, adv
+
+    def auto_reset(self, next_state, done, pool, pick, state_out, member=None, num_steps=None):
+        E = next_state.shape[0]
+        self._check(self.lib.simstep_auto_reset(self._h, _ptr(next_state), _ptr(done), _ptr(pool), _ptr(pick),
+                                                int(pool.shape[0]), E, _ptr(state_out), _ptr(member), _ptr(num_steps),
+                                                _stream(self.device)))
+        return state_out

@@ -1,0 +1,223 @@
+"""Batched on-device rollout loop: policy forward + learned-dynamics step + MILO cost over a whole horizon.
+
+Replaces the per-step host round trip of the reference's samplers (milo/milo/sampler.py:8-130 get_samples /
+sample_points: `policy.get_action(o)` in numpy, `env.step(a)` at batch 1, one trajectory at a time in a
+multiprocessing Pool) for E environments at once.  Every step is three library calls on device buffers —
+`simstep_policy_act`, `simstep_step_cost` (or `simstep_step`), `simstep_auto_reset` — and nothing returns to the
+host until the caller asks for paths or statistics.  Environments whose trajectory ends (fall contact or horizon,
+gym-simenv/gym_simenv/envs/sim_env.py:164-173) start a new one on the next step, as the reference's sampler does
+by calling env.reset(); the time-major buffers therefore hold several trajectories per env column, cut at the
+recorded `done` flags.
+
+The emitted paths have the dict layout mjrl/mjrl/algos/batch_reinforce.py:94-169 consumes (observations,
+next_observations, actions, rewards, agent_infos{mean, log_std, evaluation}, env_infos, terminated).  With a cost
+attached to the env, `rewards` already holds -cost (batch_reinforce.py:144) and the per-trajectory sums of
+batch_reinforce.py:135-141 are available from `RolloutBatch.statistics()`.
+
+Action noise: the reference draws `np.random.randn(m)` on the host per step (gaussian_mlp.py:101) after seeding
+numpy per trajectory (sampler.py:38); a batched loop cannot reproduce that stream, so standard-normal draws come
+from a seeded torch CUDA generator (or from the caller, `noise=`), and parity tests feed the same draws to the
+oracle.
+"""
+import numpy as np
+import torch
+
+
+def _policy_parts(policy):
+    """(weights, biases, nonlinearity, transformations, log_std) of an mjrl-style Gaussian MLP policy object
+    (mjrl/mjrl/policies/gaussian_mlp.py:6-58 over mjrl/mjrl/utils/fc_network.py:9-41)."""
+    model = policy.model
+    ws = [l.weight.data for l in model.fc_layers]
+    bs = [l.bias.data for l in model.fc_layers]
+    nl = getattr(model, "nonlinearity", torch.tanh)
+    name = "relu" if nl is torch.relu else "tanh"
+    log_std = torch.as_tensor(np.asarray(policy.log_std.data if hasattr(policy.log_std, "data") else policy.log_std,
+                                         dtype=np.float32)).reshape(-1)
+    return ws, bs, name, (model.in_shift, model.in_scale, model.out_shift, model.out_scale), log_std
+
+
+class RolloutBatch:
+    """Time-major device buffers of one collect() call.  T steps x E envs."""
+
+    def __init__(self, eng, T, E, S, A, with_cost):
+        dev = eng.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.eng, self.T, self.E, self.S, self.A = eng, T, E, S, A
+        self.with_cost = with_cost
+        self.observations = torch.empty((T, E, S), **f32)
+        self.next_observations = torch.empty((T, E, S), **f32)
+        self.actions = torch.empty((T, E, A), **f32)
+        self.means = torch.empty((T, E, A), **f32)
+        self.disc = torch.empty((T, E), **f32)
+        self.done = torch.empty((T, E), device=dev, dtype=torch.uint8)
+        self.cost = torch.empty((T, E), **f32) if with_cost else None
+        self.ipm = torch.empty((T, E), **f32) if with_cost else None
+        self.bonus = torch.empty((T, E), **f32) if with_cost else None
+        self.rewards = None      # set by DeviceRollout.collect: -cost, or zeros (sim_env.py:160)
+        self.final_state = torch.empty((E, S), **f32)
+        self.log_std = None
+        self.steps_taken = T
+
+    # -- returns / advantages (mjrl/mjrl/utils/process_samples.py) -------------------------------
+    def returns(self, gamma):
+        """discount_sum of the rewards per trajectory, [T, E] (process_samples.py:3-5, 37-45)."""
+        ret, _ = self.eng.discount(self.rewards, gamma, seg_end=self.done, want_returns=True, want_advantages=False)
+        return ret
+
+    def advantages(self, baseline, gamma, gae_lambda):
+        """GAE advantages per trajectory against baseline [T, E] (process_samples.py:22-30): terminated
+        trajectories bootstrap from 0, the unfinished trailing one from its last baseline value."""
+        baseline = baseline.to(self.eng.device, torch.float32).contiguous()
+        term = self.done[self.T - 1].contiguous()
+        _, adv = self.eng.discount(self.rewards, gamma, baseline=baseline, gae_lambda=gae_lambda, seg_end=self.done,
+                                   terminated=term, want_returns=False, want_advantages=True)
+        return adv
+
+    # -- host views ----------------------------------------------------------------------------
+    def segments(self, include_partial=True):
+        """[(env, t0, t1, terminated)] with t1 exclusive, ordered by env then time."""
+        done = self.done.cpu().numpy().astype(bool)
+        out = []
+        for e in range(self.E):
+            ends = np.flatnonzero(done[:, e])
+            t0 = 0
+            for t in ends:
+                out.append((e, t0, int(t) + 1, True))
+                t0 = int(t) + 1
+            if include_partial and t0 < self.T:
+                out.append((e, t0, self.T, False))
+        return out
+
+    def paths(self, include_partial=True):
+        """List of path dicts as milo/milo/sampler.py:70-81 builds them (float64 numpy arrays)."""
+        obs = self.observations.cpu().numpy().astype(np.float64)
+        nxt = self.next_observations.cpu().numpy().astype(np.float64)
+        act = self.actions.cpu().numpy().astype(np.float64)
+        mean = self.means.cpu().numpy()
+        rew = self.rewards.cpu().numpy().astype(np.float64)
+        disc = self.disc.cpu().numpy()
+        log_std = np.float64(self.log_std.cpu().numpy().ravel())
+        extra = {}
+        if self.with_cost:
+            extra = {k: getattr(self, k).cpu().numpy() for k in ("cost", "ipm", "bonus")}
+        paths = []
+        for (e, t0, t1, terminated) in self.segments(include_partial):
+            n = t1 - t0
+            infos = [{"valid": True, "disc": float(disc[t, e])} for t in range(t0, t1)]
+            path = dict(observations=obs[t0:t1, e], next_observations=nxt[t0:t1, e], actions=act[t0:t1, e],
+                        rewards=rew[t0:t1, e],
+                        agent_infos=dict(mean=mean[t0:t1, e], log_std=np.tile(log_std, (n, 1)),
+                                         evaluation=mean[t0:t1, e]),
+                        env_infos=infos, terminated=terminated)
+            for k, v in extra.items():
+                path[k] = v[t0:t1, e]
+            paths.append(path)
+        return paths
+
+    def statistics(self, include_partial=True):
+        """Per-trajectory sums of batch_reinforce.py:135-141: int = -sum(bonus), ext = -sum(ipm), reward,
+        ep_len; plus mean cost over all recorded steps (batch_reinforce.py:169's first term)."""
+        segs = self.segments(include_partial)
+        out = {"ep_len": [t1 - t0 for (_, t0, t1, _) in segs]}
+        if self.with_cost:
+            bonus = self.bonus.double().cpu().numpy()
+            ipm = self.ipm.double().cpu().numpy()
+            out["int"] = [-bonus[t0:t1, e].sum() for (e, t0, t1, _) in segs]
+            out["ext"] = [-ipm[t0:t1, e].sum() for (e, t0, t1, _) in segs]
+            out["reward"] = [a + b for a, b in zip(out["int"], out["ext"])]
+            out["mean_cost"] = float(self.cost.double().mean().item())
+        return out
+
+
+class DeviceRollout:
+    """E-environment rollout loop on one GPU.
+
+        ro = DeviceRollout(vec_env, policy, seed=0)
+        batch = ro.collect(T)              # T steps of every env, auto-reset on done
+        paths = batch.paths()              # what sampler.sample_points would have returned
+    """
+
+    def __init__(self, env, policy, seed=0):
+        self.env = env
+        self.eng = env.dynamic_ensemble.engine()
+        self.device = self.eng.device
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+        self.policy = policy
+        self.load_policy(policy)
+        pool = env.reset_states
+        if pool is None:
+            raise RuntimeError("DeviceRollout needs VecSimEnv(reset_states=...): the pool new trajectories start from")
+        self.pool = torch.as_tensor(pool).to(self.device, torch.float32).contiguous()
+        self._graphs = {}
+
+    def load_policy(self, policy=None):
+        """(Re-)upload the policy parameters — call after the learner's set_param_values."""
+        policy = policy if policy is not None else self.policy
+        ws, bs, name, (ish, isc, osh, osc), log_std = _policy_parts(policy)
+        self.eng.load_policy(ws, bs, name, ish, isc, osh, osc, log_std)
+        self.log_std = log_std
+
+    def _loop(self, batch, noise, pick, T):
+        env, eng = self.env, self.eng
+        use_cost = batch.with_cost
+        c = env.cost
+        clamp = use_cost and c.cost_range is not None
+        for t in range(T):
+            ob = batch.observations[t]
+            eng.policy_act(ob, None if noise is None else noise[t], action=batch.actions[t], mean=batch.means[t])
+            if use_cost:
+                eng.step_cost(ob, batch.actions[t], env.member, env.num_steps, env._w_dev, c.lambda_b,
+                              env.dynamic_ensemble.threshold if clamp else 1.0, c.c_min if clamp else 0.0,
+                              c.c_max if clamp else 0.0, clamp, next_state=batch.next_observations[t],
+                              disc=batch.disc[t], done=batch.done[t], cost=batch.cost[t], ipm=batch.ipm[t],
+                              bonus=batch.bonus[t])
+            else:
+                eng.step(ob, batch.actions[t], env.member, env.num_steps, next_state=batch.next_observations[t],
+                         disc=batch.disc[t], done=batch.done[t])
+            nxt = batch.observations[t + 1] if t + 1 < T else batch.final_state
+            eng.auto_reset(batch.next_observations[t], batch.done[t], self.pool, pick[t], nxt, env.member,
+                           env.num_steps)
+
+    def collect(self, num_steps, eval_mode=False, noise=None, pick=None, batch=None):
+        """Run `num_steps` steps of every env from the env's current state.  eval_mode: the mean action is used
+        (sampler.py:51).  noise [T, E, A] / pick [T, E] int32 override the generator (tests)."""
+        env = self.env
+        T, E, S, A = int(num_steps), env.num_envs, env.state_size, env.action_size
+        use_cost = env.cost is not None and env._w_dev is not None
+        if batch is None:
+            batch = RolloutBatch(self.eng, T, E, S, A, use_cost)
+        if noise is None and not eval_mode:
+            noise = torch.randn((T, E, A), device=self.device, dtype=torch.float32, generator=self.gen)
+        if eval_mode:
+            noise = None
+        if pick is None:
+            pick = torch.randint(0, self.pool.shape[0], (T, E), device=self.device, dtype=torch.int32,
+                                 generator=self.gen)
+        batch.observations[0].copy_(env.ob)
+        self._loop(batch, noise, pick, T)
+        env.ob.copy_(batch.final_state)
+        batch.rewards = -batch.cost if use_cost else torch.zeros((T, E), device=self.device, dtype=torch.float32)
+        batch.log_std = self.log_std
+        return batch
+
+    def sample_paths(self, num_to_collect, mode="samples", eval_mode=False, max_steps=None):
+        """sampler.sample_points's contract: at least `num_to_collect` samples (mode 'samples') or trajectories
+        (mode 'trajectories'), complete trajectories only (sampler.py:30-34, 79)."""
+        assert mode in ("samples", "trajectories")
+        env = self.env
+        env.reset()
+        paths, n_samples = [], 0
+        horizon = env.horizon
+        while True:
+            need = num_to_collect - (n_samples if mode == "samples" else len(paths))
+            if need <= 0:
+                break
+            T = max_steps or horizon
+            batch = self.collect(T, eval_mode=eval_mode)
+            new = batch.paths(include_partial=False)
+            paths.extend(new)
+            n_samples += sum(len(p["rewards"]) for p in new)
+            # unfinished trailing segments are dropped, like a worker that stops after its last full trajectory
+            env.reset()
+        return paths, n_samples

@@ -221,6 +221,49 @@ int simstep_imitation_reward(simstep_handle* h, const float* pose_dev, const flo
 int simstep_clip_sample(simstep_handle* h, const float* kin_time_dev, const float* kin_origin_dev, int64_t n_envs,
                         float* out_pose_dev, float* out_vel_dev, void* stream);
 
+/* ---- on-device rollout helpers ------------------------------------------ */
+
+/* Gaussian MLP policy of mjrl (mjrl/mjrl/policies/gaussian_mlp.py:6-104 over
+ * mjrl/mjrl/utils/fc_network.py:9-55): n_layers linear layers, weights_host[l] is
+ * fc_layers.l.weight [layer_out[l]][layer_in[l]] row-major, biases_host[l] its bias;
+ * tanh_act selects tanh (1) or relu (0) between layers; in_shift/in_scale [obs],
+ * out_shift/out_scale [act] are FCNetwork's transformations (NULL: 0 / 1);
+ * log_std_host [act] is the policy's log standard deviation (NULL: deterministic). */
+int simstep_load_policy(simstep_handle* h, int32_t n_layers, const int32_t* layer_in, const int32_t* layer_out,
+                        const float* const* weights_host, const float* const* biases_host, int32_t tanh_act,
+                        const float* in_shift_host, const float* in_scale_host, const float* out_shift_host,
+                        const float* out_scale_host, const float* log_std_host);
+
+/* Batched MLP.get_action (gaussian_mlp.py:95-104): mean_dev [E][act] = model(obs),
+ * action_dev [E][act] = mean + exp(log_std) * noise_dev[e] (noise_dev: standard normal
+ * draws supplied by the caller, NULL: action = mean, the 'evaluation' action).
+ * Either output may be NULL. */
+int simstep_policy_act(simstep_handle* h, const float* obs_dev, const float* noise_dev, int64_t n_envs,
+                       float* action_dev, float* mean_dev, void* stream);
+
+/* Discounted sums over time-major [T][E] arrays (mjrl/mjrl/utils/process_samples.py:3-45):
+ * returns = discount_sum(reward, gamma); advantages = GAE(gamma, gae_lambda) against
+ * baseline_dev [T][E].  An env's column holds one or more trajectories back to back:
+ * seg_end_dev [T][E] (NULL: none) != 0 marks the last step of a trajectory that terminated
+ * (milo/milo/sampler.py:79 stores terminated=done); the trailing trajectory ends at
+ * len_dev[e]-1 (NULL: T) and bootstraps from its last baseline value unless
+ * terminated_dev[e] != 0 (NULL: not terminated).  Entries at t >= len are written as 0.
+ * returns_dev / advantages_dev may be NULL. */
+int simstep_discount(simstep_handle* h, const float* reward_dev, const float* baseline_dev, const uint8_t* seg_end_dev,
+                     const int32_t* len_dev, const uint8_t* terminated_dev, int32_t T, int64_t n_envs, float gamma,
+                     float gae_lambda, float* returns_dev, float* advantages_dev, void* stream);
+
+/* Between two steps of a rollout (milo/milo/sampler.py:36-66 calls env.reset() when a
+ * trajectory ends; gym-simenv/gym_simenv/envs/sim_env.py:270-285): for every env
+ *   done_dev[e] ? state_out[e] = pool_dev[pick_dev[e] mod n_pool], num_steps[e] = 0,
+ *                 member[e] = (member[e] + 1) mod n_models
+ *               : state_out[e] = next_state[e].
+ * pool_dev [n_pool][state_dim] holds caller-supplied initial states (the reference draws
+ * them from the DeepMimic simulator, which stays outside this library). */
+int simstep_auto_reset(simstep_handle* h, const float* next_state_dev, const uint8_t* done_dev, const float* pool_dev,
+                       const int32_t* pick_dev, int32_t n_pool, int64_t n_envs, float* state_out_dev,
+                       int32_t* member_dev, int32_t* num_steps_dev, void* stream);
+
 /* ---- reductions used by the multi-GPU host code ------------------------- */
 
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */

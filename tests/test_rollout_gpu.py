@@ -1,0 +1,256 @@
+"""GPU parity of the rollout helpers through the C ABI: Gaussian MLP policy,
+discounted sums / GAE, auto-reset and the whole DeviceRollout loop against the oracle.
+
+Tolerances: the policy network and the discounted sums are plain fp32 on the CUDA cores; they differ from the
+reference's fp32 only by summation order (<= 2e-6 relative to the output scale, written below).  The rollout loop
+inherits the env step's 1e-3 budget (BASELINE.json north_star) per step.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import milo_oracle as mo
+from oracle import rollout_oracle as ro
+from tests import helpers as H
+from tests.test_parity_gpu import assert_close, make_engine
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_golden.npz"))
+
+
+class _FC:
+    def __init__(self, ws, bs, nonlinearity, in_shift=None, in_scale=None, out_shift=None, out_scale=None):
+        self.fc_layers = [torch.nn.Linear(w.shape[1], w.shape[0]) for w in ws]
+        for l, w, b in zip(self.fc_layers, ws, bs):
+            l.weight.data, l.bias.data = w.clone(), b.clone()
+        self.nonlinearity = torch.relu if nonlinearity == "relu" else torch.tanh
+        obs, act = ws[0].shape[1], ws[-1].shape[0]
+        self.in_shift = torch.zeros(obs) if in_shift is None else torch.as_tensor(in_shift)
+        self.in_scale = torch.ones(obs) if in_scale is None else torch.as_tensor(in_scale)
+        self.out_shift = torch.zeros(act) if out_shift is None else torch.as_tensor(out_shift)
+        self.out_scale = torch.ones(act) if out_scale is None else torch.as_tensor(out_scale)
+
+
+class _Policy:
+    """The attributes of mjrl's MLP policy that DeviceRollout reads (gaussian_mlp.py:36-44)."""
+
+    def __init__(self, model, log_std):
+        self.model, self.log_std = model, torch.as_tensor(log_std)
+
+
+def _golden_policy(tag, n_layers):
+    ws = [torch.from_numpy(G[f"{tag}/w{i}"]) for i in range(n_layers)]
+    bs = [torch.from_numpy(G[f"{tag}/b{i}"]) for i in range(n_layers)]
+    return ws, bs
+
+
+def _tiny_engine():
+    c = H.tiny_case("tiny_dense")
+    return c, make_engine(c, "fp16")
+
+
+def test_policy_mean_matches_reference_default_transformations():
+    _, eng = _tiny_engine()
+    ws, bs = _golden_policy("polA", 3)
+    eng.load_policy(ws, bs, "tanh", log_std=G["polA/log_std"])
+    obs = torch.from_numpy(G["polA/obs"]).cuda()
+    action, mean = eng.policy_act(obs)
+    ref = torch.from_numpy(G["polA/mean"])
+    assert_close(mean, ref, ref.abs().max().item(), rel=2e-6, what="policy mean")
+    assert torch.equal(action, mean)  # no noise: the evaluation action
+    # get_action with the reference's own numpy draws (float64 there, fp32 here)
+    noise = torch.from_numpy(G["polA/noise"]).float().cuda()
+    act8, _ = eng.policy_act(obs[:8].contiguous(), noise)
+    ref8 = torch.from_numpy(G["polA/get_action"])
+    assert_close(act8, ref8, ref8.abs().max().item(), rel=2e-6, what="get_action")
+
+
+def test_policy_relu_with_transformations_and_ragged_batches():
+    _, eng = _tiny_engine()
+    ws, bs = _golden_policy("polB", 4)
+    eng.load_policy(ws, bs, "relu", G["polB/in_shift"], G["polB/in_scale"], G["polB/out_shift"], G["polB/out_scale"])
+    ref = torch.from_numpy(G["polB/mean"])
+    for n in (50, 1, 3, 17):  # group size is 4 envs per warp: ragged tails
+        obs = torch.from_numpy(G["polB/obs"][:n]).cuda().contiguous()
+        _, mean = eng.policy_act(obs)
+        assert_close(mean, ref[:n], ref.abs().max().item(), rel=2e-6, what=f"policy mean n={n}")
+    # empty batch is a no-op
+    eng.policy_act(torch.empty((0, 40), device="cuda"))
+
+
+def test_policy_requires_load_and_validates_sizes():
+    from amp_extensions_b200 import _lib
+    _, eng = _tiny_engine()
+    with pytest.raises(_lib.SimstepError):
+        eng.policy_obs_dim, eng.policy_act_dim = 4, 2
+        eng.policy_act(torch.zeros((4, 4), device="cuda"))
+    with pytest.raises(_lib.SimstepError):  # layer sizes do not chain
+        eng.load_policy([torch.zeros(8, 4), torch.zeros(2, 9)], [torch.zeros(8), torch.zeros(2)])
+    with pytest.raises(_lib.SimstepError):  # too wide
+        eng.load_policy([torch.zeros(4096, 4)], [torch.zeros(4096)])
+
+
+def test_discount_matches_process_samples_golden():
+    """Ragged trajectories, one per env column, exactly the reference's paths (float64 there, fp32 here)."""
+    _, eng = _tiny_engine()
+    gamma, lam = [float(x) for x in G["ps/gamma_lambda"]]
+    lens, term = G["ps/lens"], G["ps/terminated"]
+    T, E = int(lens.max()), len(lens)
+    rew, base = np.zeros((T, E), np.float32), np.zeros((T, E), np.float32)
+    for i, n in enumerate(lens):
+        rew[:n, i], base[:n, i] = G[f"ps/rewards{i}"], G[f"ps/baseline{i}"]
+    ret, adv = eng.discount(torch.from_numpy(rew).cuda(), gamma, baseline=torch.from_numpy(base).cuda(),
+                            gae_lambda=lam, lengths=torch.from_numpy(lens.astype(np.int32)).cuda(),
+                            terminated=torch.from_numpy(term.astype(np.uint8)).cuda())
+    for i, n in enumerate(lens):
+        r_ref, a_ref = torch.from_numpy(G[f"ps/returns{i}"]), torch.from_numpy(G[f"ps/advantages{i}"])
+        assert_close(ret[:n, i], r_ref, r_ref.abs().max().item(), rel=1e-5, what=f"returns path {i}")
+        assert_close(adv[:n, i], a_ref, a_ref.abs().max().item(), rel=1e-5, what=f"advantages path {i}")
+        assert not ret[n:, i].any() and not adv[n:, i].any()
+
+
+def test_discount_segments_within_a_column():
+    """Several trajectories back to back in one env column, cut at seg_end flags."""
+    _, eng = _tiny_engine()
+    rng = np.random.default_rng(0)
+    T, E, gamma, lam = 97, 33, 0.99, 0.95
+    rew, base = rng.normal(size=(T, E)).astype(np.float32), rng.normal(size=(T, E)).astype(np.float32)
+    seg = (rng.random((T, E)) < 0.08).astype(np.uint8)
+    seg[:, 0] = 0
+    seg[:, 1] = 1  # every step is its own terminated trajectory
+    term = seg[T - 1].copy()
+    ret, adv = eng.discount(torch.from_numpy(rew).cuda(), gamma, baseline=torch.from_numpy(base).cuda(), gae_lambda=lam,
+                            seg_end=torch.from_numpy(seg).cuda(), terminated=torch.from_numpy(term).cuda())
+    ret, adv = ret.cpu().numpy(), adv.cpu().numpy()
+    for e in range(E):
+        t0 = 0
+        ends = list(np.flatnonzero(seg[:, e]))
+        if not ends or ends[-1] != T - 1:
+            ends.append(T - 1)
+        for t1 in ends:
+            terminated = bool(seg[t1, e])
+            r_ref = ro.discount_sum(rew[t0:t1 + 1, e].astype(np.float64), gamma)
+            a_ref = ro.gae_advantages(rew[t0:t1 + 1, e].astype(np.float64), base[t0:t1 + 1, e].astype(np.float64),
+                                      terminated, gamma, lam)
+            np.testing.assert_allclose(ret[t0:t1 + 1, e], r_ref, rtol=0, atol=2e-5 * max(1.0, np.abs(r_ref).max()))
+            np.testing.assert_allclose(adv[t0:t1 + 1, e], a_ref, rtol=0, atol=2e-5 * max(1.0, np.abs(a_ref).max()))
+            t0 = t1 + 1
+
+
+def test_auto_reset_is_exact():
+    c, eng = _tiny_engine()
+    E, S, N = 1000, c["S"], c["N"]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    nxt = torch.randn(E, S, device="cuda", generator=g)
+    pool = torch.randn(37, S, device="cuda", generator=g)
+    done = (torch.rand(E, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    pick = torch.randint(0, 1000, (E,), device="cuda", generator=g, dtype=torch.int32)
+    member = torch.randint(0, N, (E,), device="cuda", generator=g, dtype=torch.int32)
+    steps = torch.randint(0, 300, (E,), device="cuda", generator=g, dtype=torch.int32)
+    m0, s0 = member.clone(), steps.clone()
+    out = torch.full((E, S), float("nan"), device="cuda")
+    eng.auto_reset(nxt, done, pool, pick, out, member, steps)
+    d = done.bool()
+    assert torch.equal(out, torch.where(d[:, None], pool[(pick % 37).long()], nxt))
+    assert torch.equal(member, torch.where(d, (m0 + 1) % N, m0))
+    assert torch.equal(steps, torch.where(d, torch.zeros_like(s0), s0))
+
+
+@pytest.mark.parametrize("with_cost", [False, True])
+def test_device_rollout_matches_oracle_loop(with_cost):
+    """The whole loop (policy -> step -> cost -> auto-reset) against the oracle's batched restatement of the sampler,
+    same noise and reset picks on both sides.  Errors compound over steps through the learned dynamics, so the
+    per-step 1e-3 budget is checked on a short horizon; termination flags must agree except inside the band."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, RBFLinearCost, VecSimEnv
+    from amp_extensions_b200.rollout import DeviceRollout
+    c = H.ns_case()
+    S, A, N, E, T, horizon = 226, 28, 4, 96, 6, 4
+    s, a, s2 = H.synth_dataset(2048, S, A, 0)
+    ds = AmpDataset(s, a, s2)
+    ens = DynamicsEnsemble(S, A, ds, None, num_models=N, hidden_sizes=c["hidden"], dense_connect=True, transform=True,
+                           base_seed=100)
+    ens.threshold = 0.4
+    pool = H.humanoid_like_states(64, 5, fall_fraction=0.0)
+    pool[:, 0] = 1.5  # start well above the ground: falls happen through the dynamics, not at reset
+    env = VecSimEnv(ens, E, horizon=horizon, reset_states=pool, seed=1)
+    env.reset(initial_states=pool[torch.arange(E) % 64])
+    cost_o = None
+    if with_cost:
+        expert = H.ns_expert()
+        cost = RBFLinearCost(expert, feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100)
+        cost.fit_cost(torch.cat([s[:256], s2[:256]], dim=1))
+        env.attach_cost(cost)
+        cost_o = mo.RffCostOracle(expert, feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100)
+        cost_o.w = cost.w
+    ws, bs = _golden_policy("polA", 3)
+    pol = _Policy(_FC(ws, bs, "tanh"), G["polA/log_std"])
+    ro_dev = DeviceRollout(env, pol, seed=0)
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(T, E, A, generator=g)
+    pick = torch.randint(0, 64, (T, E), generator=g, dtype=torch.int32)
+    member0, steps0, ob0 = env.member.cpu().numpy(), env.num_steps.cpu().numpy(), env.ob.cpu().numpy()
+    batch = ro_dev.collect(T, noise=noise.cuda(), pick=pick.cuda())
+    wsE = [[l.weight.data for l in m.model.fc_layers] for m in ens.models]
+    bsE = [[l.bias.data for l in m.model.fc_layers] for m in ens.models]
+    ref = ro.rollout(wsE, bsE, ens.transformations, dict(ws=ws, bs=bs, log_std=G["polA/log_std"]), ob0, member0, steps0,
+                     pool.numpy(), noise.numpy(), pick.numpy(), horizon=horizon, cost=cost_o, threshold=ens.threshold,
+                     n_models=N)
+    done_dev, done_ref = batch.done.cpu().numpy().astype(bool), ref["done"]
+    # every env hits the horizon at least once in T > horizon steps, so auto-reset is exercised
+    assert done_ref.any() and (~done_ref).any()
+    agree = done_dev == done_ref
+    assert agree.mean() > 0.99
+    # compare every step up to (and including) an env's first disagreement-free prefix
+    ok = np.logical_and.accumulate(agree, axis=0)
+    ok = np.concatenate([np.ones((1, E), bool), ok[:-1]], axis=0)  # step t is comparable if flags agreed before t
+    m = torch.from_numpy(ok)
+    for name, scale in (("observations", 1.0), ("next_observations", 1.0), ("actions", 1.0), ("means", 0.1)):
+        x, r = getattr(batch, name).cpu(), torch.from_numpy(ref[name])
+        assert_close(x[m], r[m], scale, rel=3e-3, what=name)  # T compounding steps of a 1e-3-per-step budget
+    assert_close(batch.disc.cpu()[m], torch.from_numpy(ref["disc"])[m], float(ref["disc"].mean()), rel=3e-3, what="disc")
+    if with_cost:
+        assert_close(batch.cost.cpu()[m], torch.from_numpy(ref["cost"])[m], float(np.abs(ref["cost"]).max()), rel=3e-3,
+                     what="cost")
+        assert torch.equal(batch.rewards, -batch.cost)
+    # path layout (sampler.py:70-81)
+    paths = batch.paths()
+    assert sum(len(p["rewards"]) for p in paths) == T * E
+    p0 = paths[0]
+    assert p0["observations"].dtype == np.float64 and p0["observations"].shape[1] == S
+    assert set(p0["agent_infos"]) == {"mean", "log_std", "evaluation"} and p0["env_infos"][0]["valid"]
+    assert all(p["terminated"] for p in batch.paths(include_partial=False))
+    for p in paths:  # within a trajectory the next observation is the following observation
+        assert np.array_equal(p["observations"][1:], p["next_observations"][:-1])
+    # returns over the segmented columns equal per-path discount sums
+    ret = batch.returns(0.99).cpu().numpy()
+    for (e, t0, t1, _), p in zip(batch.segments(), paths):
+        np.testing.assert_allclose(ret[t0:t1, e], ro.discount_sum(p["rewards"], 0.99), rtol=0, atol=1e-5)
+    st = batch.statistics()
+    assert len(st["ep_len"]) == len(paths) and sum(st["ep_len"]) == T * E
+
+
+def test_sample_paths_contract():
+    """sample_points's contract (sampler.py:30-34): at least num_to_collect samples, complete trajectories only."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, VecSimEnv
+    from amp_extensions_b200.rollout import DeviceRollout
+    c = H.tiny_case("tiny_dense")
+    S, A = c["S"], c["A"]
+    s, a, s2 = c["ds"]
+    ens = DynamicsEnsemble(S, A, AmpDataset(s, a, s2), None, num_models=c["N"], hidden_sizes=c["hidden"],
+                           dense_connect=True, transform=True, base_seed=100)
+    from amp_extensions_b200 import HumanoidTermination
+    term = HumanoidTermination(horizon=7, fall_contact_bodies=())
+    env = VecSimEnv(ens, 16, termination=term, reset_states=s[:32], seed=0)
+    g = torch.Generator().manual_seed(0)
+    ws = [torch.randn(8, S, generator=g) * 0.1, torch.randn(A, 8, generator=g) * 0.1]
+    bs = [torch.zeros(8), torch.zeros(A)]
+    ro_dev = DeviceRollout(env, _Policy(_FC(ws, bs, "tanh"), np.full(A, -1.0, np.float32)), seed=0)
+    paths, n = ro_dev.sample_paths(300, mode="samples")
+    assert n >= 300 and n == sum(len(p["rewards"]) for p in paths)
+    assert all(p["terminated"] and len(p["rewards"]) == 7 for p in paths)  # horizon-only termination
+    paths, _ = ro_dev.sample_paths(20, mode="trajectories", eval_mode=True)
+    assert len(paths) >= 20
+    assert all(np.array_equal(p["actions"], p["agent_infos"]["mean"].astype(np.float64)) for p in paths)

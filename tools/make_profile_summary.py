@@ -62,6 +62,7 @@ def write_ncu_summary(rep, path, cmd):
             wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
             f.write(f"    {'dram traffic (read+write) per launch':72s} {rd + wr:16.0f} byte\n")
             traffic.setdefault(name.split("(")[0], []).append(rd + wr)
+            traffic.setdefault("__order__", []).append((name.split("(")[0], rd + wr))
     return traffic
 
 
@@ -98,16 +99,21 @@ sp = os.path.join(G, f"{tag}_prof_step.ncu-rep")
 if os.path.exists(sp):
     t = write_ncu_summary(sp, os.path.join(P, f"{out}_ncu_step.txt"),
                           "python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline")
-    gem = [sum(v) for k, v in t.items() if "gemm_tcgen05_kernel" in k and (", 0>" in k or ", 1>" in k)]
-    tr["ensemble_gemm_dram_bytes_per_step"] = sum(gem) if gem else None
+    # ensemble layer launches (epilogue mode 0 = hidden, 1 = final) in capture order; a step is 5 consecutive ones
+    # (the capture window may start mid-step: any 5 consecutive launches cover each layer once)
+    gem = [b for (k, b) in t.get("__order__", []) if "gemm_tcgen05_kernel" in k and
+           any(m in k for m in (", 0>", ", 1>", ", 0,", ", 1,"))]
+    tr["ensemble_gemm_dram_bytes_per_step"] = sum(gem[:5]) if len(gem) >= 5 else None
     for k, v in t.items():
+        if k == "__order__":
+            continue
         if "post_step" in k:
             tr["post_step_dram_bytes_per_launch"] = v[0]
 ip = os.path.join(G, f"{tag}_prof_imit.ncu-rep")
 if os.path.exists(ip):
     t = write_ncu_summary(ip, os.path.join(P, f"{out}_ncu_imit.txt"), "python tools/bench_imitation.py --iters 3 --warmup 1")
     for k, v in t.items():
-        if "imitation_reward" in k:
+        if k != "__order__" and "imitation_reward" in k:
             tr["imitation_dram_bytes_per_launch"] = v[0]
 if tr:
     tr["source"] = f"profiles/{out}_ncu_step.txt, profiles/{out}_ncu_imit.txt (ncu --set full, per launch)"
