@@ -19,6 +19,7 @@
 #include "imitation.cuh"
 #include "imitation_h3d.cuh"
 #include "policy.cuh"
+#include "post_tma.cuh"
 
 using namespace simstep;
 
@@ -54,6 +55,7 @@ struct simstep_handle {
   int row_align = 256;  // workspace rows are padded to whole tiles
   int S = 0, A = 0, N = 0, L = 0;
   int XP = 0, HT = 0, SP = 0;
+  int DP = 0;  // pitch (floats) of the fp32 delta workspace rows: S rounded up to 4, so a row is 16-byte granular
   std::vector<Layer> layers;  // L hidden + 1 final
   float* tf_dev = nullptr;         // mean_s | scale_s | mean_a | scale_a
   float* out_scale_dev = nullptr;  // [SP]
@@ -292,7 +294,7 @@ int ensure_workspace(simstep_handle* h, long long rows) {
   if (h->have_ensemble || h->S > 0) {
     CU_TRY(h, cudaMalloc(&h->xbuf, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMalloc(&h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
-    CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->SP * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
     CU_TRY(h, cudaMemset(h->xbuf, 0, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMemset(h->hbuf, 0, size_t(h->N) * rows * h->HT * h->esize));
     int rc = encode_operand(h, &h->tmap_x, prec, h->xbuf, h->XP, rows, h->XP, kBlockM);
@@ -303,8 +305,9 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     } else {
       h->tmap_h = h->tmap_x;
     }
-    // fp32 delta workspace, written by the final layer's TMA-store epilogue (32-float x 128-row boxes)
-    rc = encode_operand(h, &h->tmap_dws, SIMSTEP_PREC_TF32, h->dws, h->SP, static_cast<long long>(h->N) * rows, h->SP,
+    // fp32 delta workspace, written by the final layer's TMA-store epilogue (32-float x 128-row boxes); the
+    // map is DP columns wide, so the store clips the padded output columns instead of writing them
+    rc = encode_operand(h, &h->tmap_dws, SIMSTEP_PREC_TF32, h->dws, h->DP, static_cast<long long>(h->N) * rows, h->DP,
                         kBlockM);
     if (rc) return rc;
   }
@@ -401,13 +404,36 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
     rff.RK = h->RK;
     rff.split = h->rff_split;
   }
+  // TMA-staged persistent kernel (post_tma.cuh) whenever rows pair up into 16-byte granular spans
+  const PostTmaPlan plan = post_tma_plan(h->S, h->DP, h->N);
+  static const bool tma_off = [] { const char* e = std::getenv("SIMSTEP_POST_TMA"); return e && e[0] == '0'; }();
+  const bool tma = !tma_off && plan.ok && vec2 && state != nullptr && next_state != nullptr &&
+                   reinterpret_cast<uintptr_t>(state) % 16 == 0;
+#define POST_TMA_LAUNCH(NM, ET)                                                                                \
+  do {                                                                                                         \
+    auto kern = h->S == 226 ? post_step_tma_kernel<NM, ET, 226> : post_step_tma_kernel<NM, ET, 0>;             \
+    static size_t attr_smem[2] = {0, 0};                                                                       \
+    size_t& attr_ref = attr_smem[h->S == 226 ? 1 : 0];                                                                               \
+    if (attr_ref < plan.smem) {                                                                                \
+      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem)));      \
+      attr_ref = plan.smem;                                                                                    \
+    }                                                                                                          \
+    const long long pairs = (n + 1) / 2;                                                                       \
+    const int grid = int(std::min<long long>((pairs + plan.rings - 1) / plan.rings, h->sm_count));             \
+    launch_pdl(kern, dim3(grid), dim3(plan.rings * 64), plan.smem, st, h->dws, h->cap_rows, h->DP, state, member, \
+               num_steps, h->S, n, next_state, disc, done, h->term, rff, plan.stages);                         \
+  } while (0)
 #define POST_CASE(NM)                                                                                          \
   case NM:                                                                                                     \
-    if (vec2)                                                                                                  \
-      launch_pdl(post_step_kernel<NM, 2>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->SP, \
+    if (tma) {                                                                                                 \
+      if (rff.out == nullptr || h->cfg.precision == SIMSTEP_PREC_FP16) POST_TMA_LAUNCH(NM, ElemF16);           \
+      else if (h->cfg.precision == SIMSTEP_PREC_TF32) POST_TMA_LAUNCH(NM, ElemTF32);                           \
+      else POST_TMA_LAUNCH(NM, ElemBF16);                                                                      \
+    } else if (vec2)                                                                                           \
+      launch_pdl(post_step_kernel<NM, 2>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->DP, \
                  state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     else                                                                                                       \
-      launch_pdl(post_step_kernel<NM, 1>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->SP, \
+      launch_pdl(post_step_kernel<NM, 1>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->DP, \
                  state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     break;
   switch (h->N) {
@@ -415,6 +441,7 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
     default: return fail(h, SIMSTEP_EINVAL, "n_models must be in [1, 8]");
   }
 #undef POST_CASE
+#undef POST_TMA_LAUNCH
   g_launches++;
   CU_TRY(h, cudaGetLastError());
   return SIMSTEP_OK;
@@ -552,6 +579,7 @@ int simstep_create(const simstep_config* cfg, simstep_handle** out) {
   h->L = cfg->n_hidden;
   h->XP = int(round_up(h->S + h->A, 64));
   h->SP = int(round_up(h->S, kBlockN));
+  h->DP = int(round_up(h->S, 4));
   std::vector<int> hp(h->L), hcol(h->L);
   int ht = 0;
   for (int i = 0; i < h->L; ++i) {
@@ -634,7 +662,7 @@ int simstep_query(const simstep_handle* h, int32_t* n_layers, int32_t* layer_in,
   if (workspace_bytes) {
     const long long r = h->cap_rows;
     *workspace_bytes = r * h->XP * h->esize + static_cast<long long>(h->N) * r * h->HT * h->esize +
-                       static_cast<long long>(h->N) * r * h->SP * 4 + (h->have_rff ? r * (h->rff_split ? 2 * h->RK : h->RK) * h->esize : 0);
+                       static_cast<long long>(h->N) * r * h->DP * 4 + (h->have_rff ? r * (h->rff_split ? 2 * h->RK : h->RK) * h->esize : 0);
   }
   return SIMSTEP_OK;
 }
@@ -778,7 +806,7 @@ int simstep_forward(simstep_handle* h, const float* state_dev, const float* acti
     const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
     if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
     const long long total = static_cast<long long>(h->N) * n * h->S;
-    extract_delta_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, st>>>(h->dws, h->cap_rows, h->SP, h->N, h->S, n,
+    extract_delta_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, st>>>(h->dws, h->cap_rows, h->DP, h->N, h->S, n,
                                                                             delta_dev, n_envs, r0);
     g_launches++;
     CU_TRY(h, cudaGetLastError());

@@ -238,7 +238,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -361,8 +361,8 @@ def run_ours(args):
     pipe = HostStepPipeline(eng, E, n_chunks=args.e2e_chunks, with_cost=True)
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
-                              "kernels_ms_per_step": per_step, "note": "profiling run (--skip-e2e), not a bench line"}))
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
+                  "kernels_ms_per_step": per_step, "note": "profiling run (--skip-e2e), not a bench line"})
         return 0
     hs = [states[k].cpu().pin_memory() for k in range(2)]
     ha = [actions[k].cpu().pin_memory() for k in range(2)]
@@ -425,7 +425,7 @@ def run_ours(args):
             "roofline_hbm": hbm_roofline(post_ms, E, args.precision, peaks),
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -445,9 +445,25 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # stdout when NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the duration of the
+    # run and the JSON line goes to the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
