@@ -324,3 +324,37 @@ def test_fused_step_cost_matches_oracle(prec):
     cost_ref2, _ = oc.get_bonus_costs(s, a, disc_ref, thr, next_states=nxt_ref.float())
     out = eng.step_cost(s.cuda(), a.cuda(), member.cuda(), steps.cuda(), oc.w.cuda(), lam, 1.0, 0.0, 0.0, False)
     assert_close(out[3], cost_ref2[:, 0], cost_ref2.abs().max().item(), what="unclamped cost")
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: the 8-member, hidden 1024 x 4 ensemble
+
+
+def test_scale_config_8x1024_matches_oracle():
+    """8 x (1024 x 4) dense-connect members (28 discrepancy pairs, K up to 4350): step + discrepancy against the
+    fp32 oracle on the same seed-generated weights, odd batch so the row-pair staging sees a trailing row."""
+    from amp_extensions_b200.engine import Engine, HumanoidTermination
+    S, A, N, hidden, E = 226, 28, 8, [1024] * 4, 257
+    ws, bs = mo.init_ensemble(S, A, hidden, N, dense_connect=True, base_seed=100)
+    s_d, a_d, s2_d = H.synth_dataset(4096, S, A, 0)
+    tf = mo.get_transformations(s_d, a_d, s2_d)
+    eng = Engine(S, A, N, hidden, dense_connect=True, activation="relu", transform=True, precision="fp16")
+    eng.load_ensemble(ws, bs, tf)
+    eng.set_termination(HumanoidTermination(horizon=300))
+    s = H.humanoid_like_states(E, seed=21)
+    g = torch.Generator().manual_seed(22)
+    a = torch.randn(E, A, generator=g)
+    member = torch.randint(0, N, (E,), generator=g, dtype=torch.int32)
+    steps = torch.zeros(E, dtype=torch.int32)
+    preds = mo.ensemble_forward(ws, bs, tf, s, a)
+    active = preds[member.long(), torch.arange(E)]
+    nxt_ref, _, done_ref = mo.simenv_step(s.double().numpy(), active.numpy(), steps.numpy())
+    disc_ref = mo.discrepancy_from_preds(preds)
+    nxt, disc, done = eng.step(s.cuda(), a.cuda(), member.cuda(), steps.cuda())
+    assert_close(nxt, torch.from_numpy(nxt_ref), tf[1].mean().item(), what="next_state")
+    assert_close(disc, disc_ref, disc_ref.mean().item(), what="disc")
+    mism = done.cpu().bool().numpy() != done_ref
+    if mism.any():
+        assert (collision_margin(nxt_ref)[mism] < REL).all()
+    fwd = eng.forward(s[:64], a[:64])
+    assert_close(fwd, preds[:, :64], tf[5].abs().max().item(), what="delta")
