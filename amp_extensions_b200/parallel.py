@@ -35,6 +35,31 @@ def shard_range(n, rank_=None, world=None):
     return start, start + base + (1 if r < rem else 0)
 
 
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPU cores (and thereby the NUMA node) closest to its GPU before any pinned host
+    buffer is allocated: with one process per GPU the host<->device copies of all ranks otherwise share whichever
+    socket the launcher happened to start them on.  Returns the CPU list, or None when NVML / affinity is not
+    available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def _all_reduce(t, op):
     if is_dist():
         dist.all_reduce(t, op=op)

@@ -179,12 +179,62 @@ class DeviceRollout:
             eng.auto_reset(batch.next_observations[t], batch.done[t], self.pool, pick[t], nxt, env.member,
                            env.num_steps)
 
-    def collect(self, num_steps, eval_mode=False, noise=None, pick=None, batch=None):
+    def _collect_graph(self, T, eval_mode, noise, pick, use_cost):
+        """collect() with the whole T-step loop replayed from one CUDA graph (3 + 8 launches per step otherwise
+        go through Python and the driver one by one, which dominates at small batch).  The graph and its static
+        buffers are cached per configuration; the returned batch is overwritten by the next graph collect."""
+        env = self.env
+        E, S, A = env.num_envs, env.state_size, env.action_size
+        c = env.cost
+        key = (T, bool(eval_mode), use_cost, float(env.dynamic_ensemble.threshold or 0.0) if use_cost else 0.0,
+               float(c.lambda_b) if use_cost else 0.0, env._w_dev.data_ptr() if use_cost else 0, env.ob.data_ptr(),
+               env.member.data_ptr(), env.num_steps.data_ptr())
+        ent = self._graphs.get(key)
+        if ent is None:
+            batch = RolloutBatch(self.eng, T, E, S, A, use_cost)
+            s_noise = None if eval_mode else torch.zeros((T, E, A), device=self.device, dtype=torch.float32)
+            s_pick = torch.zeros((T, E), device=self.device, dtype=torch.int32)
+            # warm-up outside capture (workspace allocation, kernel attributes), on copies of the env's counters
+            saved = (env.ob.clone(), env.member.clone(), env.num_steps.clone())
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                batch.observations[0].copy_(env.ob)
+                self._loop(batch, s_noise, s_pick, min(T, 2))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            env.ob.copy_(saved[0]); env.member.copy_(saved[1]); env.num_steps.copy_(saved[2])
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                batch.observations[0].copy_(env.ob)
+                self._loop(batch, s_noise, s_pick, T)
+                env.ob.copy_(batch.final_state)
+            ent = (g, batch, s_noise, s_pick)
+            self._graphs[key] = ent
+        g, batch, s_noise, s_pick = ent
+        if s_noise is not None:
+            if noise is not None:
+                s_noise.copy_(noise)
+            else:
+                s_noise.normal_(generator=self.gen)
+        if pick is not None:
+            s_pick.copy_(pick)
+        else:
+            s_pick.random_(0, self.pool.shape[0], generator=self.gen)
+        g.replay()
+        batch.rewards = -batch.cost if use_cost else torch.zeros((T, E), device=self.device, dtype=torch.float32)
+        batch.log_std = self.log_std
+        return batch
+
+    def collect(self, num_steps, eval_mode=False, noise=None, pick=None, batch=None, graph=False):
         """Run `num_steps` steps of every env from the env's current state.  eval_mode: the mean action is used
-        (sampler.py:51).  noise [T, E, A] / pick [T, E] int32 override the generator (tests)."""
+        (sampler.py:51).  noise [T, E, A] / pick [T, E] int32 override the generator (tests).  graph=True replays
+        the loop from a cached CUDA graph (the returned batch is then reused by the next such call)."""
         env = self.env
         T, E, S, A = int(num_steps), env.num_envs, env.state_size, env.action_size
         use_cost = env.cost is not None and env._w_dev is not None
+        if graph:
+            return self._collect_graph(T, eval_mode, noise, pick, use_cost)
         if batch is None:
             batch = RolloutBatch(self.eng, T, E, S, A, use_cost)
         if noise is None and not eval_mode:

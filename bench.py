@@ -280,6 +280,7 @@ def run_ours(args):
     from amp_extensions_b200.engine import HumanoidTermination
     from amp_extensions_b200.host_api import HostStepPipeline
     from amp_extensions_b200 import parallel
+    host_cpus = parallel.bind_host_to_gpu(local_rank)  # NUMA-local pinned buffers for the host-buffer pass
 
     E = args.envs
     ds = AmpDataset(*synth_dataset(8192, 0))
@@ -412,7 +413,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "steps": e2e_steps, "chunks": len(pipe.bounds),
                     "api": "amp_extensions_b200.host_api.HostStepPipeline.submit/collect (pinned host buffers, 2 batches in "
-                           "flight)"},
+                           "flight)",
+                    "host_cpus_rank0": (f"{len(host_cpus)} cores near the GPU (NVML affinity)" if host_cpus
+                                        else "unbound")},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "gemm_tcgen05_kernel (5 ensemble layer launches per step)", "bound": "tensor",

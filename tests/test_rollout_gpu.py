@@ -254,3 +254,38 @@ def test_sample_paths_contract():
     paths, _ = ro_dev.sample_paths(20, mode="trajectories", eval_mode=True)
     assert len(paths) >= 20
     assert all(np.array_equal(p["actions"], p["agent_infos"]["mean"].astype(np.float64)) for p in paths)
+
+
+def test_graph_replay_equals_eager_loop():
+    """collect(graph=True) replays the same launches from a CUDA graph: bit-identical buffers, and the env's
+    counters advance exactly as in the eager loop (also on a second replay of the cached graph)."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, HumanoidTermination, VecSimEnv
+    from amp_extensions_b200.rollout import DeviceRollout
+    c = H.tiny_case("tiny_dense")
+    S, A = c["S"], c["A"]
+    s, a, s2 = c["ds"]
+    ens = DynamicsEnsemble(S, A, AmpDataset(s, a, s2), None, num_models=c["N"], hidden_sizes=c["hidden"],
+                           dense_connect=True, transform=True, base_seed=100)
+    g = torch.Generator().manual_seed(0)
+    ws = [torch.randn(8, S, generator=g) * 0.1, torch.randn(A, 8, generator=g) * 0.1]
+    bs = [torch.zeros(8), torch.zeros(A)]
+    pol = _Policy(_FC(ws, bs, "tanh"), np.full(A, -1.0, np.float32))
+    T, E = 9, 50
+    noise = torch.randn(2, T, E, A, generator=g).cuda()
+    pick = torch.randint(0, 32, (2, T, E), generator=g, dtype=torch.int32).cuda()
+    outs = []
+    for use_graph in (False, True):
+        env = VecSimEnv(ens, E, termination=HumanoidTermination(horizon=4, fall_contact_bodies=()),
+                        reset_states=s[:32], seed=0)
+        env.reset(initial_states=s[:E])
+        ro_dev = DeviceRollout(env, pol, seed=0)
+        got = []
+        for k in range(2):
+            b = ro_dev.collect(T, noise=noise[k], pick=pick[k], graph=use_graph)
+            got.append({n: getattr(b, n).clone() for n in ("observations", "next_observations", "actions", "disc",
+                                                            "done")})
+            got[-1].update(member=env.member.clone(), num_steps=env.num_steps.clone(), ob=env.ob.clone())
+        outs.append(got)
+    for k in range(2):
+        for n, v in outs[0][k].items():
+            assert torch.equal(v, outs[1][k][n]), (k, n)
