@@ -106,6 +106,9 @@ _SIGNATURES = {
                                    C.c_int64, C.c_float, C.c_float, _c_void_p, _c_void_p, _c_void_p]),
     "simstep_auto_reset": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, C.c_int32, C.c_int64,
                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "simstep_moments": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
+    "simstep_whiten": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, C.c_float, _c_void_p,
+                                 _c_void_p]),
     "simstep_reduce_max_sum": (C.c_int, [_c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
     "simstep_profile_enable": (C.c_int, [_c_void_p, C.c_int32]),
     "simstep_profile_read": (C.c_int, [_c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),

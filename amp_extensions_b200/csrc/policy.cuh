@@ -199,4 +199,70 @@ auto_reset_kernel(const float* __restrict__ next_state, const uint8_t* __restric
   }
 }
 
+// Moments of a (masked) vector for advantage whitening (mjrl/mjrl/utils/process_samples.py:14-19, 31-36:
+// alladv.mean(), alladv.std()) and rollout statistics: two deterministic passes, fp64 accumulation.
+//   pass 1: partial[b] = {count, sum, sum of squares} of block b's grid-stride slice
+//   pass 2: out[0..2] = sum over blocks (fixed order)
+constexpr int kMomentsThreads = 256;
+constexpr int kMomentsMaxBlocks = 1024;
+
+__global__ void __launch_bounds__(kMomentsThreads)
+moments_partial_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, long long n,
+                       double* __restrict__ partial) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  double c = 0.0, s = 0.0, q = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (valid == nullptr || valid[i]) {
+      const double v = x[i];
+      c += 1.0;
+      s += v;
+      q += v * v;
+    }
+  }
+  __shared__ double sh[3][kMomentsThreads / 32];
+  for (int off = 16; off > 0; off >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, off);
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = c;
+    sh[1][threadIdx.x >> 5] = s;
+    sh[2][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kMomentsThreads / 32; ++w) t += sh[threadIdx.x][w];
+    partial[blockIdx.x * 3 + threadIdx.x] = t;
+  }
+}
+
+__global__ void moments_final_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += partial[b * 3 + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+}
+
+// out = (x - mean) / (std + eps) with mean / population std from stats = {count, sum, sum of squares} (fp64, e.g.
+// the all-reduced output of moments); masked-out entries are written as 0.
+__global__ void whiten_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, long long n,
+                              const double* __restrict__ stats, float eps, float* __restrict__ out) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const double cnt = stats[0] > 0.0 ? stats[0] : 1.0;
+  const double mean = stats[1] / cnt;
+  const double var = stats[2] / cnt - mean * mean;
+  const double sd = sqrt(var > 0.0 ? var : 0.0);
+  const float m = static_cast<float>(mean);
+  const float inv = static_cast<float>(1.0 / (sd + static_cast<double>(eps)));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = (valid == nullptr || valid[i]) ? (x[i] - m) * inv : 0.f;
+}
+
 }  // namespace simstep

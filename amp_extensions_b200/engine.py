@@ -343,3 +343,16 @@ class Engine:
                                                 int(pool.shape[0]), E, _ptr(state_out), _ptr(member), _ptr(num_steps),
                                                 _stream(self.device)))
         return state_out
+
+    def moments(self, x, valid=None):
+        """{count, sum, sum of squares} of a device tensor as a CUDA fp64 [3] tensor."""
+        out = torch.empty((3,), device=self.device, dtype=torch.float64)
+        self._check(self.lib.simstep_moments(self._h, _ptr(x), _ptr(valid), x.numel(), _ptr(out), _stream(self.device)))
+        return out
+
+    def whiten(self, x, stats, valid=None, eps=1e-8, out=None):
+        """(x - mean) / (std + eps) with mean/std from `stats` (see moments)."""
+        out = torch.empty_like(x) if out is None else out
+        self._check(self.lib.simstep_whiten(self._h, _ptr(x), _ptr(valid), x.numel(), _ptr(stats), float(eps), _ptr(out),
+                                            _stream(self.device)))
+        return out

@@ -132,3 +132,103 @@ class HostStepPipeline:
         """One batched env step on host buffers, synchronous: submit + collect."""
         self.submit(state_h, action_h, member_h, steps_h, w_dev, lambda_b, threshold, c_min, c_max, clamp_cost)
         return self.collect()
+
+
+class HostEnvPipeline:
+    """The reference plugin's own call shape, batched: `step(actions) -> (obs, cost, done, ...)` with the env state
+    RESIDENT on the device (gym-simenv/gym_simenv/envs/sim_env.py:140-162 keeps `self.ob` inside the env and takes
+    only the action).  Per step only the actions cross PCIe host->device; observations, costs and flags come back.
+
+    `groups` independent groups of E envs alternate (submit / collect), so group g+1's action upload and group
+    g-1's result download overlap group g's compute — a sampler that steps two sets of environments in turn.
+
+        pipe = HostEnvPipeline(engine, E, groups=2)
+        pipe.reset(0, states0_h, member0_h); pipe.reset(1, states1_h, member1_h)
+        pipe.submit(0, actions_h, w_dev, lambda_b, threshold); pipe.submit(1, ...)
+        obs_h, cost_h, done_h, disc_h, steps_h = pipe.collect()       # group 0's results
+    """
+
+    def __init__(self, engine, num_envs, groups=2, n_chunks=2, with_cost=True):
+        self.eng, self.E, self.with_cost = engine, int(num_envs), with_cost
+        dev, S, A, E = engine.device, engine.S, engine.A, self.E
+        n_chunks = max(1, min(int(n_chunks), (E + 255) // 256))
+        rows = -(-(-(-E // n_chunks)) // 256) * 256
+        self.bounds = [(r0, min(E, r0 + rows)) for r0 in range(0, E, rows)]
+        self.groups = []
+        f32 = dict(device=dev, dtype=torch.float32)
+        for _ in range(int(groups)):
+            g = _Slot(engine, E)
+            g.d_state2 = torch.empty((E, S), **f32)   # ping-pong partner of d_state
+            self.groups.append(g)
+        self._inflight = collections.deque()
+        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.h2d_bytes_per_step = E * A * 4
+        self.d2h_bytes_per_step = E * (S * 4 + 4 + 1 + 4 + (4 if with_cost else 0))
+
+    def reset(self, group, state_h, member_h=None, steps_h=None):
+        """(Re)start every env of a group from host-supplied initial states (the reference draws them from the
+        DeepMimic simulator, sim_env.py:270-285); member indices / step counters default to 0."""
+        g = self.groups[group]
+        cur = torch.cuda.current_stream(self.eng.device)
+        for s in (self.s_in, self.s_compute, self.s_out):
+            cur.wait_stream(s)
+        g.d_state.copy_(state_h, non_blocking=True)
+        if member_h is None:
+            g.d_member.zero_()
+        else:
+            g.d_member.copy_(member_h, non_blocking=True)
+        if steps_h is None:
+            g.d_steps.zero_()
+        else:
+            g.d_steps.copy_(steps_h, non_blocking=True)
+        for s in (self.s_in, self.s_compute, self.s_out):
+            s.wait_stream(cur)
+
+    def submit(self, group, action_h, w_dev=None, lambda_b=0.0, threshold=1.0, c_min=-1.0, c_max=0.0,
+               clamp_cost=True):
+        """Enqueue one step of a group's envs on pinned host actions [E, A]; returns immediately."""
+        eng, g = self.eng, self.groups[group]
+        if g in self._inflight:
+            raise RuntimeError("HostEnvPipeline: collect() this group's previous step before submitting the next")
+        if g.ev_out_done is not None:          # the previous results must have left d_next / d_cost ...
+            self.s_compute.wait_event(g.ev_out_done)
+        if g.ev_compute_done is not None:      # ... and the previous step must have consumed its actions
+            self.s_in.wait_event(g.ev_compute_done)
+        ev_c = None
+        for (r0, r1) in self.bounds:
+            with torch.cuda.stream(self.s_in):
+                g.d_action[r0:r1].copy_(action_h[r0:r1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_compute):
+                self.s_compute.wait_event(ev_in)
+                if self.with_cost:
+                    eng.step_cost(g.d_state[r0:r1], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1], w_dev,
+                                  lambda_b, threshold, c_min, c_max, clamp_cost, next_state=g.d_state2[r0:r1],
+                                  disc=g.d_disc[r0:r1], done=g.d_done[r0:r1], cost=g.d_cost[r0:r1],
+                                  ipm=g.d_ipm[r0:r1], bonus=g.d_bonus[r0:r1])
+                else:
+                    eng.step(g.d_state[r0:r1], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1],
+                             next_state=g.d_state2[r0:r1], disc=g.d_disc[r0:r1], done=g.d_done[r0:r1])
+                ev_c = torch.cuda.Event()
+                ev_c.record(self.s_compute)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_c)
+                g.h_next[r0:r1].copy_(g.d_state2[r0:r1], non_blocking=True)
+                g.h_disc[r0:r1].copy_(g.d_disc[r0:r1], non_blocking=True)
+                g.h_done[r0:r1].copy_(g.d_done[r0:r1], non_blocking=True)
+                g.h_steps[r0:r1].copy_(g.d_steps[r0:r1], non_blocking=True)
+                if self.with_cost:
+                    g.h_cost[r0:r1].copy_(g.d_cost[r0:r1], non_blocking=True)
+        g.d_state, g.d_state2 = g.d_state2, g.d_state   # s' is the next step's state; it never left the device
+        g.ev_compute_done = ev_c
+        g.ev_out_done = torch.cuda.Event()
+        g.ev_out_done.record(self.s_out)
+        self._inflight.append(g)
+
+    def collect(self):
+        """Wait for the oldest in-flight step.  Returns pinned host tensors (obs [E,S], cost [E] or None, done [E]
+        uint8, disc [E], num_steps [E]), valid until that group is submitted again."""
+        g = self._inflight.popleft()
+        g.ev_out_done.synchronize()
+        return g.h_next, (g.h_cost if self.with_cost else None), g.h_done, g.h_disc, g.h_steps

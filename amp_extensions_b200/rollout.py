@@ -73,6 +73,14 @@ class RolloutBatch:
                                    terminated=term, want_returns=False, want_advantages=True)
         return adv
 
+    def normalize(self, adv, valid=None):
+        """compute_advantages(normalize=True) (process_samples.py:14-19, 31-36): (adv - mean) / (std + 1e-8) with
+        the mean and population std taken over every recorded step — of ALL ranks when torch.distributed is
+        initialised (one all-reduce of three fp64 numbers)."""
+        from . import parallel
+        stats = parallel.all_reduce_sum(self.eng.moments(adv, valid))
+        return self.eng.whiten(adv, stats, valid, eps=1e-8)
+
     # -- host views ----------------------------------------------------------------------------
     def segments(self, include_partial=True):
         """[(env, t0, t1, terminated)] with t1 exclusive, ordered by env then time."""

@@ -359,36 +359,49 @@ def run_ours(args):
     per_step = {k: v[0] / prof_steps for k, v in prof.items() if v[1] > 0}
 
     # ---- end to end through the host-buffer API: pinned H2D + step + D2H inside the timed region ----------
-    pipe = HostStepPipeline(eng, E, n_chunks=args.e2e_chunks, with_cost=True)
     if args.skip_e2e:
         if rank == 0:
             emit({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
                   "kernels_ms_per_step": per_step, "note": "profiling run (--skip-e2e), not a bench line"})
         return 0
+    from amp_extensions_b200.host_api import HostEnvPipeline
     hs = [states[k].cpu().pin_memory() for k in range(2)]
-    ha = [actions[k].cpu().pin_memory() for k in range(2)]
+    ha = [actions[k].cpu().pin_memory() for k in range(4)]
     hm, hst = member.cpu().pin_memory(), torch.zeros(E, dtype=torch.int32).pin_memory()
     e2e_steps = max(10, min(args.steps, 100))
-    # Two independent groups of envs alternate (the way a sampler keeps two batches in flight): group i+1's
-    # upload and group i-1's download overlap group i's compute.  Every step's inputs cross PCIe host->device and
-    # every step's results (next state, cost, done, disc, counters) come back and are read on the host.
-    for i in range(3):
-        pipe.step(hs[i % 2], ha[i % 2], hm, hst, w, LAMBDA_B, threshold)
-    barrier()
-    t0 = time.perf_counter()
-    chk = 0.0
-    pipe.submit(hs[0], ha[0], hm, hst, w, LAMBDA_B, threshold)
-    for i in range(1, e2e_steps):
-        pipe.submit(hs[i % 2], ha[i % 2], hm, hst, w, LAMBDA_B, threshold)
-        out = pipe.collect()
-        chk += float(out[1][0]) + float(out[0][-1, -1])  # the caller reads the step's results on the host
-    out = pipe.collect()
-    chk += float(out[1][0]) + float(out[0][-1, -1])
-    torch.cuda.synchronize(device)
-    e2e_dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = E * world * e2e_steps / float(e2e_dt.item())
+
+    def timed_host_loop(submit, collect):
+        """Two groups of envs alternate: group i+1's upload and group i-1's download overlap group i's compute.
+        Every step's inputs cross PCIe host->device and every step's results (next state, cost, done, disc,
+        counters) come back and are read on the host."""
+        for i in range(4):
+            submit(i)
+            collect()
+        barrier()
+        t0 = time.perf_counter()
+        chk = 0.0
+        submit(0)
+        for i in range(1, e2e_steps):
+            submit(i)
+            out = collect()
+            chk += float(out[1][0]) + float(out[0][-1, -1])  # the caller reads the step's results on the host
+        out = collect()
+        chk += float(out[1][0]) + float(out[0][-1, -1])
+        torch.cuda.synchronize(device)
+        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return E * world * e2e_steps / float(dt.item())
+
+    # (1) the plugin's own call shape, env.step(actions): state resident on the device (sim_env.py:140-162)
+    envp = HostEnvPipeline(eng, E, groups=2, n_chunks=args.e2e_chunks, with_cost=True)
+    envp.reset(0, hs[0], hm)
+    envp.reset(1, hs[1], hm)
+    e2e_value = timed_host_loop(lambda i: envp.submit(i % 2, ha[i % 4], w, LAMBDA_B, threshold), envp.collect)
+    # (2) stateless callers: the full state crosses PCIe both ways every step
+    pipe = HostStepPipeline(eng, E, n_chunks=args.e2e_chunks, with_cost=True)
+    e2e_stateless = timed_host_loop(lambda i: pipe.submit(hs[i % 2], ha[i % 4], hm, hst, w, LAMBDA_B, threshold),
+                                    pipe.collect)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -410,10 +423,14 @@ def run_ours(args):
             "config": workload_config(world, extra={"operands": f"{args.precision} in, fp32 accumulate (TMEM)",
                                                     "threshold": threshold}),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "steps": e2e_steps, "chunks": len(pipe.bounds),
-                    "api": "amp_extensions_b200.host_api.HostStepPipeline.submit/collect (pinned host buffers, 2 batches in "
-                           "flight)",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": envp.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": envp.d2h_bytes_per_step, "steps": e2e_steps, "chunks": len(envp.bounds),
+                    "api": "amp_extensions_b200.host_api.HostEnvPipeline.submit/collect: env.step(actions) on pinned host "
+                           "actions, env state resident on the device as in SimEnv (sim_env.py:140-162), obs / cost / "
+                           "done / disc / counters copied back and read on the host; 2 env groups alternate",
+                    "stateless": {"value": e2e_stateless, "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
+                                  "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
+                                  "api": "HostStepPipeline.submit/collect: full state uploaded every step"},
                     "host_cpus_rank0": (f"{len(host_cpus)} cores near the GPU (NVML affinity)" if host_cpus
                                         else "unbound")},
             "gpu_launches": int(launches),

@@ -264,6 +264,18 @@ int simstep_auto_reset(simstep_handle* h, const float* next_state_dev, const uin
                        const int32_t* pick_dev, int32_t n_pool, int64_t n_envs, float* state_out_dev,
                        int32_t* member_dev, int32_t* num_steps_dev, void* stream);
 
+/* Advantage whitening (mjrl/mjrl/utils/process_samples.py:14-19, 31-36) in two calls so that a
+ * multi-GPU caller can all-reduce between them:
+ *   simstep_moments: out_dev[0..2] = {count, sum, sum of squares} (fp64) of x_dev[i] over the entries
+ *                    with valid_dev[i] != 0 (NULL: all n entries); deterministic two-pass reduction.
+ *   simstep_whiten:  out_dev[i] = (x[i] - mean) / (std + eps), mean = sum/count, std = population
+ *                    standard deviation (numpy's .std()), from stats_dev = {count, sum, sumsq};
+ *                    masked-out entries are written as 0.  out_dev may alias x_dev. */
+int simstep_moments(simstep_handle* h, const float* x_dev, const uint8_t* valid_dev, int64_t n, double* out_dev,
+                    void* stream);
+int simstep_whiten(simstep_handle* h, const float* x_dev, const uint8_t* valid_dev, int64_t n, const double* stats_dev,
+                   float eps, float* out_dev, void* stream);
+
 /* ---- reductions used by the multi-GPU host code ------------------------- */
 
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */

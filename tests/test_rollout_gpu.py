@@ -289,3 +289,29 @@ def test_graph_replay_equals_eager_loop():
     for k in range(2):
         for n, v in outs[0][k].items():
             assert torch.equal(v, outs[1][k][n]), (k, n)
+
+
+def test_moments_and_whitening_match_numpy():
+    """compute_advantages(normalize=True) (process_samples.py:14-19): numpy float64 mean / population std."""
+    _, eng = _tiny_engine()
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 1000, 300 * 4001):
+        x = (rng.normal(size=n) * 3 + 0.7).astype(np.float32)
+        valid = (rng.random(n) < 0.8).astype(np.uint8)
+        valid[0] = 1
+        xd, vd = torch.from_numpy(x).cuda(), torch.from_numpy(valid).cuda()
+        for v_np, v_dev in ((None, None), (valid, vd)):
+            sel = x.astype(np.float64) if v_np is None else x.astype(np.float64)[v_np.astype(bool)]
+            st = eng.moments(xd, v_dev).cpu().numpy()
+            assert st[0] == sel.size
+            assert abs(st[1] - sel.sum()) <= 1e-9 * max(1.0, np.abs(sel).sum())
+            assert abs(st[2] - (sel ** 2).sum()) <= 1e-9 * (sel ** 2).sum()
+            out = eng.whiten(xd, torch.from_numpy(st).cuda(), v_dev).cpu().numpy()
+            ref = (x.astype(np.float64) - sel.mean()) / (sel.std() + 1e-8)
+            if v_np is not None:
+                ref = np.where(v_np.astype(bool), ref, 0.0)
+            if sel.size > 1:
+                np.testing.assert_allclose(out, ref, rtol=0, atol=2e-6 * max(1.0, np.abs(ref).max()))
+    # empty input: count 0, nothing written
+    st = eng.moments(torch.empty(0, device="cuda")).cpu().numpy()
+    assert st.tolist() == [0.0, 0.0, 0.0]
