@@ -78,6 +78,9 @@ struct simstep_handle {
   float* rff_part = nullptr;
   double* colsum_partial = nullptr;
   CUtensorMap tmap_rffw, tmap_rffin;
+  // feature net (MLPCost): hidden layers of this handle feed the cos-feature head instead of a packed input row
+  bool feat_net = false;
+  int feat_tanh = 0;
 
   TermConst term{};
   ImitConst* imit_dev = nullptr;
@@ -286,7 +289,7 @@ long long chunk_limit(const simstep_handle* h) {
 int ensure_workspace(simstep_handle* h, long long rows) {
   rows = round_up(rows < 1 ? 1 : rows, h->row_align);
   if (rows > chunk_limit(h)) rows = chunk_limit(h);
-  if (rows <= h->cap_rows && (!h->have_rff || h->rffin)) return SIMSTEP_OK;
+  if (rows <= h->cap_rows && (!h->have_rff || h->rffin || (h->feat_net && h->rff_part))) return SIMSTEP_OK;
   if (rows < h->cap_rows) rows = h->cap_rows;
   CU_TRY(h, cudaDeviceSynchronize());
   free_workspace(h);
@@ -311,7 +314,9 @@ int ensure_workspace(simstep_handle* h, long long rows) {
                         kBlockM);
     if (rc) return rc;
   }
-  if (h->have_rff) {
+  if (h->have_rff && h->feat_net) {
+    CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));  // A operand = hbuf
+  } else if (h->have_rff) {
     const int rka = h->rff_split ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
     CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * rka * h->esize));
     CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * rka * h->esize));
@@ -338,7 +343,8 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
 // w_stage != nullptr: the prep kernel also copies the cost weights into h->rff_wpad (no separate memcpy node
 // between the step's kernels).
 int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st,
-                       const float* w_stage = nullptr) {
+                       const float* w_stage = nullptr, int last_layer = -2) {
+  if (last_layer == -2) last_layer = h->L;  // -1: input preparation only
   const long long rows_pad = round_up(n, h->row_align);
   {
   ProfScope ps(h, SIMSTEP_PROF_PREP, st);
@@ -350,7 +356,7 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
-  for (int l = 0; l <= h->L; ++l) {
+  for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
     GemmArgs ga{};
     ga.m_tiles = int(rows_pad / (kBlockM * h->cg));
@@ -491,6 +497,16 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
   ga.rff_part = w_pad ? h->rff_part : nullptr;
   ga.rff_part_stride = h->cap_rows;
   ga.rff_phi_scale = float(std::sqrt(2.0 / h->D));
+  if (h->feat_net) {
+    // the head reads the last hidden layer's slice of the activation buffer
+    const Layer& fin = h->layers[h->L];
+    ga.kb_x = fin.kb_x;   // no hidden layer: the head reads the input rows themselves
+    ga.kb_h0 = fin.kb_h0;
+    ga.kb_h = fin.kb_h;
+    ga.rff_tanh = h->feat_tanh;
+    return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, h->tmap_rffw, h->tmap_h, ga,
+                                h->sm_count, st);
+  }
   return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_rffin, h->tmap_rffin, h->tmap_rffw, h->tmap_rffin, ga,
                               h->sm_count, st);
 }
@@ -523,11 +539,41 @@ int rff_sources(simstep_handle* h, const float* s, const float* a, const float* 
   return SIMSTEP_OK;
 }
 
+// Packs layer l of every member (weights_host[m * stride + l], nn.Linear layout) into the operand format.
+int upload_layer(simstep_handle* h, int l, const float* const* weights_host, const float* const* biases_host,
+                 int stride) {
+  cudaStream_t st = nullptr;
+  Layer& ly = h->layers[l];
+  const size_t wbytes = size_t(h->N) * ly.o_pad * ly.k_pad * h->esize;
+  if (!ly.w) CU_TRY(h, cudaMalloc(&ly.w, wbytes));
+  if (!ly.bias) CU_TRY(h, cudaMalloc(&ly.bias, size_t(h->N) * ly.o_pad * sizeof(float)));
+  CU_TRY(h, cudaMemsetAsync(ly.w, 0, wbytes, st));
+  CU_TRY(h, cudaMemsetAsync(ly.bias, 0, size_t(h->N) * ly.o_pad * sizeof(float), st));
+  float* tmp = nullptr;
+  CU_TRY(h, cudaMalloc(&tmp, size_t(ly.out) * ly.in_ref * sizeof(float)));
+  for (int m = 0; m < h->N; ++m) {
+    const float* wsrc = weights_host[m * stride + l];
+    const float* bsrc = biases_host[m * stride + l];
+    if (!wsrc || !bsrc) { cudaFree(tmp); return fail(h, SIMSTEP_EINVAL, "null weight or bias pointer"); }
+    CU_TRY(h, cudaMemcpyAsync(tmp, wsrc, size_t(ly.out) * ly.in_ref * sizeof(float), cudaMemcpyHostToDevice, st));
+    void* dst = static_cast<char*>(ly.w) + size_t(m) * ly.o_pad * ly.k_pad * h->esize;
+    int rc = pack_matrix(h, h->cfg.precision, tmp, ly.in_ref, ly.out, dst, ly.k_pad, ly.segs, 0, st);
+    if (rc) { cudaFree(tmp); return rc; }
+    CU_TRY(h, cudaMemcpyAsync(ly.bias + size_t(m) * ly.o_pad, bsrc, size_t(ly.out) * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaStreamSynchronize(st));  // tmp and the pageable host source are reused
+  }
+  cudaFree(tmp);
+  return encode_operand(h, &ly.tmap_w, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
+                        ly.k_pad, kBlockN / h->cg);
+}
+
 void free_clip(simstep_handle* h);
 void free_policy(simstep_handle* h);
 
 int check_step_ready(simstep_handle* h, long long n_envs) {
   if (!h) return SIMSTEP_EINVAL;
+  if (h->feat_net) return fail(h, SIMSTEP_EINVAL, "this handle holds a cost feature net, not a dynamics ensemble");
   if (!h->have_ensemble) return fail(h, SIMSTEP_EINVAL, "simstep_load_ensemble has not been called");
   if (n_envs < 0) return fail(h, SIMSTEP_EINVAL, "n_envs < 0");
   return SIMSTEP_OK;
@@ -673,31 +719,8 @@ int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host, c
   if (h->cfg.transform && !transforms_host) return fail(h, SIMSTEP_EINVAL, "transform set but no transforms given");
   CU_TRY(h, cudaSetDevice(h->device));
   const int nl = h->L + 1;
-  cudaStream_t st = nullptr;
   for (int l = 0; l < nl; ++l) {
-    Layer& ly = h->layers[l];
-    const size_t wbytes = size_t(h->N) * ly.o_pad * ly.k_pad * h->esize;
-    if (!ly.w) CU_TRY(h, cudaMalloc(&ly.w, wbytes));
-    if (!ly.bias) CU_TRY(h, cudaMalloc(&ly.bias, size_t(h->N) * ly.o_pad * sizeof(float)));
-    CU_TRY(h, cudaMemsetAsync(ly.w, 0, wbytes, st));
-    CU_TRY(h, cudaMemsetAsync(ly.bias, 0, size_t(h->N) * ly.o_pad * sizeof(float), st));
-    float* tmp = nullptr;
-    CU_TRY(h, cudaMalloc(&tmp, size_t(ly.out) * ly.in_ref * sizeof(float)));
-    for (int m = 0; m < h->N; ++m) {
-      const float* wsrc = weights_host[m * nl + l];
-      const float* bsrc = biases_host[m * nl + l];
-      if (!wsrc || !bsrc) { cudaFree(tmp); return fail(h, SIMSTEP_EINVAL, "null weight or bias pointer"); }
-      CU_TRY(h, cudaMemcpyAsync(tmp, wsrc, size_t(ly.out) * ly.in_ref * sizeof(float), cudaMemcpyHostToDevice, st));
-      void* dst = static_cast<char*>(ly.w) + size_t(m) * ly.o_pad * ly.k_pad * h->esize;
-      int rc = pack_matrix(h, h->cfg.precision, tmp, ly.in_ref, ly.out, dst, ly.k_pad, ly.segs, 0, st);
-      if (rc) { cudaFree(tmp); return rc; }
-      CU_TRY(h, cudaMemcpyAsync(ly.bias + size_t(m) * ly.o_pad, bsrc, size_t(ly.out) * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
-      CU_TRY(h, cudaStreamSynchronize(st));  // tmp and the pageable host source are reused
-    }
-    cudaFree(tmp);
-    int rc = encode_operand(h, &ly.tmap_w, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
-                            ly.k_pad, kBlockN / h->cg);
+    int rc = upload_layer(h, l, weights_host, biases_host, nl);
     if (rc) return rc;
   }
   // transforms
@@ -791,6 +814,63 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   int rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN / h->cg);
   if (rc) return rc;
   h->have_rff = true;
+  return SIMSTEP_OK;
+}
+
+int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host, const float* const* biases_host,
+                             int32_t feature_dim, const float* head_weight_host, const float* head_bias_host,
+                             int32_t head_tanh) {
+  if (!h || !weights_host || !biases_host || !head_weight_host || !head_bias_host || feature_dim < 1)
+    return fail(h, SIMSTEP_EINVAL, "bad argument");
+  if (h->N != 1 || h->A != 0 || h->cfg.transform || h->cfg.dense_connect)
+    return fail(h, SIMSTEP_EINVAL,
+                "a feature net needs a handle with n_models = 1, action_dim = 0, transform = 0 and dense_connect = 0");
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaDeviceSynchronize());
+  for (int l = 0; l < h->L; ++l) {
+    int rc = upload_layer(h, l, weights_host, biases_host, h->L);
+    if (rc) return rc;
+  }
+  if (!h->tf_dev) CU_TRY(h, cudaMalloc(&h->tf_dev, size_t(2 * h->S + 4) * sizeof(float)));
+  // head = cos-feature layer over the last hidden activations (reuses the random-feature GEMM epilogue)
+  cudaFree(h->rff_w); cudaFree(h->rff_b); cudaFree(h->rff_wpad); cudaFree(h->colsum_partial);
+  cudaFree(h->rffin); cudaFree(h->rff_part);
+  h->rff_w = nullptr; h->rff_b = nullptr; h->rff_wpad = nullptr; h->colsum_partial = nullptr;
+  h->rffin = nullptr; h->rff_part = nullptr;
+  h->have_rff = false;
+  const Layer& fin = h->layers[h->L];
+  const int in_dim = h->L > 0 ? h->cfg.hidden[h->L - 1] : h->S;
+  h->D = feature_dim;
+  h->D_pad = int(round_up(feature_dim, kBlockN));
+  h->rff_in = in_dim;
+  h->RK = (fin.kb_x + fin.kb_h) * h->bk;  // the padded width of the last hidden layer's slice (or of the input)
+  h->rff_split = 0;
+  h->RKT = h->RK;
+  const size_t wbytes = size_t(h->D_pad) * h->RKT * h->esize;
+  CU_TRY(h, cudaMalloc(&h->rff_w, wbytes));
+  CU_TRY(h, cudaMemset(h->rff_w, 0, wbytes));
+  CU_TRY(h, cudaMalloc(&h->rff_b, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMemset(h->rff_b, 0, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->rff_wpad, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMemset(h->rff_wpad, 0, size_t(h->D_pad) * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->colsum_partial, size_t(1024) * h->D_pad * sizeof(double)));
+  float* tmp = nullptr;
+  CU_TRY(h, cudaMalloc(&tmp, size_t(feature_dim) * in_dim * sizeof(float)));
+  CU_TRY(h, cudaMemcpy(tmp, head_weight_host, size_t(feature_dim) * in_dim * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->rff_b, head_bias_host, size_t(feature_dim) * sizeof(float), cudaMemcpyHostToDevice));
+  PackSegs sg{};
+  sg.n = 1; sg.src0[0] = 0; sg.width[0] = in_dim; sg.dst0[0] = 0;
+  int rc = pack_matrix(h, h->cfg.precision, tmp, in_dim, feature_dim, h->rff_w, h->RKT, sg, 0, nullptr);
+  CU_TRY(h, cudaDeviceSynchronize());
+  cudaFree(tmp);
+  if (rc) return rc;
+  rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN / h->cg);
+  if (rc) return rc;
+  free_workspace(h);
+  h->feat_tanh = head_tanh ? 1 : 0;
+  h->feat_net = true;
+  h->have_rff = true;
+  h->have_ensemble = true;
   return SIMSTEP_OK;
 }
 
@@ -900,9 +980,13 @@ int simstep_rff_features(simstep_handle* h, const float* x_dev, int64_t n_rows, 
     if ((rc = ensure_workspace(h, n_rows))) return rc;
     for (long long r0 = 0; r0 < n_rows; r0 += h->cap_rows) {
       const long long n = std::min<long long>(h->cap_rows, n_rows - r0);
-      RffSrc src{};
-      src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
-      if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+      if (h->feat_net) {
+        if ((rc = run_ensemble_chunk(h, x_dev + r0 * h->S, nullptr, n, st, nullptr, h->L - 1))) return rc;
+      } else {
+        RffSrc src{};
+        src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
+        if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+      }
       if ((rc = launch_rff_gemm(h, n, nullptr, phi_dev + r0 * h->D, st))) return rc;
     }
   }
@@ -937,9 +1021,13 @@ int simstep_bonus_cost(simstep_handle* h, const float* x_dev, const float* disc_
   if ((rc = stage_w(h, w_dev, st))) return rc;
   for (long long r0 = 0; r0 < n_rows; r0 += h->cap_rows) {
     const long long n = std::min<long long>(h->cap_rows, n_rows - r0);
-    RffSrc src{};
-    src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
-    if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    if (h->feat_net) {
+      if ((rc = run_ensemble_chunk(h, x_dev + r0 * h->S, nullptr, n, st, nullptr, h->L - 1))) return rc;
+    } else {
+      RffSrc src{};
+      src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
+      if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+    }
     if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
     if (disc_dev == nullptr) {
       // raw dot only (simstep_rff_dot): cost_dev receives phi.w

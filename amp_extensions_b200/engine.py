@@ -165,6 +165,22 @@ class Engine:
             self._check(self.lib.simstep_load_rff(self._h, w.shape[0], w.shape[1], _ptr(w), _ptr(b), int(bool(split))))
         self.rff_dim, self.rff_in = int(w.shape[0]), int(w.shape[1])
 
+    def load_feature_net(self, weights, biases, head_weight, head_bias, head_tanh=True):
+        """MLPCost's feature map (linear_cost.py:200-236): hidden nn.Linear layers + the last nn.Linear whose
+        output goes through tanh and cos.  The handle must have been created with num_models=1, action_dim=0,
+        dense_connect=False, transform=False and hidden_sizes = the hidden layers' widths."""
+        nl = len(weights)
+        ws = [w.detach().to("cpu", torch.float32).contiguous() for w in weights]
+        bs = [b.detach().to("cpu", torch.float32).contiguous() for b in biases]
+        hw = head_weight.detach().to("cpu", torch.float32).contiguous()
+        hb = head_bias.detach().to("cpu", torch.float32).contiguous()
+        wp = (C.c_void_p * max(nl, 1))(*[w.data_ptr() for w in ws])
+        bp = (C.c_void_p * max(nl, 1))(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_load_feature_net(self._h, wp, bp, int(hw.shape[0]), _ptr(hw), _ptr(hb),
+                                                          int(bool(head_tanh))))
+        self.rff_dim, self.rff_in = int(hw.shape[0]), self.S
+
     # -- ensemble -----------------------------------------------------------------------
     def forward(self, state, action):
         """All members' un-normalised predictions, CUDA tensor [N, E, S]."""

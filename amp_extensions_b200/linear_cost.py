@@ -119,3 +119,68 @@ class RBFLinearCost:
         d = dict(self.__dict__)
         d["_eng"] = None
         return d
+
+
+class MLPCost(RBFLinearCost):
+    """MILO's MMD cost over MLP features with the reference's surface (milo/milo/linear_cost.py:154-301): the
+    feature map is `net(x)` = Linear/activation stack ending in Tanh, then cos(.) * sqrt(2/feature_dim).  Same
+    constructor arguments, same torch RNG consumption (the nn.Linear layers are built in the reference's order
+    before the bandwidth draw), so `net` is bit-identical to the reference's for a given seed and torch build.
+    The hidden layers and the cos-feature head run through libsimstep's grouped tcgen05 GEMM
+    (simstep_load_feature_net); fit_cost / get_costs / get_expert_cost / get_bonus_costs are inherited."""
+
+    def __init__(self, expert_data, hidden_dims=[2048, 2048], activation="relu", feature_dim=1024, input_type="ss",
+                 cost_range=[-1.0, 0.0], bw_quantile=0.1, bw_samples=100000, lambda_b=1.0, lr=0.0, seed=100,
+                 precision=None, device=None):
+        torch.manual_seed(seed)  # linear_cost.py:187-188
+        np.random.seed(seed)
+        self.expert_data = expert_data
+        input_dim = expert_data.size(1)
+        self.input_type = input_type
+        self.feature_dim = feature_dim
+        self.cost_range = cost_range
+        if cost_range is not None:
+            self.c_min, self.c_max = cost_range
+        self.lambda_b = lambda_b
+        self.lr = lr
+        self._precision = precision
+        self._device = device
+        self._eng = None
+        # linear_cost.py:200-216, layer for layer
+        self.activation_name = "relu" if activation == "relu" else "tanh"
+        self.activation = nn.ReLU() if activation == "relu" else nn.Tanh()
+        dim = feature_dim if not hidden_dims else hidden_dims[0]
+        layers = [nn.Linear(input_dim, dim)]
+        if hidden_dims[1:]:
+            for size in hidden_dims[1:]:
+                layers.append(self.activation)
+                layers.append(nn.Linear(dim, size))
+                dim = size
+            layers.append(self.activation)
+            layers.append(nn.Linear(dim, feature_dim))
+        layers.append(nn.Tanh())
+        self.net = nn.Sequential(*layers)
+        self.quantile = bw_quantile
+        self.bw_samples = bw_samples
+        self.bw = self.fit_bandwidth(expert_data)  # linear_cost.py:219-221
+        self.w = None
+        self.expert_rep = self.get_rep(expert_data)
+        self.phi_e = self.expert_rep.mean(0)
+
+    def _linears(self):
+        return [m for m in self.net if isinstance(m, nn.Linear)]
+
+    def engine(self):
+        lin = self._linears()
+        if self._eng is None:
+            self._eng = _engine.Engine(state_dim=lin[0].in_features, action_dim=0, num_models=1,
+                                       hidden_sizes=[l.out_features for l in lin[:-1]], dense_connect=False,
+                                       activation=self.activation_name, transform=False, precision=self._precision,
+                                       device=self._device)
+            self._net_stamp = None
+        stamp = tuple((l.weight._version, l.bias._version, id(l.weight.data), id(l.bias.data)) for l in lin)
+        if stamp != self._net_stamp:
+            self._eng.load_feature_net([l.weight.data for l in lin[:-1]], [l.bias.data for l in lin[:-1]],
+                                       lin[-1].weight.data, lin[-1].bias.data, head_tanh=True)
+            self._net_stamp = stamp
+        return self._eng

@@ -221,6 +221,18 @@ int simstep_imitation_reward(simstep_handle* h, const float* pose_dev, const flo
 int simstep_clip_sample(simstep_handle* h, const float* kin_time_dev, const float* kin_origin_dev, int64_t n_envs,
                         float* out_pose_dev, float* out_vel_dev, void* stream);
 
+/* MLPCost's feature map (milo/milo/linear_cost.py:154-222): a plain MLP
+ *   x -> act(W_0 x + b_0) -> ... -> act(W_{L-1} . + b_{L-1}) -> tanh(W_head . + b_head) -> cos(.) * sqrt(2/D)
+ * on a handle created with state_dim = input width, action_dim = 0, n_models = 1, hidden = the MLP's
+ * hidden sizes, dense_connect = 0, transform = 0.  weights_host[l] / biases_host[l], l < n_hidden, are the
+ * hidden nn.Linear layers; head_weight_host [feature_dim][hidden[L-1]] / head_bias_host the last nn.Linear;
+ * head_tanh = 1 applies the tanh the reference puts before the cosine (linear_cost.py:208).  Afterwards
+ * simstep_rff_features / simstep_rff_dot / simstep_bonus_cost evaluate this feature map (x_dev rows are
+ * state_dim wide); simstep_step* are not available on such a handle. */
+int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host, const float* const* biases_host,
+                             int32_t feature_dim, const float* head_weight_host, const float* head_bias_host,
+                             int32_t head_tanh);
+
 /* ---- on-device rollout helpers ------------------------------------------ */
 
 /* Gaussian MLP policy of mjrl (mjrl/mjrl/policies/gaussian_mlp.py:6-104 over

@@ -216,6 +216,53 @@ class RffCostOracle:
         return cost, {"bonus": weighted_bonus, "ipm": ipm, "v_targ": rff_cost, "cost": cost}
 
 
+class MlpCostOracle(RffCostOracle):
+    """MLPCost (LC:154-301) restated: the feature map is an MLP ending in tanh, then cos(.) * sqrt(2/D).  Same
+    constructor arguments and RNG consumption order as the reference (net first, then the bandwidth draw)."""
+
+    def __init__(self, expert_data, hidden_dims=(2048, 2048), activation="relu", feature_dim=1024, input_type="ss",
+                 cost_range=(-1.0, 0.0), bw_quantile=0.1, bw_samples=100000, lambda_b=1.0, seed=100):
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        self.expert_data = expert_data
+        self.input_type = input_type
+        self.feature_dim = feature_dim
+        self.cost_range = cost_range
+        if cost_range is not None:
+            self.c_min, self.c_max = cost_range
+        self.lambda_b = lambda_b
+        input_dim = expert_data.size(1)
+        hidden_dims = list(hidden_dims)
+        # LC:201-214 (including its quirk: with a single hidden size the net is Linear(in, hidden[0]) + Tanh)
+        self.act = torch.relu if activation == "relu" else torch.tanh
+        dim = feature_dim if not hidden_dims else hidden_dims[0]
+        linears = [nn.Linear(input_dim, dim)]
+        if hidden_dims[1:]:
+            for size in hidden_dims[1:]:
+                linears.append(nn.Linear(dim, size))
+                dim = size
+            linears.append(nn.Linear(dim, feature_dim))
+        self.ws = [l.weight.data.clone() for l in linears]
+        self.bs = [l.bias.data.clone() for l in linears]
+        # fit_bandwidth (LC:223-229): unused by the features but it advances the RNG and is reported
+        n = expert_data.shape[0]
+        i0 = torch.randint(low=0, high=n, size=(bw_samples,))
+        i1 = torch.randint(low=0, high=n, size=(bw_samples,))
+        self.bw = torch.quantile(torch.norm(expert_data[i0, :] - expert_data[i1, :], dim=1), q=bw_quantile).item()
+        self.w = None
+        self.expert_rep = self.get_rep(expert_data)
+        self.phi_e = self.expert_rep.mean(0)
+
+    def get_rep(self, x):
+        """LC:231-236."""
+        with torch.no_grad():
+            out = x.cpu().float()
+            for i in range(len(self.ws) - 1):
+                out = self.act(torch.nn.functional.linear(out, self.ws[i], self.bs[i]))
+            out = torch.tanh(torch.nn.functional.linear(out, self.ws[-1], self.bs[-1]))
+            return torch.cos(out) * np.sqrt(2 / self.feature_dim)
+
+
 # --------------------------------------------------------------------------------------
 # sim_env.py  (state in float64, as the reference keeps it)
 

@@ -130,3 +130,38 @@ def test_simenv_step_horizon_and_velocity():
     assert not mo.simenv_step(s, d, np.array([0]))[2][0]
     assert mo.simenv_step(s, d, np.array([0]), enable_velocity_check=True)[2][0]
     assert nxt.dtype == np.float64
+
+
+# ---------------------------------------------------------------------------------------------------
+# MLPCost (linear_cost.py:154-301) against the reference's own outputs (tests/golden/mlpcost_golden.npz)
+
+MLPCOST_CASES = ["two_hidden", "one_hidden_quirk", "three_tanh"]
+
+
+def _mlpcost_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlpcost_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", MLPCOST_CASES)
+def test_mlp_cost_oracle_matches_reference(tag):
+    g = _mlpcost_golden()
+    expert = torch.from_numpy(g["expert"])
+    oc = mo.MlpCostOracle(expert, hidden_dims=g[f"{tag}/hidden"].tolist(), activation=str(g[f"{tag}/act"]),
+                          feature_dim=int(g[f"{tag}/feature_dim"]), input_type="ss", bw_quantile=0.1, lambda_b=0.3,
+                          seed=100)
+    assert len(oc.ws) == int(g[f"{tag}/n_linear"])
+    for i, (w, b) in enumerate(zip(oc.ws, oc.bs)):  # same RNG stream -> the same net, bit for bit
+        assert np.array_equal(w.numpy(), g[f"{tag}/w{i}"]) and np.array_equal(b.numpy(), g[f"{tag}/b{i}"])
+    assert oc.bw == float(g[f"{tag}/bw"])
+    xs, xa, nxt = (torch.from_numpy(g[k]) for k in ("xs", "xa", "next"))
+    pi = torch.cat([xs, nxt], dim=1)
+    assert np.array_equal(oc.phi_e.numpy(), g[f"{tag}/phi_e"])
+    assert np.array_equal(oc.get_rep(pi).numpy(), g[f"{tag}/rep"])
+    assert oc.fit_cost(pi) == float(g[f"{tag}/mmd"])
+    assert np.array_equal(oc.get_costs(pi).numpy(), g[f"{tag}/costs"])
+    assert float(oc.get_expert_cost()) == float(g[f"{tag}/expert_cost"])
+    total, info = oc.get_bonus_costs(xs, xa, torch.from_numpy(g["disc"]), 0.4, next_states=nxt)
+    assert np.array_equal(total.numpy(), g[f"{tag}/total"])
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        assert np.array_equal(info[k].numpy(), g[f"{tag}/info_{k}"]), k

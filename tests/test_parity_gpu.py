@@ -358,3 +358,76 @@ def test_scale_config_8x1024_matches_oracle():
         assert (collision_margin(nxt_ref)[mism] < REL).all()
     fwd = eng.forward(s[:64], a[:64])
     assert_close(fwd, preds[:, :64], tf[5].abs().max().item(), what="delta")
+
+
+# ---------------------------------------------------------------------------------------------------
+# MLPCost (linear_cost.py:154-301): MLP features through the grouped GEMM + tanh/cos head
+
+
+class _FixedDiscEnsemble:
+    def __init__(self, disc, threshold):
+        self.disc, self.threshold = disc, threshold
+
+    def get_action_discrepancy(self, states, actions):
+        return self.disc.clone()
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("tag", ["two_hidden", "one_hidden_quirk", "three_tanh"])
+def test_mlp_cost_matches_reference(tag, prec):
+    """Same seed -> the same net as the reference (bit for bit, built on the host); features, fitted weights,
+    costs and the bonus combine against the reference's own outputs.  Scale of a feature: sqrt(2/D)."""
+    import os
+    from amp_extensions_b200 import MLPCost
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlpcost_golden.npz"))
+    expert = torch.from_numpy(g["expert"])
+    D = int(g[f"{tag}/feature_dim"])
+    cost = MLPCost(expert, hidden_dims=g[f"{tag}/hidden"].tolist(), activation=str(g[f"{tag}/act"]), feature_dim=D,
+                   input_type="ss", bw_quantile=0.1, lambda_b=0.3, seed=100, precision=prec)
+    lin = cost._linears()
+    assert len(lin) == int(g[f"{tag}/n_linear"])
+    for i, l in enumerate(lin):
+        assert np.array_equal(l.weight.data.numpy(), g[f"{tag}/w{i}"])
+    assert cost.bw == float(g[f"{tag}/bw"])
+    xs, xa, nxt = (torch.from_numpy(g[k]) for k in ("xs", "xa", "next"))
+    pi = torch.cat([xs, nxt], dim=1)
+    fscale = (2.0 / g[f"{tag}/rep"].shape[1]) ** 0.5
+    assert_close(cost.phi_e, torch.from_numpy(g[f"{tag}/phi_e"]), fscale, what="phi_e")
+    assert_close(cost.get_rep(pi), torch.from_numpy(g[f"{tag}/rep"]), fscale, what="rep")
+    mmd = cost.fit_cost(pi)
+    w_ref = torch.from_numpy(g[f"{tag}/w"])
+    assert_close(cost.w, w_ref, w_ref.abs().max().item(), what="w")
+    assert abs(mmd - float(g[f"{tag}/mmd"])) <= 3e-3 * float(g[f"{tag}/mmd"])
+    cost.w = w_ref.clone()   # evaluate the costs with the reference's weights: isolates the feature error
+    c_ref = torch.from_numpy(g[f"{tag}/costs"])
+    cscale = max(c_ref.abs().max().item(), float(w_ref.norm()) * fscale)
+    assert_close(cost.get_costs(pi), c_ref, cscale, what="costs")
+    assert abs(float(cost.get_expert_cost()) - float(g[f"{tag}/expert_cost"])) <= REL * cscale
+    total, info = cost.get_bonus_costs(xs, xa, _FixedDiscEnsemble(torch.from_numpy(g["disc"]), 0.4), next_states=nxt)
+    t_ref = torch.from_numpy(g[f"{tag}/total"])
+    assert total.shape == t_ref.shape
+    assert_close(total, t_ref, t_ref.abs().max().item(), what="total")
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        r = torch.from_numpy(g[f"{tag}/info_{k}"])
+        assert_close(info[k], r, max(r.abs().max().item(), cscale), what=k)
+
+
+def test_mlp_cost_default_shape_matches_oracle():
+    """The reference's default MLPCost (452 -> 2048 -> 2048 -> 1024) against the fp32 oracle, 1000 rows."""
+    from amp_extensions_b200 import MLPCost
+    g = torch.Generator().manual_seed(8)
+    es = torch.randn(512, 226, generator=g)
+    expert = torch.cat([es, es + 0.05 * torch.randn(512, 226, generator=g)], dim=1)
+    cost = MLPCost(expert, lambda_b=0.0025, seed=100)
+    oc = mo.MlpCostOracle(expert, lambda_b=0.0025, seed=100)
+    x = torch.cat([es[:1000 % 512 + 488], es[:1000 % 512 + 488] * 0.9], dim=1)
+    x = torch.randn(1000, 452, generator=g)
+    rep, rep_ref = cost.get_rep(x), oc.get_rep(x)
+    assert_close(rep, rep_ref, (2.0 / 1024) ** 0.5, what="rep")
+    assert abs(cost.fit_cost(x) - oc.fit_cost(x)) <= 3e-3 * oc.fit_cost(x)
+    cost.w = oc.w.clone()
+    c_ref = oc.get_costs(x)
+    assert_close(cost.get_costs(x), c_ref, max(c_ref.abs().max().item(), float(oc.w.norm()) * (2.0 / 1024) ** 0.5),
+                 what="costs")
+    with pytest.raises(Exception):   # a feature-net handle is not an env
+        cost.engine().step(torch.zeros(4, 452).cuda(), torch.zeros(4, 0).cuda(), None, None)
