@@ -98,6 +98,8 @@ _SIGNATURES = {
     "simstep_imitation_reward": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, C.c_int64,
                                            _c_void_p, _c_void_p, _c_void_p]),
     "simstep_clip_sample": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p, _c_void_p]),
+    "simstep_record_state": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_float, _c_void_p, _c_void_p]),
     "simstep_load_feature_net": (C.c_int, [_c_void_p, C.POINTER(_c_void_p), C.POINTER(_c_void_p), C.c_int32, _c_void_p,
                                            _c_void_p, C.c_int32]),
     "simstep_load_policy": (C.c_int, [_c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

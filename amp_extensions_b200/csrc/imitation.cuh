@@ -421,4 +421,94 @@ clip_sample_kernel(const ImitConst c, const float* __restrict__ g_times, const f
   }
 }
 
+// Character state features of the learned-dynamics env (reference DeepMimicCore sim/CtController.cpp:378-495,
+// cCtController::BuildStatePose / BuildStateVel, the vector SimEnv.reset() obtains through record_state,
+// gym-simenv/gym_simenv/envs/sim_env.py:270-285) from a generalized pose / velocity: root height, then per body
+// part its centre position, rotation normal (q * y) and tangent (q * x), then per body part its linear and angular
+// velocity — in the character's heading frame (cKinTree::BuildOriginTrans, KinTree.cpp:1701-1712) unless the
+// controller's Record* flags say otherwise.  Body transforms follow the pose kinematically
+// (cKinTree::BodyWorldTrans, KinTree.cpp:1148-1166, zero attach rotations): what the simulator holds right after
+// cSimCharacter::SetPose / SetVel, i.e. at reset.  The ground is the plane y = 0.
+//   out [n][1 + 9 * n_joints + 6 * n_joints]
+struct RecordFlags {
+  int all_world;        // RecordAllWorld
+  int world_root_pos;   // RecordWorldRootPos
+  int world_root_rot;   // RecordWorldRootRot
+  float vel_scale;      // 1, or 1 / UpdateRate when RecordVelAsPos
+};
+
+__global__ void __launch_bounds__(kImitThreads)
+record_state_kernel(const ImitConst c, const float* __restrict__ pose, const float* __restrict__ vel,
+                    long long n_envs, const RecordFlags f, float* __restrict__ out) {
+  const int nj = c.n_joints;
+  const int width = 1 + 15 * nj;
+  const int vel0 = 1 + 9 * nj;
+  for (long long e = static_cast<long long>(blockIdx.x) * kImitThreads + threadIdx.x; e < n_envs;
+       e += static_cast<long long>(gridDim.x) * kImitThreads) {
+    const float* p0 = pose + e * c.dof;
+    const float* w0 = vel + e * c.dof;
+    float* o = out + e * width;
+    JointState A[SIMSTEP_MAX_JOINTS];
+    const Quat rq_raw = load_quat(p0 + 3);
+    A[0].Q = qnormalize(rq_raw);
+    A[0].p = v3(p0[0], p0[1], p0[2]);
+    A[0].v = v3(w0[0], w0[1], w0[2]);
+    A[0].w = v3(w0[3], w0[4], w0[5]);
+    float hc, hs;
+    heading_cs(rq_raw, hc, hs);
+    const Vec3 root = A[0].p;
+    o[0] = root.y;  // origin_trans * (root - ground) keeps y (CtController.cpp:388-394)
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+      if (j > 0) {
+        const int type = c.joint_type[j];
+        const int off = c.param_offset[j];
+        const int par = c.parent[j];
+        Quat ql = Quat{1.f, 0.f, 0.f, 0.f};
+        Vec3 wl = v3(0.f, 0.f, 0.f);
+        if (type == 1) {
+          ql = qnormalize(load_quat(p0 + off));
+          wl = v3(w0[off], w0[off + 1], w0[off + 2]);
+        } else if (type == 2) {
+          float s_, c_;
+          sincosf(0.5f * p0[off], &s_, &c_);
+          ql = Quat{c_, 0.f, 0.f, s_};
+          wl = v3(0.f, 0.f, w0[off]);
+        }
+        const Vec3 r = qrot(A[par].Q, v3(c.attach[j][0], c.attach[j][1], c.attach[j][2]));
+        A[j].Q = qmul(A[par].Q, ql);
+        A[j].p = A[par].p + r;
+        A[j].w = A[par].w + qrot(A[j].Q, wl);
+        A[j].v = A[par].v + cross(A[par].w, r);
+      }
+      const Vec3 rb = qrot(A[j].Q, v3(c.body_attach[j][0], c.body_attach[j][1], c.body_attach[j][2]));
+      Vec3 pos = A[j].p + rb;                       // body centre (ground height 0)
+      Vec3 lin = A[j].v + cross(A[j].w, rb);        // its linear velocity
+      Vec3 ang = A[j].w;
+      Vec3 nrm = qrot(A[j].Q, v3(0.f, 1.f, 0.f));   // CalcNormalTangent, MathUtil.cpp:622-628
+      Vec3 tan = qrot(A[j].Q, v3(1.f, 0.f, 0.f));
+      const bool is_root = j == 0;
+      if (!f.all_world) {
+        if (!f.world_root_pos || !is_root) {
+          pos = rot_heading_inv(hc, hs, v3(pos.x - root.x, pos.y, pos.z - root.z));
+          pos.y -= root.y;
+        }
+        if (!f.world_root_rot || !is_root) {
+          nrm = rot_heading_inv(hc, hs, nrm);
+          tan = rot_heading_inv(hc, hs, tan);
+          lin = rot_heading_inv(hc, hs, lin);
+          ang = rot_heading_inv(hc, hs, ang);
+        }
+      }
+      float* po = o + 1 + 9 * j;
+      po[0] = pos.x; po[1] = pos.y; po[2] = pos.z;
+      po[3] = nrm.x; po[4] = nrm.y; po[5] = nrm.z;
+      po[6] = tan.x; po[7] = tan.y; po[8] = tan.z;
+      float* vo = o + vel0 + 6 * j;
+      vo[0] = lin.x * f.vel_scale; vo[1] = lin.y * f.vel_scale; vo[2] = lin.z * f.vel_scale;
+      vo[3] = ang.x * f.vel_scale; vo[4] = ang.y * f.vel_scale; vo[5] = ang.z * f.vel_scale;
+    }
+  }
+}
+
 }  // namespace simstep

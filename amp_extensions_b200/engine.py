@@ -283,6 +283,7 @@ class Engine:
             self._check(self.lib.simstep_load_clip(self._h, C.byref(ch), fr.shape[0], _ptr(fr), _ptr(fv), _ptr(ft),
                                                    float(clip.duration), int(bool(clip.loop_wrap)), _ptr(cd)))
         self.dof = int(fr.shape[1])
+        self.n_joints = int(ch.n_joints)
 
     def imitation_reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False):
         pose, vel = _dev_f32(pose, self.device), _dev_f32(vel, self.device)
@@ -295,6 +296,18 @@ class Engine:
                                                       _ptr(kin_origin), E, _ptr(reward), _ptr(terms),
                                                       _stream(self.device)))
         return (reward, terms) if want_terms else reward
+
+    def record_state(self, pose, vel, record_all_world=False, record_world_root_pos=False,
+                     record_world_root_rot=True, vel_scale=1.0):
+        """Env state features [E, 1 + 15 * n_joints] of generalized poses / velocities (CtController.cpp:378-495);
+        the flag defaults are data/controllers/humanoid3d_rot_ctrl.txt's."""
+        pose, vel = _dev_f32(pose, self.device), _dev_f32(vel, self.device)
+        E = pose.shape[0]
+        out = torch.empty((E, 1 + 15 * self.n_joints), device=self.device, dtype=torch.float32)
+        self._check(self.lib.simstep_record_state(self._h, _ptr(pose), _ptr(vel), E, int(record_all_world),
+                                                  int(record_world_root_pos), int(record_world_root_rot),
+                                                  float(vel_scale), _ptr(out), _stream(self.device)))
+        return out
 
     def clip_sample(self, kin_time, kin_origin=None):
         kin_time = _dev_f32(kin_time, self.device)

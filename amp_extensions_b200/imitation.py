@@ -35,6 +35,17 @@ class ImitationReward:
         """Pose and velocity of the kinematic character at the given clip times: ([E, dof], [E, dof])."""
         return self.engine.clip_sample(kin_time, kin_origin)
 
+    def record_state(self, pose, vel, **flags):
+        """The env's state vector for generalized poses / velocities (CtController.cpp:378-495), e.g. 226 numbers
+        for humanoid3d; flags as in Engine.record_state."""
+        return self.engine.record_state(pose, vel, **flags)
+
+    def reset_states(self, kin_time, kin_origin=None, **flags):
+        """Initial env states for clip times (sim_env.py:270-285 with resolve / noise off: the character is set
+        to the kinematic pose and velocity at `kin_time` and its state is recorded)."""
+        pose, vel = self.sample(kin_time, kin_origin)
+        return self.record_state(pose, vel, **flags)
+
     @staticmethod
     def advance_time(kin_time, num_steps, dt=1.0 / 30.0):
         """Clip time after num_steps policy steps (20 substeps of 1/600 s, gym_deepmimic.py:106-110)."""

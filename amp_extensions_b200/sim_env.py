@@ -64,6 +64,17 @@ class VecSimEnv:
         self._w_dev = None if w is None else w.detach().to(self.device, torch.float32).contiguous()
 
     # -- gym-like surface -------------------------------------------------------------------
+    @staticmethod
+    def clip_reset_fn(imitation, device=None, **record_flags):
+        """reset_fn that starts envs on the reference motion at t ~ U(0, duration), as SimEnv.reset() does through
+        the simulator (sim_env.py:270-285: reset_time(time) then record_state) — here without the simulator: the
+        clip is sampled on the device and the state features are built kinematically
+        (ImitationReward.reset_states; resolve-ground-intersection and noise options are not applied)."""
+        def fn(n, rng):
+            t = torch.as_tensor(rng.uniform(0.0, float(imitation.clip.duration), size=n), dtype=torch.float32)
+            return imitation.reset_states(t.to(imitation.engine.device), **record_flags)
+        return fn
+
     def _draw_initial(self, n):
         if self.reset_fn is not None:
             s = self.reset_fn(n, self.rng)

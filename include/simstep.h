@@ -221,6 +221,17 @@ int simstep_imitation_reward(simstep_handle* h, const float* pose_dev, const flo
 int simstep_clip_sample(simstep_handle* h, const float* kin_time_dev, const float* kin_origin_dev, int64_t n_envs,
                         float* out_pose_dev, float* out_vel_dev, void* stream);
 
+/* Character state features of the env (DeepMimicCore sim/CtController.cpp:378-495, BuildStatePose /
+ * BuildStateVel: what SimEnv.reset() reads through record_state, sim_env.py:270-285) from generalized
+ * pose_dev / vel_dev [n][dof] of the character loaded with simstep_load_clip, body transforms taken
+ * kinematically from the pose (the simulator's state right after SetPose / SetVel), ground plane y = 0:
+ * state_dev [n][1 + 15 * n_joints] = root height | per body (pos[3], normal[3], tangent[3]) | per body
+ * (lin vel[3], ang vel[3]).  The Record* arguments mirror the controller file's RecordAllWorld /
+ * RecordWorldRootPos / RecordWorldRootRot; vel_scale = 1, or 1 / UpdateRate for RecordVelAsPos. */
+int simstep_record_state(simstep_handle* h, const float* pose_dev, const float* vel_dev, int64_t n_envs,
+                         int32_t record_all_world, int32_t record_world_root_pos, int32_t record_world_root_rot,
+                         float vel_scale, float* state_dev, void* stream);
+
 /* MLPCost's feature map (milo/milo/linear_cost.py:154-222): a plain MLP
  *   x -> act(W_0 x + b_0) -> ... -> act(W_{L-1} . + b_{L-1}) -> tanh(W_head . + b_head) -> cos(.) * sqrt(2/D)
  * on a handle created with state_dim = input width, action_dim = 0, n_models = 1, hidden = the MLP's

@@ -419,6 +419,47 @@ def calc_com(ch, pose, vel):
     return com / total, com_vel / total
 
 
+# ---- sim/CtController.cpp: the env's state vector ---------------------------------------------------------
+
+def record_state(ch, pose, vel, record_all_world=False, record_world_root_pos=False, record_world_root_rot=True,
+                 vel_scale=1.0):
+    """cCtController::BuildStatePose / BuildStateVel (CtController.cpp:378-495) for a character whose body parts
+    follow the pose kinematically (cKinTree::BodyWorldTrans, KinTree.cpp:1148-1166; what the simulator holds right
+    after SetPose / SetVel), plane ground at y = 0.  Literal: 4x4 transforms for positions and rotations, the
+    spatial Jacobian (RBDUtil.cpp:225-249, :490-496) for the body velocities.  Flag defaults are those of
+    data/controllers/humanoid3d_rot_ctrl.txt."""
+    pose, vel = np.asarray(pose, dtype=np.float64), np.asarray(vel, dtype=np.float64)
+    nj = len(ch["joint_type"])
+    origin_trans = build_origin_trans(pose)
+    origin_rot = origin_trans[0:3, 0:3]
+    root_pos = np.array([pose[0], pose[1], pose[2], 1.0])
+    root_pos_rel = origin_trans @ root_pos
+    out_pose = np.zeros(1 + 9 * nj)
+    out_vel = np.zeros(6 * nj)
+    out_pose[0] = root_pos_rel[1]
+    for i in range(nj):
+        body_joint = translate_mat(np.asarray(ch["body_attach"][i], dtype=np.float64))
+        world = joint_world_trans(ch, pose, i) @ body_joint
+        pos = world @ np.array([0, 0, 0, 1.0])
+        rot = world[0:3, 0:3]
+        if not record_all_world and (not record_world_root_pos or i != 0):
+            pos = origin_trans @ pos - root_pos_rel
+        if not record_all_world and (not record_world_root_rot or i != 0):
+            rot = origin_rot @ rot
+        out_pose[1 + 9 * i: 4 + 9 * i] = pos[0:3]
+        out_pose[4 + 9 * i: 7 + 9 * i] = rot @ np.array([0, 1.0, 0])   # CalcNormalTangent, MathUtil.cpp:622-628
+        out_pose[7 + 9 * i: 10 + 9 * i] = rot @ np.array([1.0, 0, 0])
+        world_com = (world @ np.array([0, 0, 0, 1.0]))[0:3]
+        sv = end_effector_jacobian(ch, pose, i) @ vel
+        sv = sp_apply_trans_m((np.eye(3), world_com), sv)
+        ang, lin = sv[0:3], sv[3:6]
+        if not record_all_world and (not record_world_root_rot or i != 0):
+            ang, lin = origin_rot @ ang, origin_rot @ lin
+        out_vel[6 * i: 6 * i + 3] = lin * vel_scale
+        out_vel[6 * i + 3: 6 * i + 6] = ang * vel_scale
+    return np.concatenate([out_pose, out_vel])
+
+
 # ---- scenes/SceneImitate.cpp ---------------------------------------------------------------------------
 
 def calc_reward_imitate(ch, pose0, vel0, pose1, vel1, ground_h1=0.0, return_terms=False):

@@ -149,3 +149,43 @@ def test_rows_are_independent(setup):
     assert torch.equal(imit.reward(*[a[perm] for a in args]), r[perm])
     assert torch.equal(imit.reward(*[a[100:133] for a in args]), r[100:133])
     assert imit.reward(*[a[:0] for a in args]).shape == (0,)
+
+
+# ---------------------------------------------------------------------------------------------------
+# record_state: the env's state vector from generalized pose / velocity (CtController.cpp:378-495)
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(record_world_root_rot=False), dict(record_all_world=True),
+                                   dict(record_world_root_pos=True, vel_scale=1.0 / 30.0)])
+def test_record_state_matches_oracle(setup, flags):
+    """fp32 kernel against the float64 literal restatement (4x4 transforms + spatial Jacobian velocities); scale of
+    a position / direction feature is 1, of a velocity feature the sample's own spread."""
+    imit, clip = setup
+    pose, vel, _, _ = H.perturbed_poses(64, seed=7, clip=clip, with_origin=False)
+    st = imit.record_state(torch.from_numpy(pose).float(), torch.from_numpy(vel).float(), **flags).cpu().numpy()
+    ref = np.stack([io.record_state(io.HUMANOID3D, pose[e], vel[e], **flags) for e in range(64)])
+    assert st.shape == (64, 226)
+    np.testing.assert_allclose(st[:, :136], ref[:, :136], rtol=0, atol=REL * 1.0 * 0.05)       # 5e-5 absolute
+    vscale = float(np.abs(ref[:, 136:]).mean())
+    np.testing.assert_allclose(st[:, 136:], ref[:, 136:], rtol=0, atol=REL * max(vscale, 1e-3))
+
+
+def test_clip_reset_states_feed_the_env(setup):
+    """VecSimEnv.clip_reset_fn: envs start on the reference motion; the states are what record_state gives for the
+    sampled clip poses, upright (no fall contact) and within the clip's height range."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, VecSimEnv
+    imit, clip = setup
+    t = torch.linspace(0.0, float(clip.duration) * 0.999, 50)
+    states = imit.reset_states(t.cuda()).cpu().numpy()
+    ref = np.stack([io.record_state(io.HUMANOID3D, clip.kin_pose(float(x)), clip.kin_vel(float(x))) for x in t])
+    np.testing.assert_allclose(states[:, :136], ref[:, :136], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(states[:, 136:], ref[:, 136:], rtol=0, atol=2e-3 * max(1.0, np.abs(ref[:, 136:]).max()))
+    s, a, s2 = H.synth_dataset(512, 226, 28, 0)
+    ens = DynamicsEnsemble(226, 28, AmpDataset(s, a, s2), None, num_models=2, hidden_sizes=[64, 64], dense_connect=True,
+                           transform=True, base_seed=100)
+    env = VecSimEnv(ens, 32, reset_fn=VecSimEnv.clip_reset_fn(imit), seed=3)
+    ob = env.reset().cpu().numpy()
+    assert ob.shape == (32, 226) and np.isfinite(ob).all()
+    assert (ob[:, 0] > 0.6).all() and (ob[:, 0] < 1.3).all()           # root height along the spin kick
+    from oracle import milo_oracle as mo
+    assert not mo.simenv_collided(ob.astype(np.float64)).any()          # the reference motion never falls

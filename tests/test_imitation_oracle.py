@@ -184,3 +184,75 @@ def test_product_clip_tables_equal_the_oracle_tables(clip):
     np.testing.assert_allclose(mc.cycle_delta, clip.cycle_delta, atol=1e-14)
     assert mc.duration == clip.duration and mc.loop_wrap
     np.testing.assert_allclose(ch.joint_weights(), np.asarray(CH["diff_weight"]) / 4.8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# record_state (CtController.cpp:378-495): closed-form answers
+
+
+def _tpose():
+    pose = np.zeros(43)
+    pose[1] = 0.9
+    for j, jt in enumerate(io.HUMANOID3D["joint_type"]):
+        if jt in (io.ROOT, io.SPHERICAL):
+            o = io.param_layout(io.HUMANOID3D)[0][j] + (3 if jt == io.ROOT else 0)
+            pose[o] = 1.0
+    return pose
+
+
+def test_record_state_of_the_t_pose_is_the_skeleton_table():
+    """Identity rotations, zero velocity: body i sits at sum of attach offsets along its chain + its body offset,
+    every normal is +y, every tangent +x, all velocities are 0, state[0] is the root height."""
+    ch = io.HUMANOID3D
+    st = io.record_state(ch, _tpose(), np.zeros(43))
+    assert st.shape == (226,) and st[0] == 0.9
+    for i in range(15):
+        chain, j = np.zeros(3), i
+        while j > 0:
+            chain += np.asarray(ch["attach"][j])
+            j = ch["parent"][j]
+        expect = chain + np.asarray(ch["body_attach"][i])
+        np.testing.assert_allclose(st[1 + 9 * i: 4 + 9 * i], expect, atol=1e-12)
+        np.testing.assert_allclose(st[4 + 9 * i: 7 + 9 * i], [0, 1, 0], atol=1e-12)
+        np.testing.assert_allclose(st[7 + 9 * i: 10 + 9 * i], [1, 0, 0], atol=1e-12)
+    assert not st[136:].any()
+
+
+def test_record_state_is_heading_and_translation_invariant():
+    """Turning the whole character about the vertical axis and moving it in the plane changes nothing but the
+    root's own rotation / velocity features (RecordWorldRootRot = true keeps those in the world frame)."""
+    ch = io.HUMANOID3D
+    clip = io.Clip(RAW, ch, "wrap")
+    pose, vel = clip.kin_pose(0.37), clip.kin_vel(0.37)
+    a = 0.8
+    qy = np.array([np.cos(a / 2), 0, np.sin(a / 2), 0])
+    R = io.rotate_mat_quat(qy)[0:3, 0:3]
+    pose2, vel2 = pose.copy(), vel.copy()
+    pose2[0:3] = R @ pose[0:3] + np.array([1.5, 0, -2.0])
+    pose2[3:7] = io.quat_mul(qy, pose[3:7])
+    vel2[0:3], vel2[3:6] = R @ vel[0:3], R @ vel[3:6]
+    s1, s2 = io.record_state(ch, pose, vel), io.record_state(ch, pose2, vel2)
+    keep = np.ones(226, bool)
+    keep[4:10] = False        # root normal / tangent (world)
+    keep[136:142] = False     # root linear / angular velocity (world)
+    np.testing.assert_allclose(s1[keep], s2[keep], atol=1e-9)
+    np.testing.assert_allclose(s2[4:7], R @ s1[4:7], atol=1e-9)
+    np.testing.assert_allclose(s2[136:139], R @ s1[136:139], atol=1e-9)
+    # with every Record* flag off the root features are in the heading frame too: fully invariant
+    f = dict(record_world_root_rot=False)
+    np.testing.assert_allclose(io.record_state(ch, pose, vel, **f), io.record_state(ch, pose2, vel2, **f), atol=1e-9)
+
+
+def test_record_state_velocities_are_time_derivatives_of_positions():
+    """Body linear velocities equal d/dt of the body positions along the clip (world frame, RecordAllWorld)."""
+    ch = io.HUMANOID3D
+    clip = io.Clip(RAW, ch, "wrap")
+    t, dt = 0.401, 1e-5       # inside one frame interval: the interpolated pose is smooth there
+    p0, p1 = clip.kin_pose(t - dt), clip.kin_pose(t + dt)
+    vel = io.calc_vel(ch, p0, p1, 2 * dt)   # the pose path's own generalized velocity
+    s0 = io.record_state(ch, p0, vel, record_all_world=True)
+    s1 = io.record_state(ch, p1, vel, record_all_world=True)
+    sm = io.record_state(ch, clip.kin_pose(t), vel, record_all_world=True)
+    for i in range(15):
+        fd = (s1[1 + 9 * i: 4 + 9 * i] - s0[1 + 9 * i: 4 + 9 * i]) / (2 * dt)
+        np.testing.assert_allclose(sm[136 + 6 * i: 139 + 6 * i], fd, atol=2e-4)
