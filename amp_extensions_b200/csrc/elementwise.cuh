@@ -60,6 +60,7 @@ __device__ __forceinline__ typename Pair<typename E::storage>::type make_pair_cv
 // walks rows; each thread owns two adjacent columns (XP is even) and stores
 // them as one packed pair.
 constexpr int kPrepThreads = 128;
+constexpr int kPrepRows = 4;
 template <typename E>
 __global__ void __launch_bounds__(kPrepThreads)
 prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A, int XP,
@@ -84,17 +85,36 @@ prep_input_kernel(const float* __restrict__ state, const float* __restrict__ act
       if (tf && src[i] == 0) { mean[i] = tf[col]; scale[i] = tf[S + col]; }
       if (tf && src[i] == 1) { mean[i] = tf[2 * S + col - S]; scale[i] = tf[2 * S + A + col - S]; }
     }
-    for (long long row = blockIdx.x; row < rows_pad; row += gridDim.x) {
-      float v[2] = {0.f, 0.f};
-      if (row < n_rows) {
+    // kPrepRows rows per trip: all their loads are issued before the first is used (bytes in flight, not math,
+    // bound this kernel)
+    for (long long row0 = blockIdx.x; row0 < rows_pad; row0 += static_cast<long long>(gridDim.x) * kPrepRows) {
+      float v[kPrepRows][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = c0 + i;
-          if (src[i] == 0) v[i] = (state[row * S + col] - mean[i]) / scale[i];
-          else if (src[i] == 1) v[i] = (action[row * A + col - S] - mean[i]) / scale[i];
+      for (int r = 0; r < kPrepRows; ++r) {
+        const long long row = row0 + static_cast<long long>(r) * gridDim.x;
+        v[r][0] = v[r][1] = 0.f;
+        if (row < n_rows) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int col = c0 + i;
+            if (src[i] == 0) v[r][i] = state[row * S + col];
+            else if (src[i] == 1) v[r][i] = action[row * A + col - S];
+          }
         }
       }
-      *reinterpret_cast<P*>(x + row * XP + c0) = make_pair_cvt<E>(v[0], v[1]);
+#pragma unroll
+      for (int r = 0; r < kPrepRows; ++r) {
+        const long long row = row0 + static_cast<long long>(r) * gridDim.x;
+        if (row < rows_pad) {
+          float o[2] = {0.f, 0.f};
+          if (row < n_rows) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (src[i] != 2) o[i] = (v[r][i] - mean[i]) / scale[i];
+          }
+          *reinterpret_cast<P*>(x + row * XP + c0) = make_pair_cvt<E>(o[0], o[1]);
+        }
+      }
     }
   }
 }

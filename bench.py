@@ -349,6 +349,26 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     value = E * world * args.steps / (total_ms * 1e-3)
 
+    # ---- diagnostic: the same steps replayed from CUDA graphs (no per-launch CPU work at all) ------------
+    graph_ms = None
+    if args.graph_check and world == 1:
+        graphs = []
+        for k in range(ring):
+            gk = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gk):
+                one_step(k)
+            graphs.append(gk)
+        for i in range(args.warmup):
+            graphs[i % ring].replay()
+        torch.cuda.synchronize(device)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            graphs[i % ring].replay()
+        g1.record()
+        torch.cuda.synchronize(device)
+        graph_ms = g0.elapsed_time(g1) / args.steps
+
     # ---- per-kernel device time (CUDA events inside the library, same workload, separate pass) ----------
     prof_steps = min(args.steps, 50)
     eng.profile_enable(True)
@@ -441,7 +461,7 @@ def run_ours(args):
                 "peak_source": peaks["source"], "algorithmic_flop_per_env_step": flops_per_env_step(),
                 "ms_per_step": gemm_ms,
             },
-            "kernels_ms_per_step": per_step,
+            "kernels_ms_per_step": per_step, "graph_replay_ms_per_step": graph_ms,
             "roofline_hbm": hbm_roofline(post_ms, E, args.precision, peaks),
             "cpu_baseline": cpu,
         }
@@ -462,6 +482,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: no host-buffer pass")
+    ap.add_argument("--graph-check", action="store_true", help="also time the steps replayed from CUDA graphs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

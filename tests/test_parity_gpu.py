@@ -431,3 +431,44 @@ def test_mlp_cost_default_shape_matches_oracle():
                  what="costs")
     with pytest.raises(Exception):   # a feature-net handle is not an env
         cost.engine().step(torch.zeros(4, 452).cuda(), torch.zeros(4, 0).cuda(), None, None)
+
+
+@pytest.mark.parametrize("E", [40000, 39999])
+def test_full_size_fused_step_properties(E):
+    """BASELINE.json configs[1] size through size-independent properties of the fused step (TMA-staged post kernel,
+    odd E exercises its trailing unpaired row): s' - s is exactly the active member's delta, the discrepancy equals
+    the one computed by the stand-alone entry point (different kernel, different summation order), results are
+    equivariant under a permutation of the envs, counters advance by one, the cost is inside its range."""
+    from amp_extensions_b200 import RBFLinearCost
+    from amp_extensions_b200.engine import HumanoidTermination
+    c = H.ns_case()
+    eng = make_engine(c, "fp16")
+    eng.set_termination(HumanoidTermination(horizon=300))
+    cost = RBFLinearCost(H.ns_expert(), feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100)
+    eng.load_rff(cost.rff.weight.data, cost.rff.bias.data, split=True)
+    g = torch.Generator().manual_seed(31)
+    s = H.humanoid_like_states(E, seed=33).cuda()
+    a = torch.randn(E, 28, generator=g).cuda()
+    member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32).cuda()
+    steps = torch.randint(0, 299, (E,), generator=g, dtype=torch.int32).cuda()
+    w = (torch.randn(512, generator=g) * 0.02).cuda()
+    st = steps.clone()
+    nxt, disc, done, cst, ipm, bonus = eng.step_cost(s, a, member, st, w, 0.0025, 0.35)
+    assert torch.equal(st, steps + 1)
+    # linearity: the same pass's member deltas, re-read through the forward entry point in slices
+    for r0 in range(0, E, 8192):
+        r1 = min(E, r0 + 8192)
+        f = eng.forward(s[r0:r1], a[r0:r1])
+        act = f[member[r0:r1].long(), torch.arange(r1 - r0, device="cuda")]
+        assert torch.equal(nxt[r0:r1], s[r0:r1] + act)
+    d2 = eng.discrepancy(s, a)
+    assert_close(disc, d2, d2.mean().item(), rel=2e-6, what="disc (fused vs stand-alone kernel)")
+    assert float(cst.min()) >= -1.0 - 1e-6 and float(cst.max()) <= 0.0025 + 1e-6   # (1-l) c - l * bonus, c in [-1, 0]
+    assert torch.equal(cst, ipm - bonus)
+    perm = torch.randperm(E, generator=g).cuda()
+    st2 = steps[perm].clone()
+    nxt2, disc2, done2, cst2, _, _ = eng.step_cost(s[perm].contiguous(), a[perm].contiguous(), member[perm].contiguous(),
+                                                  st2, w, 0.0025, 0.35)
+    assert torch.equal(nxt2, nxt[perm]) and torch.equal(disc2, disc[perm])
+    assert torch.equal(done2, done[perm]) and torch.equal(cst2, cst[perm])
+    assert 0 < int(done.sum()) < E
