@@ -102,6 +102,7 @@ _SIGNATURES = {
                                        C.c_float, _c_void_p, _c_void_p]),
     "simstep_load_feature_net": (C.c_int, [_c_void_p, C.POINTER(_c_void_p), C.POINTER(_c_void_p), C.c_int32, _c_void_p,
                                            _c_void_p, C.c_int32]),
+    "simstep_set_cost_transform": (C.c_int, [_c_void_p, C.c_int32]),
     "simstep_load_policy": (C.c_int, [_c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                       C.POINTER(_c_void_p), C.POINTER(_c_void_p), C.c_int32, _c_void_p, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p]),

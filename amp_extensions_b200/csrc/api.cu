@@ -80,7 +80,8 @@ struct simstep_handle {
   CUtensorMap tmap_rffw, tmap_rffin;
   // feature net (MLPCost): hidden layers of this handle feed the cos-feature head instead of a packed input row
   bool feat_net = false;
-  int feat_tanh = 0;
+  int feat_mode = 0;       // SIMSTEP_HEAD_*
+  int cost_transform = 0;  // SIMSTEP_COST_*
 
   TermConst term{};
   ImitConst* imit_dev = nullptr;
@@ -503,7 +504,9 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
     ga.kb_x = fin.kb_x;   // no hidden layer: the head reads the input rows themselves
     ga.kb_h0 = fin.kb_h0;
     ga.kb_h = fin.kb_h;
-    ga.rff_tanh = h->feat_tanh;
+    ga.rff_tanh = h->feat_mode == SIMSTEP_HEAD_TANH_COS;
+    ga.rff_linear = h->feat_mode == SIMSTEP_HEAD_LINEAR;
+    if (ga.rff_linear) ga.rff_phi_scale = 1.f;
     return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, h->tmap_rffw, h->tmap_h, ga,
                                 h->sm_count, st);
   }
@@ -515,8 +518,8 @@ int launch_combine(simstep_handle* h, const float* disc, long long n, float lamb
                    float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus, cudaStream_t st) {
   ProfScope ps(h, SIMSTEP_PROF_COMBINE, st);
   launch_pdl(cost_combine_kernel, dim3(grid_for(n, 256, h->sm_count)), dim3(256), 0, st, h->rff_part, h->cap_rows,
-             h->D_pad / kBlockN, float(std::sqrt(2.0 / h->D)), disc, n, lambda_b, threshold, c_min, c_max, clamp_cost, dot,
-             cost, ipm, bonus);
+             h->D_pad / kBlockN, (h->feat_net && h->feat_mode == SIMSTEP_HEAD_LINEAR) ? 1.f : float(std::sqrt(2.0 / h->D)),
+             disc, n, lambda_b, threshold, c_min, c_max, clamp_cost, h->cost_transform, dot, cost, ipm, bonus);
   g_launches++;
   CU_TRY(h, cudaGetLastError());
   return SIMSTEP_OK;
@@ -819,9 +822,11 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
 
 int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host, const float* const* biases_host,
                              int32_t feature_dim, const float* head_weight_host, const float* head_bias_host,
-                             int32_t head_tanh) {
+                             int32_t head_mode) {
   if (!h || !weights_host || !biases_host || !head_weight_host || !head_bias_host || feature_dim < 1)
     return fail(h, SIMSTEP_EINVAL, "bad argument");
+  if (head_mode != SIMSTEP_HEAD_TANH_COS && head_mode != SIMSTEP_HEAD_LINEAR)
+    return fail(h, SIMSTEP_EINVAL, "head_mode must be SIMSTEP_HEAD_TANH_COS or SIMSTEP_HEAD_LINEAR");
   if (h->N != 1 || h->A != 0 || h->cfg.transform || h->cfg.dense_connect)
     return fail(h, SIMSTEP_EINVAL,
                 "a feature net needs a handle with n_models = 1, action_dim = 0, transform = 0 and dense_connect = 0");
@@ -867,10 +872,17 @@ int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host
   rc = encode_operand(h, &h->tmap_rffw, h->cfg.precision, h->rff_w, h->RKT, h->D_pad, h->RKT, kBlockN / h->cg);
   if (rc) return rc;
   free_workspace(h);
-  h->feat_tanh = head_tanh ? 1 : 0;
+  h->feat_mode = head_mode;
   h->feat_net = true;
   h->have_rff = true;
   h->have_ensemble = true;
+  return SIMSTEP_OK;
+}
+
+int simstep_set_cost_transform(simstep_handle* h, int32_t transform) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (transform < SIMSTEP_COST_IDENTITY || transform > SIMSTEP_COST_GAIL_LL) return fail(h, SIMSTEP_EINVAL, "bad cost transform");
+  h->cost_transform = transform;
   return SIMSTEP_OK;
 }
 

@@ -402,7 +402,7 @@ __global__ void extract_delta_kernel(const float* __restrict__ ws, long long ws_
 
 __global__ void cost_combine_kernel(const float* __restrict__ part, long long part_stride, int n_parts,
                                     float phi_scale, const float* __restrict__ disc, long long n_rows, float lambda_b,
-                                    float threshold, float c_min, float c_max, int clamp_cost,
+                                    float threshold, float c_min, float c_max, int clamp_cost, int transform,
                                     float* __restrict__ dot_out, float* __restrict__ cost, float* __restrict__ ipm,
                                     float* __restrict__ bonus) {
   ptx::grid_dep_wait();
@@ -412,6 +412,16 @@ __global__ void cost_combine_kernel(const float* __restrict__ part, long long pa
     float dot = 0.f;
     for (int t = 0; t < n_parts; ++t) dot += part[t * part_stride + row];
     dot *= phi_scale;
+    if (transform == SIMSTEP_COST_GAIL_LS) {
+      // GAILCost.get_ls_costs (gail_cost.py:232-238): rewards = 1 - 0.25 (1 - d)^2, clipped at 0; cost = -rewards
+      const float u = 1.f - dot;
+      float r = fmaf(-0.25f * u, u, 1.f);
+      if (r < 0.f) r = 0.f;
+      dot = -r;
+    } else if (transform == SIMSTEP_COST_GAIL_LL) {
+      // GAILCost.get_ll_costs (gail_cost.py:240-246): logsigmoid(d) = min(d, 0) - log1p(exp(-|d|))
+      dot = fminf(dot, 0.f) - log1pf(expf(-fabsf(dot)));
+    }
     if (dot_out) dot_out[row] = dot;
     if (disc == nullptr) continue;
     float c = dot;

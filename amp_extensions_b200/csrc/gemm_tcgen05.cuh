@@ -139,6 +139,7 @@ struct GemmArgs {
   long long rff_part_stride;
   float rff_phi_scale;    // sqrt(2/D)
   int rff_tanh;           // kEpiRff: phi = cos(tanh(pre-activation)) (MLPCost, linear_cost.py:208-221)
+  int rff_linear;         // kEpiRff: phi = pre-activation (discriminator output, gail_cost.py:18-43)
 };
 
 template <typename E, int CG>
@@ -389,7 +390,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           const float4* w4 = reinterpret_cast<const float4*>(args.scale + n0 + c * 32);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = args.rff_tanh ? __cosf(tanhf(v[j])) : fast_cos(v[j]);
+          for (int j = 0; j < 32; ++j)
+            f[j] = args.rff_linear ? v[j] : (args.rff_tanh ? __cosf(tanhf(v[j])) : fast_cos(v[j]));
           if (args.scale != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

@@ -165,7 +165,15 @@ class Engine:
             self._check(self.lib.simstep_load_rff(self._h, w.shape[0], w.shape[1], _ptr(w), _ptr(b), int(bool(split))))
         self.rff_dim, self.rff_in = int(w.shape[0]), int(w.shape[1])
 
-    def load_feature_net(self, weights, biases, head_weight, head_bias, head_tanh=True):
+    HEAD_TANH_COS, HEAD_LINEAR = 1, 2
+    COST_IDENTITY, COST_GAIL_LS, COST_GAIL_LL = 0, 1, 2
+
+    def set_cost_transform(self, transform):
+        """What rff_dot / bonus_cost apply to phi(x).w before the bonus combine (COST_*: identity, or GAILCost's
+        least-squares / log-likelihood costs of a discriminator output, gail_cost.py:232-246)."""
+        self._check(self.lib.simstep_set_cost_transform(self._h, int(transform)))
+
+    def load_feature_net(self, weights, biases, head_weight, head_bias, head_tanh=True, head_mode=None):
         """MLPCost's feature map (linear_cost.py:200-236): hidden nn.Linear layers + the last nn.Linear whose
         output goes through tanh and cos.  The handle must have been created with num_models=1, action_dim=0,
         dense_connect=False, transform=False and hidden_sizes = the hidden layers' widths."""
@@ -177,8 +185,9 @@ class Engine:
         wp = (C.c_void_p * max(nl, 1))(*[w.data_ptr() for w in ws])
         bp = (C.c_void_p * max(nl, 1))(*[b.data_ptr() for b in bs])
         with torch.cuda.device(self.device):
+            mode = head_mode if head_mode is not None else (self.HEAD_TANH_COS if head_tanh else self.HEAD_LINEAR)
             self._check(self.lib.simstep_load_feature_net(self._h, wp, bp, int(hw.shape[0]), _ptr(hw), _ptr(hb),
-                                                          int(bool(head_tanh))))
+                                                          int(mode)))
         self.rff_dim, self.rff_in = int(hw.shape[0]), self.S
 
     # -- ensemble -----------------------------------------------------------------------

@@ -237,12 +237,27 @@ int simstep_record_state(simstep_handle* h, const float* pose_dev, const float* 
  * on a handle created with state_dim = input width, action_dim = 0, n_models = 1, hidden = the MLP's
  * hidden sizes, dense_connect = 0, transform = 0.  weights_host[l] / biases_host[l], l < n_hidden, are the
  * hidden nn.Linear layers; head_weight_host [feature_dim][hidden[L-1]] / head_bias_host the last nn.Linear;
- * head_tanh = 1 applies the tanh the reference puts before the cosine (linear_cost.py:208).  Afterwards
+ * head_mode selects what follows it (SIMSTEP_HEAD_*, below): tanh then the cosine features as in the
+ * reference's MLPCost (linear_cost.py:208-236), or nothing (a discriminator's raw output).  Afterwards
  * simstep_rff_features / simstep_rff_dot / simstep_bonus_cost evaluate this feature map (x_dev rows are
  * state_dim wide); simstep_step* are not available on such a handle. */
 int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host, const float* const* biases_host,
                              int32_t feature_dim, const float* head_weight_host, const float* head_bias_host,
-                             int32_t head_tanh);
+                             int32_t head_mode);
+
+/* head_mode of simstep_load_feature_net */
+#define SIMSTEP_HEAD_TANH_COS 1 /* MLPCost: cos(tanh(.)) * sqrt(2/D) */
+#define SIMSTEP_HEAD_LINEAR 2   /* the last nn.Linear's output itself: GAIL discriminator, gail_cost.py:18-43 */
+
+/* What simstep_rff_dot / simstep_bonus_cost do with the per-row value d = phi(x) . w before the bonus
+ * combine (default SIMSTEP_COST_IDENTITY).  With a LINEAR head of width 1 and w = [1], d is the
+ * discriminator output and the two GAIL settings give GAILCost.get_ls_costs / get_ll_costs
+ * (milo/milo/gail_cost.py:232-246); simstep_bonus_cost with clamp_cost = 0 then is
+ * GAILCost.get_bonus_costs (gail_cost.py:255-283): cost = (1 - lambda_b) c(d) - lambda_b * disc. */
+#define SIMSTEP_COST_IDENTITY 0
+#define SIMSTEP_COST_GAIL_LS 1 /* -(max(1 - 0.25 (1 - d)^2, 0)) */
+#define SIMSTEP_COST_GAIL_LL 2 /* logsigmoid(d) */
+int simstep_set_cost_transform(simstep_handle* h, int32_t transform);
 
 /* ---- on-device rollout helpers ------------------------------------------ */
 

@@ -263,6 +263,33 @@ class MlpCostOracle(RffCostOracle):
             return torch.cos(out) * np.sqrt(2 / self.feature_dim)
 
 
+def gail_disc_forward(ws, bs, x, activation="relu"):
+    """Discriminator.forward (milo/milo/gail_cost.py:18-43): Linear / activation stack, last layer linear."""
+    act = torch.relu if activation == "relu" else torch.tanh
+    out = x.cpu().float()
+    with torch.no_grad():
+        for i in range(len(ws) - 1):
+            out = act(torch.nn.functional.linear(out, ws[i], bs[i]))
+        return torch.nn.functional.linear(out, ws[-1], bs[-1])
+
+
+def gail_costs(disc_outs, loss_type="least_squares"):
+    """GAILCost.get_ls_costs / get_ll_costs (gail_cost.py:232-253)."""
+    if loss_type == "least_squares":
+        rewards = 1.0 - 0.25 * (1.0 - disc_outs) ** 2
+        rewards[rewards < 0.0] = 0.0
+        return -rewards
+    return torch.nn.functional.logsigmoid(disc_outs)
+
+
+def gail_bonus_costs(input_cost, discrepancy, lambda_b):
+    """GAILCost.get_bonus_costs (gail_cost.py:255-283) after the input concatenation and the discriminator."""
+    ipm = (1 - lambda_b) * input_cost
+    bonus = lambda_b * discrepancy.view(-1, 1)
+    cost = ipm - bonus
+    return cost, {"bonus": bonus, "ipm": ipm, "v_targ": input_cost, "cost": cost}
+
+
 # --------------------------------------------------------------------------------------
 # sim_env.py  (state in float64, as the reference keeps it)
 

@@ -165,3 +165,31 @@ def test_mlp_cost_oracle_matches_reference(tag):
     assert np.array_equal(total.numpy(), g[f"{tag}/total"])
     for k in ("bonus", "ipm", "v_targ", "cost"):
         assert np.array_equal(info[k].numpy(), g[f"{tag}/info_{k}"]), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# GAILCost evaluation side (gail_cost.py:18-43, 232-283) against the reference's own outputs
+
+GAIL_CASES = ["ls_two_hidden", "ll_small", "ls_linear"]
+
+
+def _gail_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gail_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", GAIL_CASES)
+def test_gail_cost_oracle_matches_reference(tag):
+    g = _gail_golden()
+    n = int(g[f"{tag}/n_linear"])
+    ws = [torch.from_numpy(g[f"{tag}/w{i}"]) for i in range(n)]
+    bs = [torch.from_numpy(g[f"{tag}/b{i}"]) for i in range(n)]
+    ss = torch.cat([torch.from_numpy(g["xs"]), torch.from_numpy(g["next"])], dim=1)
+    d = mo.gail_disc_forward(ws, bs, ss)
+    assert np.array_equal(d.numpy(), g[f"{tag}/disc_outs"])
+    c = mo.gail_costs(d.clone(), str(g[f"{tag}/loss_type"]))
+    assert np.array_equal(c.numpy(), g[f"{tag}/costs"])
+    total, info = mo.gail_bonus_costs(c, torch.from_numpy(g["disc"]), float(g[f"{tag}/lambda_b"]))
+    assert np.array_equal(total.numpy(), g[f"{tag}/total"])
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        assert np.array_equal(info[k].numpy(), g[f"{tag}/info_{k}"]), k

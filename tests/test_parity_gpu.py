@@ -472,3 +472,65 @@ def test_full_size_fused_step_properties(E):
     assert torch.equal(nxt2, nxt[perm]) and torch.equal(disc2, disc[perm])
     assert torch.equal(done2, done[perm]) and torch.equal(cst2, cst[perm])
     assert 0 < int(done.sum()) < E
+
+
+# ---------------------------------------------------------------------------------------------------
+# GAILCost evaluation side (gail_cost.py:232-283): discriminator through the grouped GEMM, linear head
+
+
+class _RefDisc:
+    """The attributes of the reference Discriminator / GAILCost that the device wrapper reads."""
+
+    def __init__(self, ws, bs, activation="relu"):
+        import torch.nn as nn
+        lin = [nn.Linear(w.shape[1], w.shape[0]) for w in ws]
+        for l, w, b in zip(lin, ws, bs):
+            l.weight.data, l.bias.data = w.clone(), b.clone()
+        self.activation = nn.ReLU() if activation == "relu" else nn.Tanh()
+        if len(lin) == 1:
+            self.net = lin[0]
+        else:
+            layers = [lin[0]]
+            for l in lin[1:]:
+                layers += [self.activation, l]
+            self.net = nn.Sequential(*layers)
+
+
+class _RefGail:
+    def __init__(self, ws, bs, loss_type, lambda_b, input_type="ss"):
+        self.disc = _RefDisc(ws, bs)
+        self.disc_loss_type, self.lambda_b, self.input_type = loss_type, lambda_b, input_type
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("tag", ["ls_two_hidden", "ll_small", "ls_linear"])
+def test_gail_cost_matches_reference(tag, prec):
+    import os
+    from amp_extensions_b200 import GAILCost
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gail_golden.npz"))
+    n = int(g[f"{tag}/n_linear"])
+    ws = [torch.from_numpy(g[f"{tag}/w{i}"]) for i in range(n)]
+    bs = [torch.from_numpy(g[f"{tag}/b{i}"]) for i in range(n)]
+    ref = _RefGail(ws, bs, str(g[f"{tag}/loss_type"]), float(g[f"{tag}/lambda_b"]))
+    cost = GAILCost(ref, precision=prec)
+    assert cost.lambda_b == ref.lambda_b                      # attributes are the reference object's
+    xs, xa, nxt = (torch.from_numpy(g[k]) for k in ("xs", "xa", "next"))
+    ss = torch.cat([xs, nxt], dim=1)
+    d_ref = torch.from_numpy(g[f"{tag}/disc_outs"])
+    dscale = max(d_ref.abs().max().item(), 1.0)
+    assert_close(cost.disc_outputs(ss), d_ref, dscale, what="disc outputs")
+    c_ref = torch.from_numpy(g[f"{tag}/costs"])
+    # the cost is a smooth function of d with slope <= 0.5 * (1 + |d|): same relative budget on its own scale
+    cscale = max(c_ref.abs().max().item(), dscale)
+    assert_close(cost.get_costs(ss), c_ref, cscale, what="costs")
+    total, info = cost.get_bonus_costs(xs, xa, _FixedDiscEnsemble(torch.from_numpy(g["disc"]), 1.0), next_states=nxt)
+    assert_close(total, torch.from_numpy(g[f"{tag}/total"]), cscale, what="total")
+    for k in ("bonus", "ipm", "v_targ", "cost"):
+        assert_close(info[k], torch.from_numpy(g[f"{tag}/info_{k}"]), cscale, what=k)
+    # after an in-place parameter update (what disc_opt.step() does) the packed weights are refreshed
+    with torch.no_grad():
+        for l in cost._linears():
+            l.weight.mul_(0.5)
+    ws2 = [w * 0.5 for w in ws]
+    d2 = mo.gail_disc_forward(ws2, bs, ss)
+    assert_close(cost.disc_outputs(ss), d2, max(d2.abs().max().item(), 1.0), what="disc outputs after update")
