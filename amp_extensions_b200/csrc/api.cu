@@ -507,7 +507,7 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
     ga.rff_tanh = h->feat_mode == SIMSTEP_HEAD_TANH_COS;
     ga.rff_linear = h->feat_mode == SIMSTEP_HEAD_LINEAR;
     if (ga.rff_linear) ga.rff_phi_scale = 1.f;
-    return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, h->tmap_rffw, h->tmap_h, ga,
+    return launch_gemm<kEpiFeat>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, h->tmap_rffw, h->tmap_h, ga,
                                 h->sm_count, st);
   }
   return launch_gemm<kEpiRff>(h, h->cfg.precision, h->cg, h->tmap_rffin, h->tmap_rffin, h->tmap_rffw, h->tmap_rffin, ga,

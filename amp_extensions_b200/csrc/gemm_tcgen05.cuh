@@ -111,7 +111,10 @@ struct ElemDims {
   static constexpr int kUmmaK = 32 / sizeof(typename E::storage);    // K of one tcgen05.mma
 };
 
-enum EpiMode : int { kEpiHidden = 0, kEpiFinal = 1, kEpiRff = 2, kEpiHiddenTanh = 3 };
+// kEpiFeat is kEpiRff with the feature-net heads (tanh before the cosine, or no nonlinearity at all) selected at run
+// time; it is a separate instantiation so that the random-feature kernel of the env step carries none of that code.
+enum EpiMode : int { kEpiHidden = 0, kEpiFinal = 1, kEpiRff = 2, kEpiHiddenTanh = 3, kEpiFeat = 4 };
+__host__ __device__ constexpr bool epi_is_rff(int mode) { return mode == kEpiRff || mode == kEpiFeat; }
 
 struct GemmArgs {
   // tile space: tile -> (group, m_tile, n_tile), n fastest; an m_tile is CG * 128 rows
@@ -159,6 +162,13 @@ __device__ __forceinline__ float fast_cos(float x) {
   return __cosf(r);
 }
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU: absolute error < 5e-7 everywhere (it feeds a cosine, so the absolute
+// error is what matters); saturates to +-1 through exp's overflow / underflow.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, t + 1.f);
+}
+
 template <typename E, int MODE, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_constant__ CUtensorMap tmap_ah,
@@ -169,7 +179,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
   constexpr int UK = ElemDims<E>::kUmmaK;
   constexpr int kMmasPerBlock = BK / UK;  // 4
   constexpr int kStages = S::kStages;
-  constexpr bool kStoreTile = (MODE != kEpiRff);
+  constexpr bool kStoreTile = !epi_is_rff(MODE);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -389,9 +399,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           const long long row = static_cast<long long>(m_row) + row_in_tile;
           const float4* w4 = reinterpret_cast<const float4*>(args.scale + n0 + c * 32);
           float f[32];
+          if constexpr (MODE == kEpiFeat) {
+            if (args.rff_linear) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            f[j] = args.rff_linear ? v[j] : (args.rff_tanh ? __cosf(tanhf(v[j])) : fast_cos(v[j]));
+              for (int j = 0; j < 32; ++j) f[j] = v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __cosf(fast_tanh(v[j]));  // |tanh| <= 1: no range reduction needed
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fast_cos(v[j]);
+          }
           if (args.scale != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -428,7 +447,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
         }
         process(rb, c + 1);
       }
-      if constexpr (MODE == kEpiRff) {
+      if constexpr (epi_is_rff(MODE)) {
         const long long row = static_cast<long long>(m_row) + row_in_tile;
         if (args.rff_part != nullptr && row < args.rows_valid)
           args.rff_part[size_t(n_tile) * args.rff_part_stride + row] = dot;

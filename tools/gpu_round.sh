@@ -11,6 +11,8 @@ python bench.py --impl reference --steps 5 --warmup 3 > $OUT/${TAG}_bench_ref.js
 python bench.py --steps 300 --warmup 10 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench=$?"
 python tools/bench_imitation.py > $OUT/${TAG}_imit.json 2> $OUT/${TAG}_imit.err; echo "imit=$?"
 python tools/bench_imitation.py --origin --terms >> $OUT/${TAG}_imit.json 2>> $OUT/${TAG}_imit.err
+python tools/bench_rollout.py > $OUT/${TAG}_rollout.json 2> $OUT/${TAG}_rollout.err; echo "rollout=$?"
+python tools/bench_mlpcost.py > $OUT/${TAG}_mlpcost.json 2> $OUT/${TAG}_mlpcost.err; echo "mlpcost=$?"
 if [ "${NCU:-1}" = "1" ]; then
 python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
