@@ -30,6 +30,8 @@ thread_local std::string g_create_error;
 
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
+constexpr int kMaxDevices = 64;  // per-device bookkeeping of kernel attributes / scratch buffers
+
 struct Layer {
   int in_ref = 0;   // reference nn.Linear in_features
   int out = 0;      // out_features
@@ -192,12 +194,15 @@ int encode_operand(simstep_handle* h, CUtensorMap* map, int prec, void* base, lo
 template <typename E, int MODE, int CG>
 int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
                   const CUtensorMap& out, const GemmArgs& ga, int sm_count, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};  // function attributes are per device
   auto kern = gemm_tcgen05_kernel<E, MODE, CG>;
   constexpr size_t smem = GemmShape<CG>::smem_bytes();
-  if (!attr_set) {
+  int dev = h ? h->device : 0;  // h is null for simstep_debug_gemm: use the calling thread's current device
+  if (!h) CU_TRY(h, cudaGetDevice(&dev));
+  bool& attr_done = attr_set[dev % kMaxDevices];
+  if (!attr_done) {
     CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_set = true;
+    attr_done = true;
   }
   const int total = ga.m_tiles * ga.n_tiles * ga.groups;
   if (total <= 0) return SIMSTEP_OK;
@@ -419,8 +424,8 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
 #define POST_TMA_LAUNCH(NM, ET)                                                                                \
   do {                                                                                                         \
     auto kern = h->S == 226 ? post_step_tma_kernel<NM, ET, 226> : post_step_tma_kernel<NM, ET, 0>;             \
-    static size_t attr_smem[2] = {0, 0};                                                                       \
-    size_t& attr_ref = attr_smem[h->S == 226 ? 1 : 0];                                                                               \
+    static size_t attr_smem[kMaxDevices][2] = {};  /* function attributes are per device */                   \
+    size_t& attr_ref = attr_smem[h->device % kMaxDevices][h->S == 226 ? 1 : 0];                                                                               \
     if (attr_ref < plan.smem) {                                                                                \
       CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem)));      \
       attr_ref = plan.smem;                                                                                    \
@@ -574,8 +579,19 @@ int upload_layer(simstep_handle* h, int l, const float* const* weights_host, con
 void free_clip(simstep_handle* h);
 void free_policy(simstep_handle* h);
 
+// A handle's buffers, tensor maps and kernel attributes belong to the device it was created on; work can only be
+// enqueued from a thread whose current device is that one (one process per GPU does this by construction).
+int check_device(simstep_handle* h) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device)
+    return fail(h, SIMSTEP_EINVAL, "the handle was created on device " + std::to_string(h->device) +
+                                       " but the calling thread's current device is " + std::to_string(dev));
+  return SIMSTEP_OK;
+}
+
 int check_step_ready(simstep_handle* h, long long n_envs) {
   if (!h) return SIMSTEP_EINVAL;
+  if (int rc = check_device(h)) return rc;
   if (h->feat_net) return fail(h, SIMSTEP_EINVAL, "this handle holds a cost feature net, not a dynamics ensemble");
   if (!h->have_ensemble) return fail(h, SIMSTEP_EINVAL, "simstep_load_ensemble has not been called");
   if (n_envs < 0) return fail(h, SIMSTEP_EINVAL, "n_envs < 0");
@@ -985,6 +1001,7 @@ int simstep_rff_features(simstep_handle* h, const float* x_dev, int64_t n_rows, 
                          void* stream) {
   if (!h) return SIMSTEP_EINVAL;
   if (!h->have_rff) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (int rc0 = check_device(h)) return rc0;
   if (n_rows < 0 || (n_rows > 0 && (!x_dev || !phi_dev))) return fail(h, SIMSTEP_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
@@ -1024,6 +1041,7 @@ int simstep_bonus_cost(simstep_handle* h, const float* x_dev, const float* disc_
                        int32_t clamp_cost, float* cost_dev, float* ipm_dev, float* bonus_dev, void* stream) {
   if (!h) return SIMSTEP_EINVAL;
   if (!h->have_rff) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (int rc0 = check_device(h)) return rc0;
   if (n_rows < 0) return fail(h, SIMSTEP_EINVAL, "n_rows < 0");
   if (n_rows == 0) return SIMSTEP_OK;
   if (!x_dev || !w_dev) return fail(h, SIMSTEP_EINVAL, "null device pointer");
