@@ -20,6 +20,7 @@
 #include "imitation_h3d.cuh"
 #include "policy.cuh"
 #include "post_tma.cuh"
+#include "train.cuh"
 
 using namespace simstep;
 
@@ -88,6 +89,8 @@ struct simstep_handle {
   TermConst term{};
   ImitConst* imit_dev = nullptr;
   void* policy = nullptr;  // PolicyStore (policy_api.inc)
+  void* train = nullptr;   // TrainStore (train_api.inc)
+  bool train_raw = false;  // tf32 handle in training: parameters keep all fp32 bits (they are the master copy)
   bool have_clip = false;
   int dof = 0;
 
@@ -565,7 +568,7 @@ int upload_layer(simstep_handle* h, int l, const float* const* weights_host, con
     if (!wsrc || !bsrc) { cudaFree(tmp); return fail(h, SIMSTEP_EINVAL, "null weight or bias pointer"); }
     CU_TRY(h, cudaMemcpyAsync(tmp, wsrc, size_t(ly.out) * ly.in_ref * sizeof(float), cudaMemcpyHostToDevice, st));
     void* dst = static_cast<char*>(ly.w) + size_t(m) * ly.o_pad * ly.k_pad * h->esize;
-    int rc = pack_matrix(h, h->cfg.precision, tmp, ly.in_ref, ly.out, dst, ly.k_pad, ly.segs, 0, st);
+    int rc = pack_matrix(h, h->cfg.precision, tmp, ly.in_ref, ly.out, dst, ly.k_pad, ly.segs, h->train_raw ? 3 : 0, st);
     if (rc) { cudaFree(tmp); return rc; }
     CU_TRY(h, cudaMemcpyAsync(ly.bias + size_t(m) * ly.o_pad, bsrc, size_t(ly.out) * sizeof(float),
                               cudaMemcpyHostToDevice, st));
@@ -578,6 +581,7 @@ int upload_layer(simstep_handle* h, int l, const float* const* weights_host, con
 
 void free_clip(simstep_handle* h);
 void free_policy(simstep_handle* h);
+void free_train(simstep_handle* h);
 
 // A handle's buffers, tensor maps and kernel attributes belong to the device it was created on; work can only be
 // enqueued from a thread whose current device is that one (one process per GPU does this by construction).
@@ -711,6 +715,7 @@ int simstep_destroy(simstep_handle* h) {
   cudaFree(h->colsum_partial);
   free_clip(h);
   free_policy(h);
+  free_train(h);
   delete h;
   return SIMSTEP_OK;
 }
@@ -1189,3 +1194,4 @@ int simstep_debug_gemm(int32_t precision, int32_t groups, int64_t m, int32_t n, 
 
 #include "imitation_api.inc"
 #include "policy_api.inc"
+#include "train_api.inc"

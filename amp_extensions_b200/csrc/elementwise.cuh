@@ -24,7 +24,7 @@ struct PackSegs {
 template <typename E>
 __global__ void pack_weight_kernel(const float* __restrict__ src, int src_pitch, int rows,
                                    typename E::storage* __restrict__ dst, long long dst_pitch, PackSegs segs,
-                                   int mode /*0 value, 1 hi, 2 lo*/) {
+                                   int mode /*0 value, 1 hi, 2 lo, 3 raw fp32 bits (training master copy)*/) {
   const int o = blockIdx.x;
   if (o >= rows) return;
   for (int s = 0; s < segs.n; ++s) {
@@ -32,7 +32,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int src_pitch,
       const float v = src[size_t(o) * src_pitch + segs.src0[s] + i];
       float out = v;
       if (mode == 2) out = v - static_cast<float>(E::cvt(v));
-      dst[size_t(o) * dst_pitch + segs.dst0[s] + i] = E::cvt(out);
+      dst[size_t(o) * dst_pitch + segs.dst0[s] + i] = mode == 3 ? static_cast<typename E::storage>(v) : E::cvt(out);
     }
   }
 }

@@ -394,3 +394,49 @@ class Engine:
         self._check(self.lib.simstep_whiten(self._h, _ptr(x), _ptr(valid), x.numel(), _ptr(stats), float(eps), _ptr(out),
                                             _stream(self.device)))
         return out
+
+    # -- training (tf32 handles only) ---------------------------------------------------
+    TRAIN_PARAMS, TRAIN_GRADS, TRAIN_MOMENTS = 0, 1, 2
+
+    def train_init(self, max_batch_rows, optim="sgd", lr=1e-4, momentum=0.9, beta2=0.999, eps=1e-8):
+        """Prepare the handle for DynamicsModel.train_step on device (dynamics.py:236-250).  optim: "sgd"
+        (torch.optim.SGD, nesterov=True, as dynamics.py:199) or "adam" (momentum = beta1).  Call before
+        load_ensemble: parameters loaded afterwards keep all their fp32 bits."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_train_init(self._h, int(max_batch_rows), 0 if optim == "sgd" else 1, float(lr),
+                                                    float(momentum), float(beta2), float(eps)))
+
+    def _train_call(self, fn, state, action, next_state, *extra):
+        s, a, s2 = _dev_f32(state, self.device), _dev_f32(action, self.device), _dev_f32(next_state, self.device)
+        assert s.dim() == 3 and s.shape[0] == self.N, "training batches are [n_models, batch_rows, dim]"
+        loss = torch.zeros((self.N,), device=self.device, dtype=torch.float64)
+        self._check(fn(self._h, _ptr(s), _ptr(a), _ptr(s2), int(s.shape[1]), *extra, _ptr(loss), _stream(self.device)))
+        return loss
+
+    def train_step(self, state, action, next_state, grad_clip=0.0):
+        """One optimisation step of every member on its own batch; returns the members' losses (CUDA fp64 [N])."""
+        return self._train_call(self.lib.simstep_train_step, state, action, next_state, C.c_float(float(grad_clip)))
+
+    def train_loss(self, state, action, next_state):
+        """DynamicsModel.validate_step (dynamics.py:252-262) for every member."""
+        return self._train_call(self.lib.simstep_train_loss, state, action, next_state)
+
+    def train_grads(self, state, action, next_state):
+        """Forward + backward without an update; read the gradients with train_export(TRAIN_GRADS)."""
+        return self._train_call(self.lib.simstep_train_grads, state, action, next_state)
+
+    def train_export(self, what=0):
+        """(weights[m][l], biases[m][l]) CPU tensors in nn.Linear layout: parameters, last gradients or the first
+        optimiser moment."""
+        n_layers = C.c_int32()
+        lin = (C.c_int32 * 16)()
+        lout = (C.c_int32 * 16)()
+        self._check(self.lib.simstep_query(self._h, C.byref(n_layers), lin, lout, None, None))
+        nl = n_layers.value
+        ws = [[torch.empty((lout[l], lin[l]), dtype=torch.float32) for l in range(nl)] for _ in range(self.N)]
+        bs = [[torch.empty((lout[l],), dtype=torch.float32) for l in range(nl)] for _ in range(self.N)]
+        wp = (C.c_void_p * (self.N * nl))(*[ws[m][l].data_ptr() for m in range(self.N) for l in range(nl)])
+        bp = (C.c_void_p * (self.N * nl))(*[bs[m][l].data_ptr() for m in range(self.N) for l in range(nl)])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.simstep_train_export(self._h, int(what), wp, bp))
+        return ws, bs

@@ -314,6 +314,35 @@ int simstep_moments(simstep_handle* h, const float* x_dev, const uint8_t* valid_
 int simstep_whiten(simstep_handle* h, const float* x_dev, const uint8_t* valid_dev, int64_t n, const double* stats_dev,
                    float eps, float* out_dev, void* stream);
 
+/* ---- ensemble training (milo/milo/dynamics.py:236-250, DynamicsModel.train_step) ------------------- */
+
+/* All n_models members take one optimisation step per call, each on its own batch of batch_rows
+ * transitions: forward on normalised inputs (unnormalize_out = False), MSE against the normalised state
+ * difference, backward, optional clip_grad_norm_(grad_clip) per member, then torch.optim.SGD(nesterov=True)
+ * (optimizer = 0; lr, momentum) or torch.optim.Adam (optimizer = 1; lr, momentum = beta1, beta2, eps).
+ * The handle must have been created with SIMSTEP_PREC_TF32: the fp32 parameters inside the handle are
+ * the master copy and the tensor-core operands at once.  Call simstep_train_init BEFORE
+ * simstep_load_ensemble so that the parameters are stored with all their bits.
+ *   state_dev / next_state_dev [n_models][batch_rows][state_dim], action_dev [n_models][batch_rows][action_dim]
+ *   loss_dev [n_models] fp64: each member's mean-squared error on its batch (before the update)
+ * simstep_train_loss is DynamicsModel.validate_step (dynamics.py:252-262): forward + loss only.
+ * simstep_train_grads runs forward + backward and leaves the gradients in the handle (no update).
+ * simstep_train_export copies parameters, the last gradients or the first optimiser moment (SGD momentum
+ * buffer / Adam exp_avg) back in nn.Linear layout: weights_host[m * n_layers + l] -> float[out][in],
+ * biases_host[...] -> float[out] (NULL entries are skipped). */
+#define SIMSTEP_TRAIN_PARAMS 0
+#define SIMSTEP_TRAIN_GRADS 1
+#define SIMSTEP_TRAIN_MOMENTS 2
+int simstep_train_init(simstep_handle* h, int32_t max_batch_rows, int32_t optimizer, float lr, float momentum,
+                       float beta2, float eps);
+int simstep_train_step(simstep_handle* h, const float* state_dev, const float* action_dev, const float* next_state_dev,
+                       int32_t batch_rows, float grad_clip, double* loss_dev, void* stream);
+int simstep_train_loss(simstep_handle* h, const float* state_dev, const float* action_dev, const float* next_state_dev,
+                       int32_t batch_rows, double* loss_dev, void* stream);
+int simstep_train_grads(simstep_handle* h, const float* state_dev, const float* action_dev, const float* next_state_dev,
+                        int32_t batch_rows, double* loss_dev, void* stream);
+int simstep_train_export(simstep_handle* h, int32_t what, float* const* weights_host, float* const* biases_host);
+
 /* ---- reductions used by the multi-GPU host code ------------------------- */
 
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */

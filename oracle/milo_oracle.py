@@ -290,6 +290,57 @@ def gail_bonus_costs(input_cost, discrepancy, lambda_b):
     return cost, {"bonus": bonus, "ipm": ipm, "v_targ": input_cost, "cost": cost}
 
 
+class TrainOracle:
+    """DynamicsModel.train_step / validate_step for one member (DYN:236-262) restated with torch autograd on the
+    CPU: BasicMLP forward on normalised inputs (DYN:422-433), MSE against the normalised difference, backward,
+    optional clip_grad_norm_, torch.optim.SGD(nesterov=True) or torch.optim.Adam (DYN:198-203)."""
+
+    def __init__(self, ws, bs, transforms, dense_connect=True, activation="relu", optim_args=None):
+        optim_args = optim_args or {"optim": "sgd", "lr": 1e-4, "momentum": 0.9}
+        self.ws = [nn.Parameter(w.clone().float()) for w in ws]
+        self.bs = [nn.Parameter(b.clone().float()) for b in bs]
+        self.tf = transforms
+        self.dense, self.activation = dense_connect, activation
+        params = [p for pair in zip(self.ws, self.bs) for p in pair]   # nn.Module order: weight, bias per layer
+        self.params = params
+        if optim_args["optim"] == "sgd":
+            self.opt = torch.optim.SGD(params, lr=optim_args["lr"], momentum=optim_args["momentum"], nesterov=True)
+        else:
+            self.opt = torch.optim.Adam(params, lr=optim_args["lr"], eps=optim_args["eps"])
+
+    def _loss(self, state, action, next_state):
+        sm, ss, am, as_, dm, dsc = self.tf if self.tf is not None else (0, 1, 0, 1, 0, 1)
+        x = torch.cat([(state - sm) / ss, (action - am) / as_], dim=-1) if self.tf is not None else \
+            torch.cat([state, action], dim=-1)
+        act = torch.relu if self.activation == "relu" else torch.tanh
+        inp = x
+        for i in range(len(self.ws) - 1):
+            out = act(torch.nn.functional.linear(inp, self.ws[i], self.bs[i]))
+            inp = torch.cat([inp, out], dim=-1) if self.dense else out
+        pred = torch.nn.functional.linear(inp, self.ws[-1], self.bs[-1])
+        target = next_state - state
+        if self.tf is not None:
+            target = (target - dm) / dsc
+        return torch.nn.functional.mse_loss(pred, target)
+
+    def validate_step(self, state, action, next_state):
+        with torch.no_grad():
+            return self._loss(state, action, next_state).item()
+
+    def grads(self, state, action, next_state):
+        self.opt.zero_grad()
+        loss = self._loss(state, action, next_state)
+        loss.backward()
+        return loss.item()
+
+    def train_step(self, grad_clip, state, action, next_state):
+        loss = self.grads(state, action, next_state)
+        if grad_clip:
+            nn.utils.clip_grad_norm_(self.params, grad_clip)
+        self.opt.step()
+        return loss
+
+
 # --------------------------------------------------------------------------------------
 # sim_env.py  (state in float64, as the reference keeps it)
 

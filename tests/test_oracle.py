@@ -193,3 +193,48 @@ def test_gail_cost_oracle_matches_reference(tag):
     assert np.array_equal(total.numpy(), g[f"{tag}/total"])
     for k in ("bonus", "ipm", "v_targ", "cost"):
         assert np.array_equal(info[k].numpy(), g[f"{tag}/info_{k}"]), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# DynamicsModel.train_step (dynamics.py:236-250) against the reference's own three steps
+
+
+def _train_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_golden.npz"))
+
+
+def train_case(g, tag):
+    dims = g[f"{tag}/dims"].tolist()
+    S, A, N, dense, B = dims[:5]
+    hidden = dims[5:]
+    nl = len(hidden) + 1
+    tf = tuple(torch.from_numpy(g[f"{tag}/tf{i}"]) for i in range(6))
+    optim = {"optim": str(g[f"{tag}/optim"]), "lr": float(g[f"{tag}/lr"]), "momentum": 0.9, "eps": 1e-8}
+    ws = [[torch.from_numpy(g[f"{tag}/init/m{k}/fc_layers.{l}.weight"]) for l in range(nl)] for k in range(N)]
+    bs = [[torch.from_numpy(g[f"{tag}/init/m{k}/fc_layers.{l}.bias"]) for l in range(nl)] for k in range(N)]
+    data = tuple(torch.from_numpy(g[k]) for k in ("ds_s", "ds_a", "ds_s2"))
+    return dict(S=S, A=A, N=N, dense=bool(dense), B=B, hidden=hidden, nl=nl, tf=tf, optim=optim, ws=ws, bs=bs,
+                act=str(g[f"{tag}/act"]), clip=float(g[f"{tag}/clip"]), idx=torch.from_numpy(g["idx"]), data=data)
+
+
+@pytest.mark.parametrize("tag", ["sgd_dense", "adam_plain_tanh"])
+def test_train_oracle_matches_reference(tag):
+    g = _train_golden()
+    c = train_case(g, tag)
+    s, a, s2 = c["data"]
+    for k in range(c["N"]):
+        o = mo.TrainOracle(c["ws"][k], c["bs"][k], c["tf"], c["dense"], c["act"], c["optim"])
+        bi = c["idx"][0, k]
+        assert o.validate_step(s[bi], a[bi], s2[bi]) == float(g[f"{tag}/val0/m{k}"])
+        o.grads(s[bi], a[bi], s2[bi])
+        for l in range(c["nl"]):
+            assert np.array_equal(o.ws[l].grad.numpy(), g[f"{tag}/grad0/m{k}/fc_layers.{l}.weight"])
+            assert np.array_equal(o.bs[l].grad.numpy(), g[f"{tag}/grad0/m{k}/fc_layers.{l}.bias"])
+        for step in range(3):
+            bi = c["idx"][step, k]
+            loss = o.train_step(c["clip"], s[bi], a[bi], s2[bi])
+            assert loss == float(g[f"{tag}/loss/m{k}"][step])
+            for l in range(c["nl"]):
+                assert np.array_equal(o.ws[l].detach().numpy(), g[f"{tag}/step{step}/m{k}/fc_layers.{l}.weight"])
+                assert np.array_equal(o.bs[l].detach().numpy(), g[f"{tag}/step{step}/m{k}/fc_layers.{l}.bias"])

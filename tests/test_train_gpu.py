@@ -1,0 +1,155 @@
+"""GPU parity of the ensemble training step (reference milo/milo/dynamics.py:236-262)
+through the C ABI: losses, gradients and parameters after three optimiser steps against the reference's own
+DynamicsModel.train_step outputs (tests/golden/train_golden.npz) and against the torch-autograd oracle at the
+north-star shape.
+
+Tolerance: operands are tf32 (10-bit mantissa) with fp32 accumulation, the reference is fp32 throughout.  Losses
+and validation losses: 1e-3 relative (north star).  A gradient tensor is compared against its own largest
+magnitude: 4e-3 (two chained tf32 GEMMs plus tf32-rounded activation gradients).  Parameters after a step are
+compared through the size of the step they took.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import milo_oracle as mo
+from tests import helpers as H
+from tests.test_oracle import _train_golden, train_case
+
+pytestmark = pytest.mark.gpu
+GRAD_REL = 4e-3
+
+
+def make_train_engine(c, max_batch):
+    from amp_extensions_b200.engine import Engine
+    eng = Engine(c["S"], c["A"], c["N"], c["hidden"], dense_connect=c["dense"], activation=c["act"], transform=True,
+                 precision="tf32")
+    o = c["optim"]
+    eng.train_init(max_batch, optim=o["optim"], lr=o["lr"], momentum=o.get("momentum", 0.9), eps=o.get("eps", 1e-8))
+    eng.load_ensemble(c["ws"], c["bs"], c["tf"])
+    return eng
+
+
+def batch(c, step):
+    s, a, s2 = c["data"]
+    bi = c["idx"][step]                       # [N, B]
+    return s[bi].contiguous(), a[bi].contiguous(), s2[bi].contiguous()
+
+
+def rel_to_max(x, ref):
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.mark.parametrize("tag", ["sgd_dense", "adam_plain_tanh"])
+def test_gradients_and_three_steps_match_reference(tag):
+    g = _train_golden()
+    c = train_case(g, tag)
+    eng = make_train_engine(c, c["B"])
+    # parameters round-trip exactly (fp32 master copy, nn.Linear layout restored)
+    ws, bs = eng.train_export(eng.TRAIN_PARAMS)
+    for k in range(c["N"]):
+        for l in range(c["nl"]):
+            assert torch.equal(ws[k][l], c["ws"][k][l]) and torch.equal(bs[k][l], c["bs"][k][l])
+    s, a, s2 = batch(c, 0)
+    val = eng.train_loss(s, a, s2).cpu().numpy()
+    loss = eng.train_grads(s, a, s2).cpu().numpy()
+    gw, gb = eng.train_export(eng.TRAIN_GRADS)
+    for k in range(c["N"]):
+        ref_val = float(g[f"{tag}/val0/m{k}"])
+        assert abs(val[k] - ref_val) <= 1e-3 * ref_val and abs(loss[k] - ref_val) <= 1e-3 * ref_val
+        for l in range(c["nl"]):
+            assert rel_to_max(gw[k][l], g[f"{tag}/grad0/m{k}/fc_layers.{l}.weight"]) < GRAD_REL, (k, l)
+            assert rel_to_max(gb[k][l], g[f"{tag}/grad0/m{k}/fc_layers.{l}.bias"]) < GRAD_REL, (k, l)
+    prev = [[(c["ws"][k][l].numpy(), c["bs"][k][l].numpy()) for l in range(c["nl"])] for k in range(c["N"])]
+    for step in range(3):
+        s, a, s2 = batch(c, step)
+        loss = eng.train_step(s, a, s2, grad_clip=c["clip"]).cpu().numpy()
+        ws, bs = eng.train_export(eng.TRAIN_PARAMS)
+        for k in range(c["N"]):
+            ref_loss = float(g[f"{tag}/loss/m{k}"][step])
+            assert abs(loss[k] - ref_loss) <= 2e-3 * ref_loss, (step, k, loss[k], ref_loss)
+            for l in range(c["nl"]):
+                rw = g[f"{tag}/step{step}/m{k}/fc_layers.{l}.weight"]
+                rb = g[f"{tag}/step{step}/m{k}/fc_layers.{l}.bias"]
+                # error relative to the largest step any entry of this tensor took from its previous value
+                dw = max(np.abs(rw - prev[k][l][0]).max(), 1e-12)
+                db = max(np.abs(rb - prev[k][l][1]).max(), 1e-12)
+                # Adam normalises every coordinate's step to ~lr, so a relative gradient error on a tiny coordinate
+                # moves it by a sizeable share of lr: the budget widens with the step count
+                tol = (0.02 if tag.startswith("sgd") else 0.25) * (step + 1)
+                assert np.abs(ws[k][l].numpy() - rw).max() <= tol * dw, (step, k, l, "weight")
+                assert np.abs(bs[k][l].numpy() - rb).max() <= tol * db, (step, k, l, "bias")
+                prev[k][l] = (rw, rb)
+
+
+@pytest.mark.parametrize("act", ["tanh", "relu"])
+def test_north_star_shape_gradients_match_autograd(act):
+    """4 x (512 x 4) dense-connect, humanoid3d dims, 256-row batches (the reference's batch_size): gradients of
+    every layer against torch autograd on the CPU, members on different batches.
+
+    tanh: every entry within GRAD_REL of the tensor's largest gradient.  relu: the tf32 forward moves
+    pre-activations by ~1e-4 of their scale, so about one unit in a hundred has ONE batch row whose sign differs
+    from the fp32 forward; that row's contribution (not small) appears in / disappears from the unit's gradient
+    row, and propagates thinly into the layers below.  The gradient is exact for the activations the device
+    computed, and the difference to the fp32 reference is sparse: bounded here in the Frobenius norm, with the
+    final layer (no mask between it and the loss) held to the strict per-entry bound."""
+    c = H.ns_case()
+    S, A, N, B = 226, 28, 4, 256
+    s, a, s2 = H.synth_dataset(2048, S, A, 0)
+    cc = dict(S=S, A=A, N=N, hidden=c["hidden"], dense=True, act=act, tf=c["tf"], ws=c["ws"], bs=c["bs"],
+              optim={"optim": "sgd", "lr": 1e-4, "momentum": 0.9})
+    eng = make_train_engine(cc, B)
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, 2048, (N, B), generator=g)
+    sb, ab, s2b = s[idx].contiguous(), a[idx].contiguous(), s2[idx].contiguous()
+    loss = eng.train_grads(sb, ab, s2b).cpu().numpy()
+    gw, gb = eng.train_export(eng.TRAIN_GRADS)
+
+    def check(x, ref, strict, what):
+        x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+        if strict:
+            assert rel_to_max(x, ref) < GRAD_REL, what
+        else:
+            assert np.linalg.norm(x - ref) <= 3e-2 * np.linalg.norm(ref), what
+            assert np.median(np.abs(x - ref)) <= GRAD_REL * np.abs(ref).max(), what
+
+    for k in range(N):
+        o = mo.TrainOracle(c["ws"][k], c["bs"][k], c["tf"], True, act)
+        ref_loss = o.grads(sb[k], ab[k], s2b[k])
+        assert abs(loss[k] - ref_loss) <= 1e-3 * ref_loss
+        for l in range(5):
+            strict = act == "tanh" or l == 4
+            check(gw[k][l], o.ws[l].grad.numpy(), strict, (k, l, "weight"))
+            check(gb[k][l], o.bs[l].grad.numpy(), strict, (k, l, "bias"))
+    # a ragged last batch (B not a tile multiple) uses the same buffers
+    loss2 = eng.train_grads(sb[:, :200].contiguous(), ab[:, :200].contiguous(), s2b[:, :200].contiguous()).cpu().numpy()
+    o = mo.TrainOracle(c["ws"][0], c["bs"][0], c["tf"], True, act)
+    ref = o.grads(sb[0, :200], ab[0, :200], s2b[0, :200])
+    assert abs(loss2[0] - ref) <= 1e-3 * ref
+    gw2, _ = eng.train_export(eng.TRAIN_GRADS)
+    assert rel_to_max(gw2[0][4], o.ws[4].grad.numpy()) < GRAD_REL
+
+
+def test_training_reduces_the_loss_and_validates_arguments():
+    from amp_extensions_b200 import _lib
+    from amp_extensions_b200.engine import Engine
+    g = _train_golden()
+    c = train_case(g, "sgd_dense")
+    eng = make_train_engine(c, c["B"])
+    s, a, s2 = batch(c, 0)
+    first = eng.train_loss(s, a, s2).cpu().numpy()
+    for _ in range(40):
+        eng.train_step(s, a, s2, grad_clip=1.0)
+    last = eng.train_loss(s, a, s2).cpu().numpy()
+    assert (last < 0.7 * first).all()
+    with pytest.raises(_lib.SimstepError):      # larger than the size given to train_init
+        eng.train_step(torch.zeros(c["N"], c["B"] + 1, c["S"]), torch.zeros(c["N"], c["B"] + 1, c["A"]),
+                       torch.zeros(c["N"], c["B"] + 1, c["S"]))
+    half = Engine(c["S"], c["A"], c["N"], c["hidden"], dense_connect=True, transform=True, precision="fp16")
+    with pytest.raises(_lib.SimstepError):      # training needs the tf32 handle
+        half.train_init(64)
+    fresh = Engine(c["S"], c["A"], c["N"], c["hidden"], dense_connect=True, transform=True, precision="tf32")
+    fresh.load_ensemble(c["ws"], c["bs"], c["tf"])
+    with pytest.raises(_lib.SimstepError):      # train_init has not been called
+        fresh.train_step(s, a, s2)
