@@ -318,8 +318,9 @@ int simstep_whiten(simstep_handle* h, const float* x_dev, const uint8_t* valid_d
 
 /* All n_models members take one optimisation step per call, each on its own batch of batch_rows
  * transitions: forward on normalised inputs (unnormalize_out = False), MSE against the normalised state
- * difference, backward, optional clip_grad_norm_(grad_clip) per member, then torch.optim.SGD(nesterov=True)
- * (optimizer = 0; lr, momentum) or torch.optim.Adam (optimizer = 1; lr, momentum = beta1, beta2, eps).
+ * difference, backward, optional gradient-norm clipping at grad_clip per member, then one of the reference's
+ * optimisers (dynamics.py:198-203): SGD with Nesterov momentum (optimizer = 0; lr, momentum) or Adam
+ * (optimizer = 1; lr, momentum = beta1, beta2, eps), with the update rules of the optimiser library it uses.
  * The handle must have been created with SIMSTEP_PREC_TF32: the fp32 parameters inside the handle are
  * the master copy and the tensor-core operands at once.  Call simstep_train_init BEFORE
  * simstep_load_ensemble so that the parameters are stored with all their bits.
