@@ -7,8 +7,9 @@ other (dynamics.py:110-131), SimEnv can index `.models[i]` and call `.forward`/`
 `.threshold` (linear_cost.py:132).
 
 What is different by design: every member is evaluated in ONE grouped tensor-core launch per layer,
-so `models[i].forward` and `compute_discrepancy` share a single pass; training stays with the
-reference class (wrap a trained reference object with `DynamicsEnsemble.from_reference`).
+so `models[i].forward` and `compute_discrepancy` share a single pass.  `DynamicsEnsemble.train` trains all members
+at once on the device (each on its own shuffled batches, dynamics.py:82-108, 236-250, 264-380); a reference-trained
+object can also be wrapped with `DynamicsEnsemble.from_reference`.
 """
 import numpy as np
 import torch
@@ -85,8 +86,8 @@ class DynamicsModel:
         return {"model": self.model.state_dict(), "optim": self._optim_state if self._optim_state else {}}
 
     def train(self, *args, **kwargs):
-        raise NotImplementedError("training is done with the reference milo.dynamics classes; wrap the result "
-                                  "with DynamicsEnsemble.from_reference()")
+        raise NotImplementedError("members are trained together: call DynamicsEnsemble.train() (all members step in "
+                                  "one grouped pass on the device)")
 
 
 class DynamicsEnsemble:
@@ -110,6 +111,7 @@ class DynamicsEnsemble:
         self.base_seed = base_seed
         self.precision = precision
         self.max_chunk_envs = max_chunk_envs
+        self.optim_args = dict(optim_args) if optim_args else {"optim": "sgd", "lr": 1e-4, "momentum": 0.9}
         self.transformations = None
         if transform:
             if train_dataset is None:
@@ -147,6 +149,7 @@ class DynamicsEnsemble:
         self.base_seed = getattr(ref, "base_seed", 100)
         self.precision = precision
         self.max_chunk_envs = 0
+        self.optim_args = {"optim": "sgd", "lr": 1e-4, "momentum": 0.9}
         self.transformations = tuple(t.detach().cpu() for t in ref.transformations) if ref.transform else None
         self.models = []
         for k, rm in enumerate(ref.models):
@@ -161,6 +164,75 @@ class DynamicsEnsemble:
         self._eng = None
         self._param_stamp = None
         return self
+
+    # -- training on the device ------------------------------------------------------------
+    def train(self, epochs, validate=False, logger=None, log_epoch=False, grad_clip=0, save_path=None,
+              save_checkpoints=False, writer=None, seed=None):
+        """dynamics.py:82-108 over DynamicsModel.train (:264-380), with all members stepping together: per epoch
+        every member walks its own random permutation of the train dataset in batches of `batch_size`
+        (DataLoader(shuffle=True), dynamics.py:58); train_step = forward on normalised inputs, MSE, backward,
+        optional clip_grad_norm_, SGD-Nesterov or Adam (dynamics.py:236-250, 198-203) on a tf32 training handle.
+        After training each member holds the parameters of its best-training-loss epoch (dynamics.py:370-372).
+        Returns [(train_min_loss, first_epoch_loss)] per member like the reference."""
+        ds = self.train_dataset
+        n = len(ds)
+        B = min(int(self.batch_size), n)
+        oa = self.optim_args
+        dev = self.device if self.device.type == "cuda" else None
+        eng = _engine.Engine(self.state_dim, self.action_dim, self.num_models, self.hidden_sizes,
+                             dense_connect=self.dense_connect, activation=self.activation, transform=self.transform,
+                             precision="tf32", device=dev)
+        eng.train_init(B, optim=oa.get("optim", "sgd"), lr=oa.get("lr", 1e-4), momentum=oa.get("momentum", 0.9),
+                       eps=oa.get("eps", 1e-8))
+        ws = [[l.weight.data for l in m.model.fc_layers] for m in self.models]
+        bs = [[l.bias.data for l in m.model.fc_layers] for m in self.models]
+        eng.load_ensemble(ws, bs, self.transformations)
+        d = eng.device
+        S_all = ds.states.to(d, torch.float32)
+        A_all = ds.actions.to(d, torch.float32)
+        N_all = ds.next_states.to(d, torch.float32)
+        gen = torch.Generator(device=d)
+        gen.manual_seed(int(self.base_seed if seed is None else seed))
+        N = self.num_models
+        best = [float("inf")] * N
+        best_params = [None] * N
+        first = [None] * N
+        history = []
+        for epoch in range(int(epochs)):
+            perms = torch.stack([torch.randperm(n, device=d, generator=gen) for _ in range(N)])
+            tot = torch.zeros(N, device=d, dtype=torch.float64)
+            nb = 0
+            for i0 in range(0, n, B):
+                idx = perms[:, i0:i0 + B]                       # the last batch may be short (drop_last=False)
+                tot += eng.train_step(S_all[idx], A_all[idx], N_all[idx], grad_clip=float(grad_clip or 0.0))
+                nb += 1
+            avg = (tot / nb).cpu().tolist()                      # np.average of the batch losses, dynamics.py:283
+            history.append(avg)
+            improved = [k for k in range(N) if avg[k] < best[k]]
+            if improved:
+                pw, pb = eng.train_export(eng.TRAIN_PARAMS)
+                for k in improved:
+                    best[k] = avg[k]
+                    best_params[k] = (pw[k], pb[k])
+            for k in range(N):
+                if first[k] is None:
+                    first[k] = avg[k]
+            if logger is not None and log_epoch:
+                logger.info("Epoch: {}, Train Loss: {}".format(epoch, avg))
+            if writer is not None:
+                for k in range(N):
+                    writer.add_scalar(f"Loss/train/model{k}", avg[k], epoch)
+        for k, m in enumerate(self.models):                      # dynamics.py:370-372: keep the best-train-loss epoch
+            if best_params[k] is not None:
+                for l, layer in enumerate(m.model.fc_layers):
+                    layer.weight.data = best_params[k][0][l].clone()
+                    layer.bias.data = best_params[k][1][l].clone()
+        self.mark_dirty()
+        self.train_history = history
+        eng.close()
+        if save_path is not None:
+            self.save_ensemble(save_path if str(save_path).endswith(".pt") else str(save_path) + "/ensemble.pt")
+        return [(best[k], first[k]) for k in range(N)]
 
     def _assign_transforms(self):
         if self.transform and self.transformations is not None:
@@ -197,10 +269,6 @@ class DynamicsEnsemble:
         return self.engine().forward(state, action)
 
     # -- reference API ------------------------------------------------------------------
-    def train(self, *args, **kwargs):
-        raise NotImplementedError("train the reference milo.dynamics.DynamicsEnsemble, then wrap it with "
-                                  "amp_extensions_b200.DynamicsEnsemble.from_reference(ref)")
-
     def save_ensemble(self, save_path):
         """dynamics.py:110-116: list of {'model': state_dict, 'optim': state_dict}."""
         torch.save([m.get_state_dicts() for m in self.models], save_path)

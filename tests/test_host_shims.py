@@ -77,10 +77,16 @@ def test_ensemble_pickles_without_its_device_handle():
     assert torch.equal(clone.models[1].model.fc_layers[0].weight, ens.models[1].model.fc_layers[0].weight)
 
 
-def test_training_is_left_to_the_reference_class():
+def test_training_needs_the_device_and_members_train_together():
+    """DynamicsEnsemble.train runs on the GPU only (no CPU fallback); a single member cannot be trained alone
+    (the grouped pass steps all of them); ResidualMLP members are outside the accelerated path."""
+    from amp_extensions_b200 import _lib
     _, ens = tiny_ensemble()
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SimstepError):
+            ens.train(1)
     with pytest.raises(NotImplementedError):
-        ens.train()
+        ens.models[0].train(1, None)
     with pytest.raises(NotImplementedError):
         DynamicsEnsemble(4, 2, None, None, transform=False, use_resnet=True)
 

@@ -153,3 +153,48 @@ def test_training_reduces_the_loss_and_validates_arguments():
     fresh.load_ensemble(c["ws"], c["bs"], c["tf"])
     with pytest.raises(_lib.SimstepError):      # train_init has not been called
         fresh.train_step(s, a, s2)
+
+
+def test_ensemble_train_loop_matches_oracle_replay():
+    """DynamicsEnsemble.train on the device against the oracle replaying the same shuffled batches member by member
+    (dynamics.py:264-290): per-epoch average losses, the best-epoch bookkeeping and the parameters the members end
+    up with; afterwards the trained ensemble steps envs like any other."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble
+    S, A, N, B, n, epochs = 20, 6, 3, 64, 200, 3          # 200 rows / 64: three full batches and one of 8 rows
+    s, a, s2 = H.synth_dataset(n, S, A, 0)
+    ds = AmpDataset(s, a, s2)
+    optim = {"optim": "sgd", "lr": 0.05, "momentum": 0.9}
+    ens = DynamicsEnsemble(S, A, ds, None, num_models=N, batch_size=B, hidden_sizes=[32, 24], dense_connect=True,
+                           activation="tanh", transform=True, optim_args=optim, base_seed=100)
+    init = [([l.weight.data.clone() for l in m.model.fc_layers], [l.bias.data.clone() for l in m.model.fc_layers])
+            for m in ens.models]
+    out = ens.train(epochs, grad_clip=1.0, seed=7)
+    # replay: the same generator stream gives the same permutations
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    oracles = [mo.TrainOracle(init[k][0], init[k][1], ens.transformations, True, "tanh", optim) for k in range(N)]
+    best = [float("inf")] * N
+    best_w = [None] * N
+    for epoch in range(epochs):
+        perms = torch.stack([torch.randperm(n, device="cuda", generator=gen) for _ in range(N)]).cpu()
+        for k in range(N):
+            losses = []
+            for i0 in range(0, n, B):
+                bi = perms[k, i0:i0 + B]
+                losses.append(oracles[k].train_step(1.0, s[bi], a[bi], s2[bi]))
+            avg = float(np.average(losses))
+            assert abs(ens.train_history[epoch][k] - avg) <= 3e-3 * avg, (epoch, k)
+            if avg < best[k]:
+                best[k] = avg
+                best_w[k] = [w.detach().clone() for w in oracles[k].ws]
+    for k in range(N):
+        assert abs(out[k][0] - best[k]) <= 3e-3 * best[k]
+        for l, layer in enumerate(ens.models[k].model.fc_layers):
+            step = (best_w[k][l] - init[k][0][l]).abs().max().item()
+            assert (layer.weight.data - best_w[k][l]).abs().max().item() <= 0.05 * step, (k, l)
+    # the trained members are what the env step now evaluates
+    preds = ens.forward_all(s[:16], a[:16]).cpu()
+    wsT = [[l.weight.data for l in m.model.fc_layers] for m in ens.models]
+    bsT = [[l.bias.data for l in m.model.fc_layers] for m in ens.models]
+    ref = mo.ensemble_forward(wsT, bsT, ens.transformations, s[:16], a[:16], dense_connect=True, activation="tanh")
+    assert (preds - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
