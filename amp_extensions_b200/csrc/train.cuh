@@ -45,23 +45,25 @@ __global__ void train_prep_kernel(const float* __restrict__ state, const float* 
   }
 }
 
+constexpr int kTrainPartials = 256;  // partial sums per member and region (deterministic two-pass reductions)
+
 // MSE loss and its gradient with respect to the final layer's output (dynamics.py:241-246):
 //   target = ((s' - s) - mean_d) / scale_d,  e = pred - target,  loss_g = mean_{r<B, c<S} e^2,
 //   dY[g][r][col0 + c] = 2 e / (B S)   (0 on padding rows / columns).
-// One warp per (member, row).  loss[g] accumulates in fp64 (atomics: the order only touches the last bits).
-__global__ void train_loss_kernel(const float* __restrict__ pred, int DP, const float* __restrict__ state,
-                                  const float* __restrict__ next_state, int S, int B, int Bp, int n_members,
-                                  const float* __restrict__ d_mean, const float* __restrict__ d_scale,
-                                  float* __restrict__ dy, int OT, int col0, int width, double* __restrict__ loss) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+// grid = (blocks, members), one warp per row; partial[g][blockIdx.x] = the block's share of sum e^2 (fp64, fixed
+// order), summed by train_sum_partials_kernel: the same inputs always give the same bits.
+__global__ void __launch_bounds__(256)
+train_loss_kernel(const float* __restrict__ pred, int DP, const float* __restrict__ state,
+                  const float* __restrict__ next_state, int S, int B, int Bp, const float* __restrict__ d_mean,
+                  const float* __restrict__ d_scale, float* __restrict__ dy, int OT, int col0, int width,
+                  double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = blockIdx.y;
   const float gscale = 2.f / (static_cast<float>(B) * static_cast<float>(S));
-  for (long long row = warp; row < static_cast<long long>(n_members) * Bp; row += n_warps) {
-    const int r = static_cast<int>(row % Bp);
-    const int g = static_cast<int>(row / Bp);
+  double acc = 0.0;
+  for (int r = blockIdx.x * 8 + wib; r < Bp; r += gridDim.x * 8) {
+    const long long row = static_cast<long long>(g) * Bp + r;
     float* drow = dy ? dy + row * OT + col0 : nullptr;
-    double acc = 0.0;
     for (int c = lane; c < width; c += 32) {
       float grad = 0.f;
       if (r < B && c < S) {
@@ -74,9 +76,29 @@ __global__ void train_loss_kernel(const float* __restrict__ pred, int DP, const 
       }
       if (drow) drow[c] = ptx::round_tf32(grad);
     }
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0 && r < B) atomicAdd(&loss[g], acc / (static_cast<double>(B) * S));
   }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  __shared__ double sh[8];
+  if (lane == 0) sh[wib] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partial[g * kTrainPartials + blockIdx.x] = t;
+  }
+}
+
+// out[g] = scale * sum over regions r and slots b of partial[(r * n_members + g) * kTrainPartials + b]; one warp per
+// member, fixed order.
+__global__ void train_sum_partials_kernel(const double* __restrict__ partial, int regions, int n_members, double scale,
+                                          double* __restrict__ out) {
+  const int g = blockIdx.x, lane = threadIdx.x;
+  if (g >= n_members || lane >= 32) return;
+  double acc = 0.0;
+  for (int r = 0; r < regions; ++r)
+    for (int b = lane; b < kTrainPartials; b += 32) acc += partial[(static_cast<long long>(r) * n_members + g) * kTrainPartials + b];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[g] = scale * acc;
 }
 
 // dst[z][c][r] = src[z][r][c] for r < rows, c < cols (32 x 32 tiles through shared memory); blockIdx.z = batch.
@@ -127,12 +149,12 @@ __global__ void train_rowsum_kernel(const float* __restrict__ x, int pitch, int 
   }
 }
 
-// sumsq[g] += sum of squares of member g's slice x[g][0 .. per_member) (gradient norm, dynamics.py:247-248).
-__global__ void train_sumsq_kernel(const float* __restrict__ x, long long per_member, int n_members,
-                                   double* __restrict__ sumsq) {
+// partial[g][blockIdx.x] = this block's share of the sum of squares of member g's slice x[g * stride .. + per_member)
+// (gradient norm, dynamics.py:247-248); grid = (blocks <= kTrainPartials, members).
+__global__ void __launch_bounds__(256)
+train_sumsq_kernel(const float* __restrict__ x, long long per_member, long long stride, double* __restrict__ partial) {
   const int g = blockIdx.y;
-  if (g >= n_members) return;
-  const float* p = x + static_cast<long long>(g) * per_member;
+  const float* p = x + static_cast<long long>(g) * stride;
   double acc = 0.0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_member;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -140,13 +162,13 @@ __global__ void train_sumsq_kernel(const float* __restrict__ x, long long per_me
     acc += v * v;
   }
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  __shared__ double sh[32];
+  __shared__ double sh[8];
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += sh[w];
-    atomicAdd(&sumsq[g], t);
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partial[g * kTrainPartials + blockIdx.x] = t;
   }
 }
 
@@ -157,18 +179,36 @@ struct OptimArgs {
   float beta2;
   float eps;
   float grad_clip;   // 0: off; else clip_grad_norm_(max_norm) over one member's parameters
-  float bc1, bc2;    // Adam bias corrections 1 - beta^t
+};
+
+// Step-dependent optimiser quantities live on the device so that a captured CUDA graph of the training step can
+// be replayed: every step starts with train_tick_kernel.
+struct OptimState {
+  long long step;    // optimiser steps taken, including the current one
+  float bc1, bc2;    // Adam bias corrections 1 - beta^step
   int first_step;    // SGD: the momentum buffer starts as the gradient itself
 };
+
+__global__ void train_tick_kernel(OptimState* st, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = st->step + 1;
+    st->step = t;
+    st->first_step = t == 1;
+    st->bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(t)));
+    st->bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(t)));
+  }
+}
 
 // Parameter update of one tensor: member g's parameters at p[g * p_stride + i], its gradient and optimiser moments
 // at {g, m, v}[g * g_stride + g_off + i], i < count; the clip coefficient comes from the member's gradient norm:
 //   coef = min(1, clip / (sqrt(sumsq) + 1e-6))    (torch.nn.utils.clip_grad_norm_)
 __global__ void train_optim_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                    float* __restrict__ v, long long count, long long p_stride, long long g_stride,
-                                   long long g_off, int n_members, const double* __restrict__ sumsq, const OptimArgs a) {
+                                   long long g_off, int n_members, const double* __restrict__ sumsq, const OptimArgs a,
+                                   const OptimState* __restrict__ state) {
   const int gi = blockIdx.y;
   if (gi >= n_members) return;
+  const OptimState os = *state;
   float coef = 1.f;
   if (a.grad_clip > 0.f) {
     const float c = a.grad_clip / (static_cast<float>(sqrt(sumsq[gi])) + 1e-6f);
@@ -181,7 +221,7 @@ __global__ void train_optim_kernel(float* __restrict__ p, const float* __restric
     const float grad = g[gbase + i] * coef;
     float w = pp[i];
     if (a.kind == 0) {
-      const float buf = a.first_step ? grad : fmaf(a.momentum, m[gbase + i], grad);
+      const float buf = os.first_step ? grad : fmaf(a.momentum, m[gbase + i], grad);
       m[gbase + i] = buf;
       w -= a.lr * fmaf(a.momentum, buf, grad);
     } else {
@@ -189,8 +229,8 @@ __global__ void train_optim_kernel(float* __restrict__ p, const float* __restric
       const float v1 = fmaf(a.beta2, v[gbase + i], (1.f - a.beta2) * grad * grad);
       m[gbase + i] = m1;
       v[gbase + i] = v1;
-      const float denom = sqrtf(v1) / sqrtf(a.bc2) + a.eps;
-      w -= (a.lr / a.bc1) * (m1 / denom);
+      const float denom = sqrtf(v1) / sqrtf(os.bc2) + a.eps;
+      w -= (a.lr / os.bc1) * (m1 / denom);
     }
     pp[i] = w;
   }

@@ -167,7 +167,7 @@ class DynamicsEnsemble:
 
     # -- training on the device ------------------------------------------------------------
     def train(self, epochs, validate=False, logger=None, log_epoch=False, grad_clip=0, save_path=None,
-              save_checkpoints=False, writer=None, seed=None):
+              save_checkpoints=False, writer=None, seed=None, graph=True):
         """dynamics.py:82-108 over DynamicsModel.train (:264-380), with all members stepping together: per epoch
         every member walks its own random permutation of the train dataset in batches of `batch_size`
         (DataLoader(shuffle=True), dynamics.py:58); train_step = forward on normalised inputs, MSE, backward,
@@ -204,7 +204,8 @@ class DynamicsEnsemble:
             nb = 0
             for i0 in range(0, n, B):
                 idx = perms[:, i0:i0 + B]                       # the last batch may be short (drop_last=False)
-                tot += eng.train_step(S_all[idx], A_all[idx], N_all[idx], grad_clip=float(grad_clip or 0.0))
+                step = eng.train_step_graph if graph else eng.train_step   # full batches replay one CUDA graph
+                tot += step(S_all[idx], A_all[idx], N_all[idx], grad_clip=float(grad_clip or 0.0))
                 nb += 1
             avg = (tot / nb).cpu().tolist()                      # np.average of the batch losses, dynamics.py:283
             history.append(avg)

@@ -417,6 +417,36 @@ class Engine:
         """One optimisation step of every member on its own batch; returns the members' losses (CUDA fp64 [N])."""
         return self._train_call(self.lib.simstep_train_step, state, action, next_state, C.c_float(float(grad_clip)))
 
+    def train_step_graph(self, state, action, next_state, grad_clip=0.0):
+        """train_step replayed from a CUDA graph (the step is ~45 small launches at the reference's 256-row batches,
+        launch-latency bound when issued one by one).  The first call for a batch size runs eagerly (it also warms
+        the kernels up), the second captures, later ones replay; inputs are copied into the graph's static
+        buffers.  The returned loss tensor is overwritten by the next replay."""
+        cache = self.__dict__.setdefault("_train_graphs", {})
+        key = (int(state.shape[1]), float(grad_clip))
+        ent = cache.get(key)
+        if ent is None:
+            cache[key] = "warm"
+            return self.train_step(state, action, next_state, grad_clip)
+        if ent == "warm":
+            f32 = dict(device=self.device, dtype=torch.float32)
+            sb = torch.empty(tuple(state.shape), **f32)
+            ab = torch.empty(tuple(action.shape), **f32)
+            nb = torch.empty(tuple(next_state.shape), **f32)
+            loss = torch.zeros((self.N,), device=self.device, dtype=torch.float64)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._check(self.lib.simstep_train_step(self._h, _ptr(sb), _ptr(ab), _ptr(nb), int(sb.shape[1]),
+                                                        C.c_float(float(grad_clip)), _ptr(loss), _stream(self.device)))
+            ent = cache[key] = (g, sb, ab, nb, loss)
+        g, sb, ab, nb, loss = ent
+        sb.copy_(state, non_blocking=True)
+        ab.copy_(action, non_blocking=True)
+        nb.copy_(next_state, non_blocking=True)
+        g.replay()
+        return loss
+
     def train_loss(self, state, action, next_state):
         """DynamicsModel.validate_step (dynamics.py:252-262) for every member."""
         return self._train_call(self.lib.simstep_train_loss, state, action, next_state)

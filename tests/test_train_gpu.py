@@ -198,3 +198,23 @@ def test_ensemble_train_loop_matches_oracle_replay():
     bsT = [[l.bias.data for l in m.model.fc_layers] for m in ens.models]
     ref = mo.ensemble_forward(wsT, bsT, ens.transformations, s[:16], a[:16], dense_connect=True, activation="tanh")
     assert (preds - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_graph_replayed_steps_equal_eager_steps():
+    """train_step_graph (CUDA-graph replay, step-dependent optimiser state kept on the device) takes exactly the
+    steps train_step takes: identical parameters after six Adam steps with clipping."""
+    g = _train_golden()
+    c = train_case(g, "adam_plain_tanh")
+    outs = []
+    for use_graph in (False, True):
+        eng = make_train_engine(c, c["B"])
+        for step in range(6):
+            s, a, s2 = batch(c, step % 3)
+            fn = eng.train_step_graph if use_graph else eng.train_step
+            loss = fn(s.cuda(), a.cuda(), s2.cuda(), grad_clip=0.3).clone()
+        ws, bs = eng.train_export(eng.TRAIN_PARAMS)
+        outs.append((loss.cpu(), ws, bs))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in range(c["N"]):
+        for l in range(c["nl"]):
+            assert torch.equal(outs[0][1][k][l], outs[1][1][k][l]) and torch.equal(outs[0][2][k][l], outs[1][2][k][l])

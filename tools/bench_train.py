@@ -58,6 +58,17 @@ def main():
         tflops = 3 * flop_fwd * rows * N / (ms * 1e-3) / 1e12
         res[f"rows{rows}"] = {"rows_per_member": rows, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
                               "transitions_per_s": rows * N / (ms * 1e-3), "algorithmic_tflops": tflops}
+        for _ in range(3):
+            eng.train_step_graph(sd, ad, nd, grad_clip=1.0)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(iters):
+            eng.train_step_graph(sd, ad, nd, grad_clip=1.0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        msg = e0.elapsed_time(e1) / iters
+        res[f"rows{rows}"]["graph"] = {"ms_per_step": msg, "transitions_per_s": rows * N / (msg * 1e-3),
+                                      "algorithmic_tflops": 3 * flop_fwd * rows * N / (msg * 1e-3) / 1e12}
         eng.close()
     cpu = None
     if not args.skip_cpu:
