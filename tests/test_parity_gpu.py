@@ -534,3 +534,32 @@ def test_gail_cost_matches_reference(tag, prec):
     ws2 = [w * 0.5 for w in ws]
     d2 = mo.gail_disc_forward(ws2, bs, ss)
     assert_close(cost.disc_outputs(ss), d2, max(d2.abs().max().item(), 1.0), what="disc outputs after update")
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_unaligned_state_rows_take_the_fallback_kernel_with_the_same_results(prec):
+    """A state slice that starts on an odd row is only 8-byte aligned: the TMA-staged post kernel needs 16 bytes, so
+    the library falls back to the one-warp-per-row kernel.  Same numbers either way (next state and flags bit for
+    bit; the discrepancy up to its summation order)."""
+    from amp_extensions_b200 import RBFLinearCost
+    from amp_extensions_b200.engine import HumanoidTermination
+    c = H.ns_case()
+    eng = make_engine(c, prec)
+    eng.set_termination(HumanoidTermination(horizon=300))
+    cost = RBFLinearCost(H.ns_expert(), feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100,
+                         precision=prec)
+    eng.load_rff(cost.rff.weight.data, cost.rff.bias.data, split=True)
+    E = 777
+    g = torch.Generator().manual_seed(41)
+    big = H.humanoid_like_states(E + 1, seed=43).cuda()
+    a = torch.randn(E, 28, generator=g).cuda()
+    member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32).cuda()
+    w = (torch.randn(512, generator=g) * 0.02).cuda()
+    odd = big[1:]                        # data_ptr is 904 bytes past a 256-byte boundary
+    assert odd.data_ptr() % 16 == 8 and odd.is_contiguous()
+    aligned = odd.clone()
+    out_odd = eng.step_cost(odd, a, member, torch.zeros(E, dtype=torch.int32).cuda(), w, 0.0025, 0.35)
+    out_al = eng.step_cost(aligned, a, member, torch.zeros(E, dtype=torch.int32).cuda(), w, 0.0025, 0.35)
+    assert torch.equal(out_odd[0], out_al[0]) and torch.equal(out_odd[2], out_al[2])
+    assert_close(out_odd[1], out_al[1], out_al[1].mean().item(), rel=2e-6, what="disc")
+    assert_close(out_odd[3], out_al[3], out_al[3].abs().max().item(), rel=1e-5, what="cost")
