@@ -265,4 +265,30 @@ __global__ void whiten_kernel(const float* __restrict__ x, const uint8_t* __rest
     out[i] = (valid == nullptr || valid[i]) ? (x[i] - m) * inv : 0.f;
 }
 
+// Fixed-range histogram for the multi-GPU quantile (parallel.global_quantile): counts[b] += #{i : x[i] in [lo, hi],
+// bin(x[i]) == b}, bin = clamp(floor((x - lo) / width), 0, bins - 1) evaluated in fp64 like the host code.  Integer
+// counts: the result does not depend on scheduling.  Shared-memory bins per block, then one atomic per non-empty bin.
+constexpr int kHistMaxBins = 8192;
+
+__global__ void __launch_bounds__(256)
+histogram_kernel(const float* __restrict__ x, long long n, double lo, double hi, int bins,
+                 unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int sh_bins[];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) sh_bins[b] = 0u;
+  __syncthreads();
+  const double width = (hi - lo) / bins;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double v = x[i];
+    if (v >= lo && v <= hi) {
+      int b = static_cast<int>(floor((v - lo) / width));
+      b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+      atomicAdd(&sh_bins[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x)
+    if (sh_bins[b]) atomicAdd(&counts[b], static_cast<unsigned long long>(sh_bins[b]));
+}
+
 }  // namespace simstep

@@ -261,6 +261,14 @@ class Engine:
                                                 _ptr(cost), _ptr(ipm), _ptr(bonus), _stream(self.device)))
         return cost, ipm, bonus
 
+    def histogram(self, x, lo, hi, bins):
+        """int64 [bins] counts of a device fp32 vector over [lo, hi] (see simstep_histogram)."""
+        x = _dev_f32(x, self.device).reshape(-1)
+        out = torch.empty((int(bins),), device=self.device, dtype=torch.int64)
+        self._check(self.lib.simstep_histogram(self._h, _ptr(x), x.numel(), float(lo), float(hi), int(bins), _ptr(out),
+                                               _stream(self.device)))
+        return out
+
     def reduce_max_sum(self, x, out=None):
         """[max, sum] of a device vector as fp64 (written into `out` when given)."""
         x = _dev_f32(x, self.device)

@@ -135,12 +135,14 @@ def rollout_stats(cost, ipm, bonus, done, num_steps):
     }
 
 
-def global_quantile(x_local, q, bins=4096, refine=2):
+def global_quantile(x_local, q, bins=4096, refine=2, engine=None):
     """q-quantile (linear interpolation between order statistics, as torch.quantile) of the union of every
     rank's x_local, without gathering the samples: all-reduce of min/max and of fixed-range histograms, refined
     `refine` times around the two order statistics that bracket the quantile.  Exact up to the final bin width
     (range / bins**(refine+1)); used for threshold_mode='quantile', an extension over the reference's dataset
-    maximum."""
+    maximum.  With `engine` (and a CUDA fp32 vector) the histograms are taken by libsimstep's histogram kernel;
+    without it (CPU tensors in the gloo tests) by torch."""
+    x32 = torch.as_tensor(x_local).reshape(-1) if engine is not None else None
     x = torch.as_tensor(x_local).to(torch.float64).reshape(-1)
     dev = x.device
     n = all_reduce_sum(torch.tensor([float(x.numel())], device=dev, dtype=torch.float64))[0]
@@ -160,9 +162,12 @@ def global_quantile(x_local, q, bins=4096, refine=2):
             if b <= a:
                 return a
             width = (b - a) / bins
-            idx = torch.clamp(((x - a) / width).floor(), 0, bins - 1).long()
-            sel = (x >= a) & (x <= b)
-            hist = torch.bincount(idx[sel], minlength=bins).to(torch.float64)
+            if engine is not None and x32.is_cuda and x32.dtype == torch.float32:
+                hist = engine.histogram(x32, a, b, bins).to(torch.float64)
+            else:
+                idx = torch.clamp(((x - a) / width).floor(), 0, bins - 1).long()
+                sel = (x >= a) & (x <= b)
+                hist = torch.bincount(idx[sel], minlength=bins).to(torch.float64)
             hist = all_reduce_sum(hist)
             cum = torch.cumsum(hist, 0) + below
             bin_i = int(torch.searchsorted(cum, torch.tensor([float(k) + 0.5], device=dev, dtype=torch.float64)).item())

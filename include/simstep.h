@@ -346,6 +346,12 @@ int simstep_train_export(simstep_handle* h, int32_t what, float* const* weights_
 
 /* ---- reductions used by the multi-GPU host code ------------------------- */
 
+/* counts_dev[b] (int64, bins entries, overwritten) = number of x_dev[i] in [lo, hi] whose bin
+ * clamp(floor((x - lo) / ((hi - lo) / bins)), 0, bins - 1) is b; 1 <= bins <= 8192.  The all-reduced
+ * histograms of the ranks give the global discrepancy quantile without gathering samples. */
+int simstep_histogram(simstep_handle* h, const float* x_dev, int64_t n, double lo, double hi, int32_t bins,
+                      int64_t* counts_dev, void* stream);
+
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */
 int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, double* out_dev, void* stream);
 

@@ -50,7 +50,7 @@ def _run(ens, cost, xs, xa, member, device, parallel):
     w = parallel.global_fit_cost(cost, torch.cat([xs, nxt], dim=1)).to(device)
     nxt, disc, done, cst, ipm, bonus = eng.step_cost(xs, xa, member, steps, w, cost.lambda_b, thr)
     stats = parallel.rollout_stats(cst, ipm, bonus, done, steps)
-    q = parallel.global_quantile(disc, 0.9)
+    q = parallel.global_quantile(disc, 0.9, engine=eng)
     return dict(thr=thr, w=w.cpu(), nxt=nxt.cpu(), disc=disc.cpu(), cost=cst.cpu(), done=done.cpu(), stats=stats, q=q)
 
 

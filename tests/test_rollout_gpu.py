@@ -315,3 +315,23 @@ def test_moments_and_whitening_match_numpy():
     # empty input: count 0, nothing written
     st = eng.moments(torch.empty(0, device="cuda")).cpu().numpy()
     assert st.tolist() == [0.0, 0.0, 0.0]
+
+
+def test_histogram_kernel_and_device_quantile_match_torch():
+    """simstep_histogram against torch.histc-style counting in fp64, and parallel.global_quantile through it against
+    torch.quantile (single process: the all-reduces are identities)."""
+    from amp_extensions_b200 import parallel
+    _, eng = _tiny_engine()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand(200_003, device="cuda", generator=g) ** 3 * 0.7
+    lo, hi, bins = 0.05, 0.6, 4096
+    counts = eng.histogram(x, lo, hi, bins).cpu()
+    xd = x.double().cpu()
+    sel = (xd >= lo) & (xd <= hi)
+    idx = torch.clamp(((xd[sel] - lo) / ((hi - lo) / bins)).floor(), 0, bins - 1).long()
+    assert torch.equal(counts, torch.bincount(idx, minlength=bins))
+    assert int(eng.histogram(torch.empty(0, device="cuda"), 0.0, 1.0, 16).sum()) == 0
+    for q in (0.1, 0.5, 0.9, 0.999):
+        got = parallel.global_quantile(x, q, engine=eng)
+        ref = float(torch.quantile(xd, q))
+        assert abs(got - ref) <= 1e-6 * float(xd.max() - xd.min()), (q, got, ref)

@@ -110,7 +110,7 @@ def main():
 
     for i in range(args.warmup):
         one_step(i)
-    q = parallel.global_quantile(disc, 0.9)
+    q = parallel.global_quantile(disc, 0.9, engine=eng)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_q, n_q = 0.0, 0
@@ -120,7 +120,7 @@ def main():
         one_step(args.warmup + i)
         if (i + 1) % args.quantile_every == 0:
             tq0 = time.perf_counter()
-            q = parallel.global_quantile(disc, 0.9)   # host-synchronous: inside the timed region on purpose
+            q = parallel.global_quantile(disc, 0.9, engine=eng)   # host-synchronous: inside the timed region on purpose
             t_q += time.perf_counter() - tq0
             n_q += 1
     e1.record()
