@@ -16,6 +16,7 @@
 #include "../../include/simstep.h"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_fused.cuh"
 #include "imitation.cuh"
 #include "imitation_h3d.cuh"
 #include "policy.cuh"
@@ -69,6 +70,7 @@ struct simstep_handle {
   void* xbuf = nullptr;
   void* hbuf = nullptr;
   float* dws = nullptr;
+  unsigned int* ready = nullptr;  // fused forward: [L + 1][N][m_tiles] completed-tile counters
   CUtensorMap tmap_x, tmap_h, tmap_dws;
 
   // RFF cost
@@ -284,6 +286,7 @@ void free_workspace(simstep_handle* h) {
   cudaFree(h->xbuf); h->xbuf = nullptr;
   cudaFree(h->hbuf); h->hbuf = nullptr;
   cudaFree(h->dws); h->dws = nullptr;
+  cudaFree(h->ready); h->ready = nullptr;
   cudaFree(h->rffin); h->rffin = nullptr;
   cudaFree(h->rff_part); h->rff_part = nullptr;
   h->cap_rows = 0;
@@ -307,6 +310,7 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     CU_TRY(h, cudaMalloc(&h->xbuf, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMalloc(&h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
     CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->ready, size_t(h->L + 1) * h->N * (rows / h->row_align + 1) * sizeof(unsigned int)));
     CU_TRY(h, cudaMemset(h->xbuf, 0, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMemset(h->hbuf, 0, size_t(h->N) * rows * h->HT * h->esize));
     int rc = encode_operand(h, &h->tmap_x, prec, h->xbuf, h->XP, rows, h->XP, kBlockM);
@@ -347,6 +351,82 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
   g_launches++;
 }
 
+// SIMSTEP_FUSED_LAYERS=1: all layers of the forward pass in one persistent launch (gemm_fused.cuh)
+bool fused_layers_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_FUSED_LAYERS"); return e && e[0] == '1'; }();
+  return on;
+}
+
+template <typename E>
+int launch_fused_t(simstep_handle* h, const FusedMaps& maps, const FusedArgs& fa, cudaStream_t st) {
+  static bool attr_set[kMaxDevices] = {};
+  auto kern = ensemble_fused_kernel<E>;
+  constexpr size_t smem = GemmShape<2>::smem_bytes();
+  bool& done = attr_set[h->device % kMaxDevices];
+  if (!done) {
+    CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    done = true;
+  }
+  const int slots = std::min(fa.total_tiles, h->sm_count / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(slots * 2));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, maps, fa));
+  g_launches++;
+  return SIMSTEP_OK;
+}
+
+int launch_fused_forward(simstep_handle* h, long long rows_pad, cudaStream_t st) {
+  FusedMaps maps;
+  FusedArgs fa{};
+  maps.x = h->tmap_x;
+  maps.h = h->tmap_h;
+  maps.out_final = h->tmap_dws;
+  fa.n_layers = h->L + 1;
+  fa.m_tiles = int(rows_pad / (kBlockM * 2));
+  fa.groups = h->N;
+  fa.a_rows_per_group = int(h->cap_rows);
+  fa.ax_rows_per_group = 0;
+  fa.out_rows_per_group = int(h->cap_rows);
+  fa.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
+  fa.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
+  fa.ready = h->ready;
+  int tile = 0;
+  for (int l = 0; l <= h->L; ++l) {
+    const Layer& ly = h->layers[l];
+    maps.w[l] = ly.tmap_w;
+    FusedLayer& fl = fa.layer[l];
+    fl.tile0 = tile;
+    fl.n_tiles = ly.o_pad / kBlockN;
+    fl.kb_x = ly.kb_x;
+    fl.kb_h0 = ly.kb_h0;
+    fl.kb_h = ly.kb_h;
+    fl.b_rows_per_group = ly.o_pad;
+    fl.out_col0 = l < h->L ? ly.out_col0 : 0;
+    fl.mode = l < h->L ? (h->cfg.activation == SIMSTEP_ACT_RELU ? int(kEpiHidden) : int(kEpiHiddenTanh)) : int(kEpiFinal);
+    fl.bias = ly.bias;
+    tile += fa.m_tiles * fl.n_tiles * fa.groups;
+  }
+  for (int l = h->L + 1; l < kFusedMaxLayers; ++l) maps.w[l] = h->layers[h->L].tmap_w;
+  fa.total_tiles = tile;
+  switch (h->cfg.precision) {
+    case SIMSTEP_PREC_TF32: return launch_fused_t<ElemTF32>(h, maps, fa, st);
+    case SIMSTEP_PREC_FP16: return launch_fused_t<ElemF16>(h, maps, fa, st);
+    default: return launch_fused_t<ElemBF16>(h, maps, fa, st);
+  }
+}
+
 // prep + all layer GEMMs for rows [0, n) of a chunk; leaves un-normalised member
 // deltas in h->dws[N][cap_rows][SP].
 // w_stage != nullptr: the prep kernel also copies the cost weights into h->rff_wpad (no separate memcpy node
@@ -355,6 +435,9 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
                        const float* w_stage = nullptr, int last_layer = -2) {
   if (last_layer == -2) last_layer = h->L;  // -1: input preparation only
   const long long rows_pad = round_up(n, h->row_align);
+  const bool fused = fused_layers_enabled() && h->cg == 2 && last_layer == h->L;
+  if (fused)  // tile-completion counters of the fused forward; ordered before the prep kernel, hence before the GEMM
+    CU_TRY(h, cudaMemsetAsync(h->ready, 0, size_t(h->L + 1) * h->N * (rows_pad / h->row_align) * sizeof(unsigned int), st));
   {
   ProfScope ps(h, SIMSTEP_PROF_PREP, st);
   switch (h->cfg.precision) {
@@ -365,6 +448,7 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
+  if (fused) return launch_fused_forward(h, rows_pad, st);
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
     GemmArgs ga{};
