@@ -12,8 +12,9 @@
 // What it is meant to buy: no drain / launch / pipeline-fill between layers, and at small batches layers that
 // overlap instead of five latency-bound launches.  STATUS (round 1): opt-in (SIMSTEP_FUSED_LAYERS=1), results
 // bit-identical to the per-layer path, but at the 40 000-env bench batch it needs 0.75 ms where the five per-layer
-// launches need 0.68 ms (tensor pipe 62 % vs 75 % active under ncu); it is the faster path only for small eager
-// batches.  The per-layer path stays the default until the gap is understood.
+// launches need 0.68 ms (tensor pipe 62 % vs 75 % active under ncu): with the dependency tracking switched off the
+// tile loop alone takes 0.70 ms (programmatic dependent launch already hides most of what a kernel boundary
+// costs), the counters add 0.06 ms.  It is the faster path only for small eager batches.  The per-layer path stays the default until the gap is understood.
 // Pipeline, barriers, TMEM double-buffering and the TMA-store epilogue are those of gemm_tcgen05.cuh (CG = 2 only).
 #pragma once
 #include "gemm_tcgen05.cuh"
