@@ -38,8 +38,7 @@ class RBFLinearCost:
         self.rff.bias.data = (torch.rand_like(self.rff.bias.data) - 0.5) * 2.0 * np.pi
         self.rff.weight.data = torch.rand_like(self.rff.weight.data) / (self.bw + 1e-8)
         self.w = None
-        self.expert_rep = self.get_rep(expert_data)  # linear_cost.py:61-62
-        self.phi_e = self.expert_rep.mean(dim=0)
+        self.expert_rep, self.phi_e = self._expert_features(expert_data)  # linear_cost.py:61-62
 
     # -- host-side fitting (same arithmetic and RNG stream as the reference) --------------------
     def fit_bandwidth(self, data):
@@ -63,6 +62,11 @@ class RBFLinearCost:
             self._rff_stamp = stamp
         return self._eng
 
+    def _expert_features(self, expert_data):
+        """(phi(expert) as a CPU tensor, its mean): the mean comes from the device's fp64 column sums."""
+        phi, psum = self.engine().rff_features(expert_data, want_sum=True)
+        return phi.cpu(), (psum / max(int(expert_data.shape[0]), 1)).float().cpu()
+
     def get_rep(self, x):
         """linear_cost.py:64-71: cos(rff(x)) * sqrt(2/D), returned on the CPU like the reference."""
         with torch.no_grad():
@@ -84,9 +88,16 @@ class RBFLinearCost:
         return dot
 
     def get_expert_cost(self):
-        """linear_cost.py:105-109."""
-        return (1 - self.lambda_b) * torch.clamp(torch.mm(self.expert_rep, self.w.unsqueeze(1)), self.c_min,
-                                                 self.c_max).mean()
+        """linear_cost.py:105-109: (1 - lambda_b) * mean(clamp(phi(expert) . w)), evaluated on the device: the combine
+        kernel's `ipm` output is (1 - lambda_b) * clamp(.), its mean comes from the fp64 moments kernel."""
+        eng = self.engine()
+        x = self.expert_data.float()
+        zeros = torch.zeros(x.shape[0], device=eng.device, dtype=torch.float32)
+        clamp = self.cost_range is not None
+        c_min, c_max = (self.c_min, self.c_max) if clamp else (0.0, 0.0)
+        _, ipm, _ = eng.bonus_cost(x, zeros, self.w, self.lambda_b, 1.0, c_min, c_max, clamp)
+        stats = eng.moments(ipm)
+        return (stats[1] / stats[0]).float().cpu()
 
     def rff_input(self, states, actions, next_states=None):
         """linear_cost.py:115-126."""
@@ -164,8 +175,7 @@ class MLPCost(RBFLinearCost):
         self.bw_samples = bw_samples
         self.bw = self.fit_bandwidth(expert_data)  # linear_cost.py:219-221
         self.w = None
-        self.expert_rep = self.get_rep(expert_data)
-        self.phi_e = self.expert_rep.mean(0)
+        self.expert_rep, self.phi_e = self._expert_features(expert_data)
 
     def _linears(self):
         return [m for m in self.net if isinstance(m, nn.Linear)]

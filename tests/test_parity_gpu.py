@@ -271,6 +271,8 @@ def test_rbf_linear_cost_matches_reference(tag, D, prec):
     costs_ref = H.t(g[f"{tag}/costs"])
     cscale = max(costs_ref.abs().max().item(), 1e-6)
     assert_close(cost.get_costs(pi), costs_ref, cscale, what="costs")
+    ec = cost.get_expert_cost()                               # linear_cost.py:105-109, evaluated on the device
+    assert ec.dim() == 0 and abs(float(ec) - float(g[f"{tag}/expert_cost"])) <= REL * max(cscale, abs(float(g[f"{tag}/expert_cost"])))
 
     class Ens:  # the reference passes the ensemble object (linear_cost.py:132)
         threshold = c["threshold"]
