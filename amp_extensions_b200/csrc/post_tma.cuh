@@ -126,6 +126,23 @@ __device__ __forceinline__ float post_max_of_lane_sums(float (&acc)[NP > 0 ? NP 
   }
 }
 
+// the member pairs (a, b), a < b, in the order (0,1), (0,2), ..., (1,2), ... as compile-time tables
+template <int N>
+struct PostPairs {
+  static constexpr int kCount = N * (N - 1) / 2;
+  int a[kCount > 0 ? kCount : 1];
+  int b[kCount > 0 ? kCount : 1];
+  constexpr PostPairs() : a{}, b{} {
+    int p = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        a[p] = i;
+        b[p] = j;
+        ++p;
+      }
+  }
+};
+
 // One env row out of a staged pair.  srow: the row's state in shared memory (overwritten with s'), drow0: member
 // 0's delta row, member m's row sits m * dstride floats further.  SC: compile-time state width (0: use S).
 template <int NM, typename E, int SC>
@@ -158,19 +175,19 @@ __device__ __forceinline__ void post_tma_row(float* srow, const float* drow0, in
   if (disc != nullptr) {
     float acc[NP > 0 ? NP : 1];
     const float2 neg1 = make_float2(-1.f, -1.f);
-    int p = 0;
+    // one flat loop over the member pairs (indices are compile-time after unrolling: a nested a/b loop is left
+    // partly rolled at N = 8 and drags the delta rows into local memory)
+    constexpr PostPairs<NM> pairs{};
 #pragma unroll
-    for (int a = 0; a < NM; ++a) {
+    for (int p = 0; p < NP; ++p) {
+      const int a = pairs.a[p], b = pairs.b[p];
+      float2 q = make_float2(0.f, 0.f);  // packed fp32 pairs: one issue slot per two elements
 #pragma unroll
-      for (int b = a + 1; b < NM; ++b) {
-        float2 q = make_float2(0.f, 0.f);  // packed fp32 pairs: one issue slot per two elements
-#pragma unroll
-        for (int i = 0; i < kSlots; ++i) {
-          const float2 t = __ffma2_rn(d[b][i], neg1, d[a][i]);  // a - b, exactly
-          q = __ffma2_rn(t, t, q);
-        }
-        acc[p++] = q.x + q.y;
+      for (int i = 0; i < kSlots; ++i) {
+        const float2 t = __ffma2_rn(d[b][i], neg1, d[a][i]);  // a - b, exactly
+        q = __ffma2_rn(t, t, q);
       }
+      acc[p] = q.x + q.y;
     }
     const float best = post_max_of_lane_sums<NP>(acc, lane);
     if (lane == 0) disc[row] = sqrtf(best);
