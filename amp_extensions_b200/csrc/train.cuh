@@ -119,6 +119,34 @@ __global__ void train_transpose_kernel(const float* __restrict__ src, long long 
   }
 }
 
+// Several transposes in one launch (the weight slices every dgrad reads): blockIdx.z = descriptor * batch + member.
+struct TransposeDesc {
+  const float* src;
+  long long src_batch;
+  int src_pitch, rows, cols;
+  float* dst;
+  long long dst_batch;
+  int dst_pitch;
+};
+__global__ void train_transpose_batch_kernel(const TransposeDesc* __restrict__ descs, int batch) {
+  __shared__ float tile[32][33];
+  const TransposeDesc d = descs[blockIdx.z / batch];
+  const int member = blockIdx.z % batch;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= d.cols || r0 >= d.rows) return;
+  const float* s = d.src + member * d.src_batch;
+  float* o = d.dst + member * d.dst_batch;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < d.rows && c < d.cols) ? s[static_cast<long long>(r) * d.src_pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < d.cols && r < d.rows) o[static_cast<long long>(c) * d.dst_pitch + r] = tile[threadIdx.x][i];
+  }
+}
+
 // dY_j = dH (.) act'(h_j): relu' = [h > 0], tanh' = 1 - h^2, written as a tf32 operand into the gradient concat.
 __global__ void train_mask_kernel(const float* __restrict__ dh, int dh_pitch, const float* __restrict__ hbuf,
                                   int h_pitch, int h_col0, int width, long long n_rows, int tanh_act,
@@ -149,29 +177,6 @@ __global__ void train_rowsum_kernel(const float* __restrict__ x, int pitch, int 
   }
 }
 
-// partial[g][blockIdx.x] = this block's share of the sum of squares of member g's slice x[g * stride .. + per_member)
-// (gradient norm, dynamics.py:247-248); grid = (blocks <= kTrainPartials, members).
-__global__ void __launch_bounds__(256)
-train_sumsq_kernel(const float* __restrict__ x, long long per_member, long long stride, double* __restrict__ partial) {
-  const int g = blockIdx.y;
-  const float* p = x + static_cast<long long>(g) * stride;
-  double acc = 0.0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_member;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const double v = p[i];
-    acc += v * v;
-  }
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  __shared__ double sh[8];
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += sh[w];
-    partial[g * kTrainPartials + blockIdx.x] = t;
-  }
-}
-
 struct OptimArgs {
   int kind;          // 0: SGD with Nesterov momentum (torch.optim.SGD(nesterov=True)), 1: Adam
   float lr;
@@ -199,36 +204,67 @@ __global__ void train_tick_kernel(OptimState* st, float beta1, float beta2) {
   }
 }
 
-// Parameter update of one tensor: member g's parameters at p[g * p_stride + i], its gradient and optimiser moments
-// at {g, m, v}[g * g_stride + g_off + i], i < count; the clip coefficient comes from the member's gradient norm:
+// Every parameter tensor of the ensemble in one launch: blockIdx.z = tensor, blockIdx.y = member.  Member g's
+// parameters sit at p[g * p_stride + i], its gradient and optimiser moments at {g, m, v}[g * g_stride + g_off + i].
+// The norm kernel writes fixed-order block partials (gradient norm, dynamics.py:247-248); the update applies
 //   coef = min(1, clip / (sqrt(sumsq) + 1e-6))    (torch.nn.utils.clip_grad_norm_)
-__global__ void train_optim_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                   float* __restrict__ v, long long count, long long p_stride, long long g_stride,
-                                   long long g_off, int n_members, const double* __restrict__ sumsq, const OptimArgs a,
-                                   const OptimState* __restrict__ state) {
+// and then SGD-Nesterov or Adam.
+struct ParamDesc {
+  float* p;         // parameters, member stride p_stride
+  const float* g;   // gradient; {g, m, v}[member * g_stride + g_off + i]
+  float* m;
+  float* v;
+  long long count, p_stride, g_stride, g_off;
+};
+
+__global__ void __launch_bounds__(256)
+train_sumsq_batch_kernel(const ParamDesc* __restrict__ descs, int n_members, double* __restrict__ partial) {
+  const ParamDesc d = descs[blockIdx.z];
+  const int g = blockIdx.y;
+  const float* p = d.g + g * d.g_stride + d.g_off;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < d.count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double v = p[i];
+    acc += v * v;
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partial[(static_cast<long long>(blockIdx.z) * n_members + g) * kTrainPartials + blockIdx.x] = t;
+  }
+}
+
+__global__ void train_optim_batch_kernel(const ParamDesc* __restrict__ descs, int n_members,
+                                         const double* __restrict__ sumsq, const OptimArgs a,
+                                         const OptimState* __restrict__ state) {
+  const ParamDesc d = descs[blockIdx.z];
   const int gi = blockIdx.y;
-  if (gi >= n_members) return;
   const OptimState os = *state;
   float coef = 1.f;
   if (a.grad_clip > 0.f) {
     const float c = a.grad_clip / (static_cast<float>(sqrt(sumsq[gi])) + 1e-6f);
     coef = c < 1.f ? c : 1.f;
   }
-  float* pp = p + gi * p_stride;
-  const long long gbase = gi * g_stride + g_off;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+  float* pp = d.p + gi * d.p_stride;
+  const long long gbase = gi * d.g_stride + d.g_off;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < d.count;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float grad = g[gbase + i] * coef;
+    const float grad = d.g[gbase + i] * coef;
     float w = pp[i];
     if (a.kind == 0) {
-      const float buf = os.first_step ? grad : fmaf(a.momentum, m[gbase + i], grad);
-      m[gbase + i] = buf;
+      const float buf = os.first_step ? grad : fmaf(a.momentum, d.m[gbase + i], grad);
+      d.m[gbase + i] = buf;
       w -= a.lr * fmaf(a.momentum, buf, grad);
     } else {
-      const float m1 = fmaf(a.momentum, m[gbase + i], (1.f - a.momentum) * grad);
-      const float v1 = fmaf(a.beta2, v[gbase + i], (1.f - a.beta2) * grad * grad);
-      m[gbase + i] = m1;
-      v[gbase + i] = v1;
+      const float m1 = fmaf(a.momentum, d.m[gbase + i], (1.f - a.momentum) * grad);
+      const float v1 = fmaf(a.beta2, d.v[gbase + i], (1.f - a.beta2) * grad * grad);
+      d.m[gbase + i] = m1;
+      d.v[gbase + i] = v1;
       const float denom = sqrtf(v1) / sqrtf(os.bc2) + a.eps;
       w -= (a.lr / os.bc1) * (m1 / denom);
     }
