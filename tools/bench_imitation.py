@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--origin", action="store_true")
     ap.add_argument("--terms", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     from amp_extensions_b200 import ImitationReward
     dev = torch.device("cuda", 0)
@@ -65,9 +66,31 @@ def main():
         peak = json.load(open(p))["hbm_gbs"]
     gbs = bytes_per_pose * E / (ms * 1e-3) / 1e9
     rr = r[0] if isinstance(r, tuple) else r
+    cpu = None
+    if not args.skip_cpu and args.iters >= 10:
+        # the float64 restatement of CalcRewardImitate (oracle/imitation_oracle.py), one core, on a bounded sample
+        import time
+        import numpy as np
+        from oracle import imitation_oracle as io
+        clip = io.Clip(np.load(os.path.join(ROOT, "amp_extensions_b200", "data", "humanoid3d_spinkick.npz"))["frames_raw"],
+                       io.HUMANOID3D, "wrap")
+        p, v, t = sets[0]
+        n = 64
+        pp, vv, tt = p[:n].double().cpu().numpy(), v[:n].double().cpu().numpy(), t[:n].double().cpu().numpy()
+        io.imitation_reward_batch(io.HUMANOID3D, clip, pp[:4], vv[:4], tt[:4])
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 8.0:
+            io.imitation_reward_batch(io.HUMANOID3D, clip, pp, vv, tt)
+            reps += 1
+        cpu = {"value": n * reps / (time.perf_counter() - t0), "unit": "poses/s", "cores": 1, "kind": "port",
+               "sample": f"{reps} x {n} poses, numpy float64 restatement of CalcRewardImitate"}
     print(json.dumps({"workload": f"imitation reward, {E} poses vs spinkick clip", "ms_per_launch": ms,
                       "poses_per_s": E / (ms * 1e-3), "bytes_per_pose": bytes_per_pose, "achieved_gbs": gbs,
-                      "hbm_peak_gbs": peak, "frac": gbs / peak, "reward_mean": float(rr.mean())}))
+                      "hbm_peak_gbs": peak, "frac": gbs / peak, "reward_mean": float(rr.mean()),
+                      "fp32_roofline": {"flop_per_pose": 4104, "peak_tflops": 148 * 128 * 2 * 1.87e9 / 1e12,
+                                        "achieved_tflops": 4104 * E / (ms * 1e-3) / 1e12,
+                                        "note": "FLOP per pose counted from the ncu source page (DESIGN.md section 5)"},
+                      "cpu_baseline": cpu}))
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke=$?"
 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "bench_ref=$?"
 python bench.py --steps 300 --warmup 10 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench=$?"
 python tools/bench_imitation.py > $OUT/${TAG}_imit.json 2> $OUT/${TAG}_imit.err; echo "imit=$?"
-python tools/bench_imitation.py --origin --terms >> $OUT/${TAG}_imit.json 2>> $OUT/${TAG}_imit.err
+python tools/bench_imitation.py --origin --terms --skip-cpu >> $OUT/${TAG}_imit.json 2>> $OUT/${TAG}_imit.err
 python tools/bench_rollout.py > $OUT/${TAG}_rollout.json 2> $OUT/${TAG}_rollout.err; echo "rollout=$?"
 python tools/bench_mlpcost.py > $OUT/${TAG}_mlpcost.json 2> $OUT/${TAG}_mlpcost.err; echo "mlpcost=$?"
 if [ "${NCU:-1}" = "1" ]; then
