@@ -4,17 +4,26 @@ numpy float64 restatement, kept deliberately literal (4x4 homogeneous matrices, 
 Jacobian-based centre-of-mass velocity), of the reference C++ under
 deepmimic/deepmimic/DeepMimicCore/ (cited per function as FILE:LINE).
 
-PARITY UNPINNED: the reference C++ needs Eigen 3.3.7 + Bullet 2.88 + SWIG, none of which exist in the
-build image, and the reference ships no test vectors for it.  This restatement is anchored on closed-form
-known answers (tests/test_imitation_oracle.py): reward == 1 at pose == clip(t); a chest rotation by theta
-gives pose_err = w_chest*theta^2; FK against hand-computed joint positions; COM velocity against a finite
-difference of the COM position.  One deliberate deviation, shared with the CUDA path and stated in
-DESIGN.md: the simulated character's COM velocity comes from the same kinematic formula as the kinematic
+PARITY PINNED (kinematics), PARTLY RESTATED (glue): oracle/ref_build.py compiles the reference's own
+util/MathUtil.cpp, anim/KinTree.cpp, anim/Motion.cpp, sim/RBDUtil.cpp, sim/SpAlg.cpp, sim/RBDModel.cpp, util/JsonUtil.cpp,
+util/FileUtil.cpp and util/json/*.cpp where they lie into oracle/_ref/libdmref.so.  Eigen 3.3.7 is absent from the
+image (as are Bullet 2.88 and SWIG), so those files are compiled against the stand-in headers in oracle/eigen_shim;
+the ~60 lines of cSceneImitate::CalcRewardImitate that combine the error terms, the kinematic character's loop /
+origin handling and CtController's state layout need Bullet-dependent classes and are restated in oracle/ref_driver.cpp
+around calls into the compiled reference functions.  tests/test_imitation_ref.py checks every function of this file
+against that library (live, and through the committed vectors tests/golden/imitation_ref_golden.npz written by
+tests/golden/make_imitation_ref_golden.py): clip tables, clip sampling, per-joint pose / velocity errors, forward
+kinematics, heading and origin transform, centre of mass and its velocity, state features, reward and its five terms
+agree to <= 1e-9 (observed 1e-14).  The closed-form known answers of tests/test_imitation_oracle.py remain as an
+independent anchor: reward == 1 at pose == clip(t); a chest rotation by theta gives pose_err = w_chest*theta^2; FK
+against hand-computed joint positions; COM velocity against a finite difference of the COM position.
+
+One deliberate deviation, shared with the CUDA path and stated in DESIGN.md: the simulated character's COM velocity comes from the same kinematic formula as the kinematic
 character's (RBDUtil.cpp:572-613); the reference takes it from Bullet body velocities
 (SimCharacter.cpp:398-436), which do not exist for a learned-dynamics state.
 
 Eigen arithmetic that is not under the reference tree (Quaternion::slerp, q*v) is restated from Eigen
-3.3.7 (pinned in the reference's setup.md:27).
+3.3.7 (pinned in the reference's setup.md:27) - here and, independently, in oracle/eigen_shim/Eigen/Core.
 """
 import numpy as np
 

@@ -189,3 +189,53 @@ def test_clip_reset_states_feed_the_env(setup):
     assert (ob[:, 0] > 0.6).all() and (ob[:, 0] < 1.3).all()           # root height along the spin kick
     from oracle import milo_oracle as mo
     assert not mo.simenv_collided(ob.astype(np.float64)).any()          # the reference motion never falls
+
+
+# ---- against outputs of the reference's own compiled kinematics code (tests/golden/imitation_ref_golden.npz) ----
+
+def _ref_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "imitation_ref_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", ["plain", "origin", "far"])
+def test_reward_matches_reference_golden(setup, tag):
+    """The CUDA reward against cKinTree / cRBDUtil / cMotion themselves (compiled from the reference sources by
+    oracle/ref_build.py, vectors written by tests/golden/make_imitation_ref_golden.py).  Inputs are exactly
+    float32-representable; tolerance 1e-3 relative on the reward and on each exponential sub-reward."""
+    imit, _ = setup
+    g = _ref_golden()
+    pose, vel, t = g[f"{tag}_pose"], g[f"{tag}_vel"], g[f"{tag}_t"]
+    origin = torch.from_numpy(g[f"{tag}_origin"]).float() if tag == "origin" else None
+    r, terms = imit.reward(torch.from_numpy(pose).float(), torch.from_numpy(vel).float(), torch.from_numpy(t).float(),
+                           origin, want_terms=True)
+    close(terms.cpu().numpy(), g[f"{tag}_terms"])
+    close(r.cpu().numpy(), g[f"{tag}_reward"])
+
+
+def test_clip_sampling_matches_reference_golden(setup):
+    imit, clip = setup
+    g = _ref_golden()
+    t, org = g["sample_t"], g["sample_origin"]
+    pose, vel = imit.sample(torch.from_numpy(t).float(), torch.from_numpy(org).float())
+    # a sample whose time sits on a cycle boundary may wrap one way in fp32 and the other in float64
+    phase = np.mod(t, clip.duration)
+    ok = np.minimum(phase, clip.duration - phase) > 1e-4
+    assert ok.sum() >= t.size - 4
+    np.testing.assert_allclose(pose.cpu().numpy()[ok], g["sample_pose"][ok], atol=2e-5)
+    np.testing.assert_allclose(vel.cpu().numpy()[ok], g["sample_vel"][ok], atol=2e-3, rtol=1e-4)
+
+
+def test_record_state_matches_reference_golden(setup):
+    imit, _ = setup
+    g = _ref_golden()
+    pose, vel = g["plain_pose"], g["plain_vel"]
+    n = g["state_features"].shape[1]
+    for k, (aw, wrp, wrr, vs) in enumerate(g["state_flags"]):
+        st = imit.record_state(torch.from_numpy(pose[:n]).float(), torch.from_numpy(vel[:n]).float(),
+                               record_all_world=bool(aw), record_world_root_pos=bool(wrp),
+                               record_world_root_rot=bool(wrr), vel_scale=float(vs)).cpu().numpy()
+        ref = g["state_features"][k]
+        np.testing.assert_allclose(st[:, :136], ref[:, :136], rtol=0, atol=5e-5)
+        vscale = float(np.abs(ref[:, 136:]).mean())
+        np.testing.assert_allclose(st[:, 136:], ref[:, 136:], rtol=0, atol=REL * max(vscale, 1e-3))
