@@ -1,4 +1,6 @@
 """CPU: the oracle restatement against the golden vectors produced by the reference's own code."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -130,6 +132,65 @@ def test_simenv_step_horizon_and_velocity():
     assert not mo.simenv_step(s, d, np.array([0]))[2][0]
     assert mo.simenv_step(s, d, np.array([0]), enable_velocity_check=True)[2][0]
     assert nxt.dtype == np.float64
+
+
+# ---------------------------------------------------------------------------------------------------
+# SimEnv against the reference's own sim_env.py (tests/golden/simenv_golden.npz, written by
+# tests/golden/make_simenv_golden.py: the reference class run unmodified over stubbed gym / simulator imports)
+
+def _simenv_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "simenv_golden.npz"))
+
+
+def test_simenv_tables_match_the_reference_constructor():
+    """sim_env.py:84-116 with the reference's spinkick arg / character / controller files."""
+    g = _simenv_golden()
+    assert list(g["fall_offsets"]) == [9 * b + 1 for b in mo.HUMANOID3D_FALL_BODIES]
+    for i, b in enumerate(mo.HUMANOID3D_FALL_BODIES):
+        shape, p0, p1 = mo.HUMANOID3D_BODY_DEFS[b]
+        assert (shape == "capsule") == bool(g["fall_is_capsule"][i])
+        assert (p0, p1) == (g["fall_params"][i, 0], g["fall_params"][i, 1])
+    assert int(g["record_all_world"]) == 0 and int(g["record_world_root_pos"]) == 0
+
+
+def test_simenv_contact_thresholds_match_the_reference():
+    """116 states placed 2e-6 / 1e-3 either side of `<= radius + 1e-4` for every fall body and both capsule caps."""
+    g = _simenv_golden()
+    got = mo.simenv_collided(g["contact_states"])
+    assert (got == g["contact_collided"]).all()
+    assert 0 < g["contact_collided"].sum() < g["contact_collided"].size
+
+
+def test_simenv_velocity_check_matches_the_reference():
+    g = _simenv_golden()
+    zero = np.zeros_like(g["vel_states"], dtype=np.float32)
+    steps = np.zeros(len(zero), dtype=np.int64)
+    assert (mo.simenv_step(g["vel_states"], zero, steps, enable_velocity_check=True)[2] == g["vel_done_enabled"]).all()
+    assert (mo.simenv_step(g["vel_states"], zero, steps)[2] == g["vel_done_default"]).all()
+    assert g["vel_done_enabled"].any() and not g["vel_done_default"].any()
+
+
+def test_simenv_episodes_match_the_reference():
+    """reset -> 10 steps, five episodes, horizon 8: observations, step counter, done flags and the member
+    round-robin of the reference SimEnv, replayed by the oracle (ensemble rebuilt from the seed and checked
+    against the stored weight checksums)."""
+    g = _simenv_golden()
+    N, hidden = int(g["N"]), [int(h) for h in g["hidden"]]
+    s, a, s2 = H.synth_dataset(int(g["dataset_rows"]), 226, 28, int(g["dataset_seed"]))
+    ws, bs = mo.init_ensemble(226, 28, hidden, N, base_seed=int(g["base_seed"]), dense_connect=True)
+    np.testing.assert_allclose([[float(w.double().abs().sum()) for w in m] for m in ws], g["weight_checksum"], rtol=1e-12)
+    tf = mo.get_transformations(s, a, s2)
+    assert list(g["traj_member"]) == [(e + 1) % N for e in range(len(g["traj_member"]))]   # sim_env.py:282-283
+    for e in range(g["traj_ob0"].shape[0]):
+        ob = g["traj_ob0"][e:e + 1].copy()
+        m = int(g["traj_member"][e])
+        steps = np.zeros(1, dtype=np.int64)
+        for k in range(g["traj_actions"].shape[1]):
+            act = torch.from_numpy(g["traj_actions"][e, k:k + 1]).float()
+            preds = mo.ensemble_forward(ws, bs, tf, torch.from_numpy(ob).float(), act)
+            ob, steps, done = mo.simenv_step(ob, preds[m].numpy(), steps, horizon=8)
+            np.testing.assert_allclose(ob[0], g["traj_obs"][e, k], rtol=0, atol=1e-5)
+            assert int(steps[0]) == int(g["traj_num_steps"][e, k]) and bool(done[0]) == bool(g["traj_done"][e, k])
 
 
 # ---------------------------------------------------------------------------------------------------
