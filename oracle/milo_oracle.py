@@ -7,9 +7,12 @@ does and fails loudly without its CUDA library.
 
 Pinning: tests/golden/milo_golden.npz was produced by tests/golden/make_golden.py, which imports the
 reference's own milo/milo/{dynamics,datasets,linear_cost}.py in the build container and stores their
-outputs; tests/test_oracle.py checks every function below against those vectors.  SimEnv itself
-(gym + SWIG DeepMimicCore) cannot be imported anywhere, so `simenv_*` is pinned only by hand-built
-known-answer states: parity unpinned for that part.
+outputs; tests/test_oracle.py checks every function below against those vectors.  SimEnv imports gym and
+the SWIG DeepMimicCore, which are absent; tests/golden/make_simenv_golden.py stubs exactly those two imports
+and runs the reference's gym_simenv/envs/sim_env.py unmodified (constructor on the reference's own arg /
+character / controller files, reset, step, is_done, check_*), so `simenv_*` is pinned by
+tests/golden/simenv_golden.npz (episodes, 116 contact-threshold states, velocity check) as well as by the
+hand-built known-answer states.
 
 Reference files (paths under the reference tree):
   DYN = milo/milo/dynamics.py     DS = milo/milo/datasets.py

@@ -8,8 +8,10 @@ this module.
 Pinning: tests/golden/rollout_golden.npz was produced by tests/golden/make_rollout_golden.py, which imports the
 reference's own mjrl/mjrl/utils/{fc_network,process_samples}.py and mjrl/mjrl/policies/gaussian_mlp.py in the
 build container and stores their outputs; tests/test_rollout_oracle.py checks the functions below against those
-vectors.  The sampler loop itself (milo/milo/sampler.py) needs a gym env and is restated on top of the pinned
-pieces: parity unpinned for `rollout`.
+vectors.  The sampler loop itself (milo/milo/sampler.py::get_samples) is pinned as well:
+tests/golden/make_sampler_golden.py runs it unmodified over the reference SimEnv (gym / simulator imports stubbed as
+in make_simenv_golden.py), a reference DynamicsEnsemble and the reference MLP policy; `rollout` replays those
+trajectories from the stored seeds' exploration draws (tests/test_rollout_oracle.py, tests/golden/sampler_golden.npz).
 
 Reference files (paths under the reference tree):
   FC  = mjrl/mjrl/utils/fc_network.py          GM = mjrl/mjrl/policies/gaussian_mlp.py

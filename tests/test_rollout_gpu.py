@@ -335,3 +335,44 @@ def test_histogram_kernel_and_device_quantile_match_torch():
         got = parallel.global_quantile(x, q, engine=eng)
         ref = float(torch.quantile(xd, q))
         assert abs(got - ref) <= 1e-6 * float(xd.max() - xd.min()), (q, got, ref)
+
+
+def test_device_rollout_matches_the_reference_sampler():
+    """tests/golden/sampler_golden.npz: the reference's own get_samples + SimEnv + DynamicsEnsemble + MLP policy, six
+    trajectories.  Here each trajectory is one env column of DeviceRollout.collect, started from the same state and
+    member, fed the same exploration draws; the prefix up to the reference trajectory's end must agree (1e-3 per
+    step of the state scale 1.0), and the column must signal `done` at the same step unless the deciding height is
+    within 1e-3 of its threshold."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, VecSimEnv
+    from amp_extensions_b200.rollout import DeviceRollout
+    from tests.test_parity_gpu import collision_margin
+    from tests.test_rollout_oracle import sampler_golden, sampler_noise
+    g = sampler_golden()
+    S, A = 226, 28
+    N, hidden, horizon = int(g["N"]), [int(h) for h in g["hidden"]], int(g["horizon"])
+    ds = AmpDataset(*H.synth_dataset(int(g["dataset_rows"]), S, A, int(g["dataset_seed"])))
+    ens = DynamicsEnsemble(S, A, ds, None, num_models=N, hidden_sizes=hidden, dense_connect=True, transform=True,
+                           base_seed=int(g["base_seed"]))
+    got = [[float(l.weight.data.double().abs().sum()) for l in m.model.fc_layers] for m in ens.models]
+    np.testing.assert_allclose(got, g["weight_checksum"], rtol=1e-12)
+    n_traj, T, _ = g["actions"].shape
+    ob0 = torch.from_numpy(g["observations"][:, 0]).float()
+    env = VecSimEnv(ens, n_traj, horizon=horizon, reset_states=ob0, seed=1)
+    env.reset(initial_states=ob0)
+    env.member.copy_(torch.from_numpy(g["member"]).to(torch.int32))
+    ws = [torch.from_numpy(g[f"pol_w{i}"]) for i in range(3)]
+    bs = [torch.from_numpy(g[f"pol_b{i}"]) for i in range(3)]
+    pol = _Policy(_FC(ws, bs, "tanh"), g["log_std"])
+    noise = torch.from_numpy(sampler_noise(g)).float().cuda()
+    batch = DeviceRollout(env, pol, seed=0).collect(T, noise=noise, pick=torch.zeros((T, n_traj), dtype=torch.int32).cuda())
+    done = batch.done.cpu().numpy().astype(bool)
+    for k in range(n_traj):
+        n = int(g["length"][k])
+        for name in ("observations", "next_observations", "actions", "means"):
+            x = getattr(batch, name).cpu().numpy()[:n, k]
+            err = np.abs(x - g[name][k, :n]).max(axis=1)
+            assert (err < 1e-3 * np.arange(1, n + 1)).all(), (k, name, err)
+        first = int(np.argmax(done[:, k])) + 1 if done[:, k].any() else None
+        if first != n:
+            t = min(n, first or n) - 1
+            assert collision_margin(g["next_observations"][k, t][None])[0] < 1e-3, (k, first, n)

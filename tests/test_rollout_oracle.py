@@ -44,3 +44,51 @@ def test_returns_and_gae_match_process_samples():
         assert len(r) == n
         assert np.array_equal(ro.discount_sum(r, gamma), G[f"ps/returns{i}"])
         assert np.array_equal(ro.gae_advantages(r, b, bool(term), gamma, lam), G[f"ps/advantages{i}"])
+
+
+# ---- the whole loop against the reference's own sampler.get_samples (tests/golden/sampler_golden.npz) ----------
+
+def sampler_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "sampler_golden.npz"))
+
+
+def sampler_noise(g):
+    """The draws MLP.get_action made inside get_samples: np.random.seed(seed + k) per trajectory (sampler.py:36-38),
+    then uniform() and randn(action_dim) per step (gaussian_mlp.py:95-104)."""
+    n_traj, T, A = g["actions"].shape
+    noise = np.zeros((T, n_traj, A))
+    for k in range(n_traj):
+        rs = np.random.RandomState(int(g["seed"]) + k + 1)
+        for t in range(int(g["length"][k])):
+            rs.uniform()
+            noise[t, k] = rs.randn(A)
+    return noise
+
+
+def test_rollout_loop_matches_the_reference_sampler():
+    """get_samples + SimEnv + DynamicsEnsemble + MLP policy of the reference, six trajectories (early falls and horizon
+    cuts), replayed by the batched restatement with the same exploration draws: observations, actions, policy means,
+    trajectory lengths and the member round-robin."""
+    from oracle import milo_oracle as mo
+    from tests import helpers as H
+    g = sampler_golden()
+    N, hidden, horizon = int(g["N"]), [int(h) for h in g["hidden"]], int(g["horizon"])
+    s, a, s2 = H.synth_dataset(int(g["dataset_rows"]), 226, 28, int(g["dataset_seed"]))
+    ws, bs = mo.init_ensemble(226, 28, hidden, N, base_seed=int(g["base_seed"]), dense_connect=True)
+    np.testing.assert_allclose([[float(w.double().abs().sum()) for w in m] for m in ws], g["weight_checksum"], rtol=1e-12)
+    tf = mo.get_transformations(s, a, s2)
+    policy = dict(ws=[torch.from_numpy(g[f"pol_w{i}"]) for i in range(3)], bs=[torch.from_numpy(g[f"pol_b{i}"]) for i in range(3)],
+                  log_std=g["log_std"])
+    n_traj, T, _ = g["actions"].shape
+    noise = sampler_noise(g)
+    res = ro.rollout(ws, bs, tf, policy, g["observations"][:, 0], g["member"], np.zeros(n_traj, dtype=np.int64),
+                     g["observations"][:, 0], noise, np.zeros((T, n_traj), dtype=np.int64), horizon=horizon, n_models=N)
+    for k in range(n_traj):
+        n = int(g["length"][k])
+        first_done = int(np.argmax(res["done"][:, k])) + 1
+        assert res["done"][:, k].any() and first_done == n, (k, first_done, n)     # same trajectory length
+        np.testing.assert_allclose(res["means"][:n, k], g["means"][k, :n], atol=2e-5)
+        np.testing.assert_allclose(res["actions"][:n, k], g["actions"][k, :n], atol=2e-5)
+        np.testing.assert_allclose(res["observations"][:n, k], g["observations"][k, :n], atol=2e-5)
+        np.testing.assert_allclose(res["next_observations"][:n, k], g["next_observations"][k, :n], atol=2e-5)
+    assert sorted(set(int(x) for x in g["length"])) != [horizon]   # some trajectories ended on a fall
