@@ -68,22 +68,38 @@ def main():
     rr = r[0] if isinstance(r, tuple) else r
     cpu = None
     if not args.skip_cpu and args.iters >= 10:
-        # the float64 restatement of CalcRewardImitate (oracle/imitation_oracle.py), one core, on a bounded sample
+        # CPU baseline on a bounded sample: the reference's own compiled kinematics code (oracle/_ref/libdmref.so, built
+        # by oracle/ref_build.py from the reference sources; "reference") when it was shipped, else the float64 numpy
+        # restatement of CalcRewardImitate ("port"); one core either way (the reference's reward is single-threaded)
+        import ctypes
         import time
         import numpy as np
         from oracle import imitation_oracle as io
-        clip = io.Clip(np.load(os.path.join(ROOT, "amp_extensions_b200", "data", "humanoid3d_spinkick.npz"))["frames_raw"],
-                       io.HUMANOID3D, "wrap")
+        from oracle import ref_build
         p, v, t = sets[0]
-        n = 64
-        pp, vv, tt = p[:n].double().cpu().numpy(), v[:n].double().cpu().numpy(), t[:n].double().cpu().numpy()
-        io.imitation_reward_batch(io.HUMANOID3D, clip, pp[:4], vv[:4], tt[:4])
+        lib = ref_build.load()
+        if lib is not None:
+            n = 4096
+            pp, vv, tt = (np.ascontiguousarray(x[:n].double().cpu().numpy()) for x in (p, v, t))
+            out = np.zeros(n)
+            PD = ctypes.POINTER(ctypes.c_double)
+            call = lambda: lib.dmref_reward_batch(n, pp.ctypes.data_as(PD), vv.ctypes.data_as(PD), tt.ctypes.data_as(PD),
+                                                  None, out.ctypes.data_as(PD), None)
+            kind, what = "reference", "cSceneImitate::CalcRewardImitate over the reference's compiled cKinTree / cRBDUtil / cMotion (oracle/_ref/libdmref.so)"
+        else:
+            n = 64
+            clip = io.Clip(np.load(os.path.join(ROOT, "amp_extensions_b200", "data", "humanoid3d_spinkick.npz"))["frames_raw"],
+                           io.HUMANOID3D, "wrap")
+            pp, vv, tt = p[:n].double().cpu().numpy(), v[:n].double().cpu().numpy(), t[:n].double().cpu().numpy()
+            call = lambda: io.imitation_reward_batch(io.HUMANOID3D, clip, pp, vv, tt)
+            kind, what = "port", "numpy float64 restatement of CalcRewardImitate"
+        call()
         t0, reps = time.perf_counter(), 0
         while time.perf_counter() - t0 < 8.0:
-            io.imitation_reward_batch(io.HUMANOID3D, clip, pp, vv, tt)
+            call()
             reps += 1
-        cpu = {"value": n * reps / (time.perf_counter() - t0), "unit": "poses/s", "cores": 1, "kind": "port",
-               "sample": f"{reps} x {n} poses, numpy float64 restatement of CalcRewardImitate"}
+        cpu = {"value": n * reps / (time.perf_counter() - t0), "unit": "poses/s", "cores": 1, "kind": kind,
+               "sample": f"{reps} x {n} poses, {what}"}
     print(json.dumps({"workload": f"imitation reward, {E} poses vs spinkick clip", "ms_per_launch": ms,
                       "poses_per_s": E / (ms * 1e-3), "bytes_per_pose": bytes_per_pose, "achieved_gbs": gbs,
                       "hbm_peak_gbs": peak, "frac": gbs / peak, "reward_mean": float(rr.mean()),
