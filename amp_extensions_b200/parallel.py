@@ -6,7 +6,8 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests) carries only small reduc
   * the discrepancy threshold = dataset maximum (reference milo/milo/dynamics.py:145-152) -> all-reduce MAX,
     or, as an extension, a global quantile of the per-row discrepancies via a two-pass histogram all-reduce;
   * fit_cost's feature mean (reference milo/milo/linear_cost.py:84-94) -> all-reduce SUM of [D] sums + count;
-  * rollout cost / return statistics (reference mjrl/mjrl/algos/batch_reinforce.py:135-141, 288-295).
+  * rollout cost / return statistics (reference mjrl/mjrl/algos/batch_reinforce.py:135-141, 288-295);
+  * normalisation statistics of a sharded offline dataset (reference milo/milo/datasets.py:23-43).
 
 Every function works un-initialised (world size 1) and on CPU tensors (gloo) as well as CUDA tensors (NCCL).
 """
@@ -109,6 +110,25 @@ def global_mean(sum_local, count_local):
                         torch.as_tensor([float(count_local)], dtype=torch.float64).to(torch.as_tensor(sum_local).device)])
     packed = all_reduce_sum(packed)
     return packed[:-1] / packed[-1].clamp_min(1.0)
+
+
+def global_transformations(states_local, actions_local, next_states_local):
+    """AmpDataset.get_transformations (datasets.py:23-43) over an offline dataset whose rows are sharded across
+    ranks: two passes, each one all-reduce(SUM) of the per-rank column sums (fp64) — first the means, then the mean
+    absolute deviations around the GLOBAL means.  Returns the reference's tuple (state_mean, state_scale,
+    action_mean, action_scale, diff_mean, diff_scale) as fp32 tensors, identical on every rank.  Host-side
+    statistics, computed once when the ensemble is built (the reference does the same on the host)."""
+    parts = [states_local.double(), actions_local.double(), (next_states_local - states_local).double()]
+    n_local = float(states_local.shape[0])
+    widths = [p.shape[1] for p in parts]
+    packed = torch.cat([p.sum(dim=0) for p in parts] + [torch.tensor([n_local], dtype=torch.float64)])
+    packed = all_reduce_sum(packed)
+    n = packed[-1].clamp_min(1.0)
+    means = [m.float() for m in torch.split(packed[:-1] / n, widths)]
+    dev = torch.cat([(p.float() - m).abs().double().sum(dim=0) for p, m in zip(parts, means)])
+    dev = all_reduce_sum(dev)
+    scales = [(d / n).float() + 1e-8 for d in torch.split(dev, widths)]
+    return (means[0], scales[0], means[1], scales[1], means[2], scales[2])
 
 
 def rollout_stats(cost, ipm, bonus, done, num_steps):

@@ -53,6 +53,13 @@ def _worker(rank, world, port, out_dir):
     steps = torch.randint(1, 300, (E,), generator=g2, dtype=torch.int32)
     a, b = parallel.shard_range(E)
     res["stats"] = parallel.rollout_stats(cost[a:b], ipm[a:b], bonus[a:b], done[a:b], steps[a:b])
+    # normalisation statistics of an offline dataset sharded unevenly across the ranks
+    g3 = torch.Generator().manual_seed(13)
+    ds_s = torch.randn(3001, 226, generator=g3) * 2 + 0.5
+    ds_a = torch.randn(3001, 28, generator=g3)
+    ds_n = ds_s + 0.05 * torch.randn(3001, 226, generator=g3)
+    cut = slice(0, 1000) if rank == 0 else slice(1000, 3001)
+    res["tf"] = parallel.global_transformations(ds_s[cut], ds_a[cut], ds_n[cut])
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,6 +118,24 @@ def test_rollout_stats_equal_the_single_process_values(two_rank_results):
         assert abs(s["int"] - float((-bonus).double().sum())) < 1e-6
         assert abs(s["ext"] - float((-ipm).double().sum())) < 1e-6
         assert abs(s["ep_len_mean"] - float(steps[done].double().mean())) < 1e-9
+
+
+def test_sharded_transformations_equal_the_single_process_values(two_rank_results):
+    """parallel.global_transformations against AmpDataset.get_transformations (itself pinned to the reference's
+    datasets.py by tests/test_host_shims.py) on the union of the shards; fp32 statistics, sums carried in fp64."""
+    sys.path.insert(0, ROOT)
+    from amp_extensions_b200 import AmpDataset
+    g3 = torch.Generator().manual_seed(13)
+    ds_s = torch.randn(3001, 226, generator=g3) * 2 + 0.5
+    ds_a = torch.randn(3001, 28, generator=g3)
+    ds_n = ds_s + 0.05 * torch.randn(3001, 226, generator=g3)
+    ref = AmpDataset(ds_s, ds_a, ds_n).get_transformations()
+    for r in two_rank_results:
+        for got, want in zip(r["tf"], ref):
+            assert got.dtype == torch.float32 and got.shape == want.shape
+            torch.testing.assert_close(got, want, rtol=2e-6, atol=1e-7)
+    for x, y in zip(two_rank_results[0]["tf"], two_rank_results[1]["tf"]):
+        assert torch.equal(x, y)
 
 
 def test_single_process_path_needs_no_process_group():
