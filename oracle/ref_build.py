@@ -114,7 +114,17 @@ def load():
     lib.dmref_reward.argtypes, lib.dmref_reward.restype = [pd, pd, pd, pd, d, pd], d
     lib.dmref_record_state.argtypes, lib.dmref_record_state.restype = [pd, pd, i, i, i, d, pd], None
     lib.dmref_reward_batch.argtypes, lib.dmref_reward_batch.restype = [i, pd, pd, pd, pd, pd, pd], None
-    rc = lib.dmref_init(char_file.encode(), motion_file.encode())
+    # cMotion::Load reports on stdout (Motion.cpp); keep the caller's stdout clean (bench lines are parsed as JSON)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        rc = lib.dmref_init(char_file.encode(), motion_file.encode())
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
     if rc != 0:
         raise RuntimeError(f"dmref_init failed with code {rc}")
     _lib = lib
