@@ -345,7 +345,11 @@ template <typename E>
 void launch_prep(simstep_handle* h, const float* s, const float* a, long long n, long long rows_pad,
                  const float* w_src, cudaStream_t st) {
   const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
-  launch_pdl(prep_input_kernel<E>, dim3(grid), dim3(kPrepThreads), 0, st, s, a, h->S, h->A, h->XP, n, rows_pad,
+  // column pairs are read with one 8-byte load when no pair straddles the state / action boundary
+  const bool vec = h->S % 2 == 0 && h->A % 2 == 0 && reinterpret_cast<uintptr_t>(s) % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(a) % 8 == 0;
+  auto kern = vec ? prep_input_kernel<E, true> : prep_input_kernel<E, false>;
+  launch_pdl(kern, dim3(grid), dim3(kPrepThreads), 0, st, s, a, h->S, h->A, h->XP, n, rows_pad,
              h->cfg.transform ? h->tf_dev : nullptr, static_cast<typename E::storage*>(h->xbuf), w_src,
              w_src ? h->rff_wpad : nullptr, h->D);
   g_launches++;

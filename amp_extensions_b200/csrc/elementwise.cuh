@@ -58,10 +58,14 @@ __device__ __forceinline__ typename Pair<typename E::storage>::type make_pair_cv
 // milo/milo/dynamics.py:225-230) written in the GEMM operand format.  Rows in
 // [n_rows, rows_pad) are zero-filled so padded tiles stay finite.  One block
 // walks rows; each thread owns two adjacent columns (XP is even) and stores
-// them as one packed pair.
+// them as one packed pair.  VEC: S and A are even and both sources 8-byte
+// aligned, so a column pair never straddles the state / action boundary and is
+// read with one 8-byte load.  The kernel was issue-bound (ncu: 16 M warp
+// instructions for 61 MB of traffic), hence the per-thread source pointer,
+// the hoisted reciprocal scale and the pointer-stepped row loop.
 constexpr int kPrepThreads = 128;
 constexpr int kPrepRows = 4;
-template <typename E>
+template <typename E, bool VEC>
 __global__ void __launch_bounds__(kPrepThreads)
 prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A, int XP,
                   long long n_rows, long long rows_pad,
@@ -74,43 +78,55 @@ prep_input_kernel(const float* __restrict__ state, const float* __restrict__ act
   // the step's cost weights ride along: block 0 stages w into the zero-padded vector the RFF epilogue reads
   if (w_src != nullptr && blockIdx.x == 0)
     for (int i = threadIdx.x; i < w_len; i += kPrepThreads) w_dst[i] = w_src[i];
+  const long long stride = gridDim.x;
   for (int c0 = 2 * threadIdx.x; c0 < XP; c0 += 2 * kPrepThreads) {
     // per-column constants hoisted out of the row loop
-    float mean[2] = {0.f, 0.f}, scale[2] = {1.f, 1.f};
-    int src[2];  // 0: state, 1: action, 2: zero padding
+    float mean[2] = {0.f, 0.f}, rscale[2] = {1.f, 1.f};
+    const float* col_ptr[2] = {nullptr, nullptr};  // null: zero padding
+    long long pitch[2] = {0, 0};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int col = c0 + i;
-      src[i] = col < S ? 0 : (col < S + A ? 1 : 2);
-      if (tf && src[i] == 0) { mean[i] = tf[col]; scale[i] = tf[S + col]; }
-      if (tf && src[i] == 1) { mean[i] = tf[2 * S + col - S]; scale[i] = tf[2 * S + A + col - S]; }
+      if (col < S) {
+        col_ptr[i] = state + col;
+        pitch[i] = S;
+        if (tf) { mean[i] = tf[col]; rscale[i] = 1.f / tf[S + col]; }
+      } else if (col < S + A) {
+        col_ptr[i] = action + (col - S);
+        pitch[i] = A;
+        if (tf) { mean[i] = tf[2 * S + col - S]; rscale[i] = 1.f / tf[2 * S + A + col - S]; }
+      }
     }
-    // kPrepRows rows per trip: all their loads are issued before the first is used (bytes in flight, not math,
-    // bound this kernel)
-    for (long long row0 = blockIdx.x; row0 < rows_pad; row0 += static_cast<long long>(gridDim.x) * kPrepRows) {
+    // kPrepRows rows per trip: all their loads are issued before the first is used
+    for (long long row0 = blockIdx.x; row0 < rows_pad; row0 += stride * kPrepRows) {
       float v[kPrepRows][2];
 #pragma unroll
       for (int r = 0; r < kPrepRows; ++r) {
-        const long long row = row0 + static_cast<long long>(r) * gridDim.x;
+        const long long row = row0 + r * stride;
         v[r][0] = v[r][1] = 0.f;
         if (row < n_rows) {
+          if (VEC) {
+            if (col_ptr[0] != nullptr) {
+              const float2 t = *reinterpret_cast<const float2*>(col_ptr[0] + row * pitch[0]);
+              v[r][0] = t.x;
+              v[r][1] = t.y;
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int col = c0 + i;
-            if (src[i] == 0) v[r][i] = state[row * S + col];
-            else if (src[i] == 1) v[r][i] = action[row * A + col - S];
+            for (int i = 0; i < 2; ++i)
+              if (col_ptr[i] != nullptr) v[r][i] = col_ptr[i][row * pitch[i]];
           }
         }
       }
 #pragma unroll
       for (int r = 0; r < kPrepRows; ++r) {
-        const long long row = row0 + static_cast<long long>(r) * gridDim.x;
+        const long long row = row0 + r * stride;
         if (row < rows_pad) {
           float o[2] = {0.f, 0.f};
           if (row < n_rows) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              if (src[i] != 2) o[i] = (v[r][i] - mean[i]) / scale[i];
+              if (col_ptr[i] != nullptr) o[i] = (v[r][i] - mean[i]) * rscale[i];
           }
           *reinterpret_cast<P*>(x + row * XP + c0) = make_pair_cvt<E>(o[0], o[1]);
         }

@@ -25,6 +25,11 @@
 
 namespace simstep {
 
+// depth of the operand ring of the cta_group::2 kernel: 5 x 32 KB + 2 x 16 KB of store staging = 193 KB; 6 fits
+// (225 KB of the 227 KB a CTA may use) and was measured, see DESIGN.md section 7
+#ifndef SIMSTEP_GEMM_STAGES_CG2
+#define SIMSTEP_GEMM_STAGES_CG2 5
+#endif
 constexpr int kBlockM = 128;   // accumulator rows per CTA
 constexpr int kBlockN = 256;   // accumulator columns (output features per tile)
 constexpr int kNumEpiWarps = 4;
@@ -40,7 +45,7 @@ struct GemmShape {
   static constexpr int kBRows = kBlockN / CG;          // B rows staged per CTA
   static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = CG == 2 ? 5 : 4;
+  static constexpr int kStages = CG == 2 ? SIMSTEP_GEMM_STAGES_CG2 : 4;
   static constexpr size_t smem_bytes() {
     return 1024 /*align slack*/ + size_t(kStages) * kStageBytes + size_t(kOutStages) * kOutStageBytes + 256;
   }
