@@ -30,6 +30,10 @@ namespace simstep {
 #ifndef SIMSTEP_GEMM_STAGES_CG2
 #define SIMSTEP_GEMM_STAGES_CG2 5
 #endif
+// staging tiles of the TMA-store epilogue (16 KB each); kOutStages - 1 stores may still be reading shared memory
+#ifndef SIMSTEP_GEMM_OUT_STAGES
+#define SIMSTEP_GEMM_OUT_STAGES 2
+#endif
 constexpr int kBlockM = 128;   // accumulator rows per CTA
 constexpr int kBlockN = 256;   // accumulator columns (output features per tile)
 constexpr int kNumEpiWarps = 4;
@@ -38,7 +42,7 @@ constexpr int kGemmThreads = 64 + kNumEpiThreads;  // warp 0 TMA, warp 1 MMA, wa
 constexpr int kTmemCols = 512;                     // two 128x256 fp32 accumulators
 constexpr int kABytes = kBlockM * 128;             // one swizzle atom (128 B) per row
 constexpr int kOutStageBytes = kBlockM * 128;      // staging tile of the TMA-store epilogue: 128 rows x 128 B
-constexpr int kOutStages = 2;
+constexpr int kOutStages = SIMSTEP_GEMM_OUT_STAGES;
 
 template <int CG>
 struct GemmShape {
