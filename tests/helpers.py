@@ -116,3 +116,42 @@ def perturbed_poses(E, seed, clip=None, t_max=None, with_origin=True):
                 p[o] += rng.normal(0, 0.2)
         pose[e], vel[e] = p, v
     return pose, vel, t, origin
+
+
+def trainstep_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trainstep_golden.npz"))
+
+
+def trainstep_paths(g):
+    """The rollout of tests/golden/trainstep_golden.npz as the list of path dicts train_step works on."""
+    paths = []
+    for k in range(len(g["length"])):
+        n = int(g["length"][k])
+        paths.append(dict(observations=g["observations"][k, :n].copy(), next_observations=g["next_observations"][k, :n].copy(),
+                          actions=g["actions"][k, :n].copy(), rewards=np.zeros(n)))
+    return paths
+
+
+def reward_replacement(paths, reward_func, ensemble):
+    """BatchREINFORCE.train_step's reward replacement (mjrl/mjrl/algos/batch_reinforce.py:103-169, cost input 'ss',
+    no GAIL), written against the objects' public methods only, so the same lines run over the reference classes,
+    over the oracle and over this package's shims.  Mutates paths[i]['rewards']; returns the infos dict."""
+    infos = {"int": [], "ext": [], "reward": [], "ep_len": []}
+    cost_input = np.concatenate([np.concatenate([t["observations"], t["next_observations"]], axis=1) for t in paths], axis=0)
+    infos["mb_mmd"] = reward_func.fit_cost(torch.from_numpy(cost_input).float())                    # BR:113
+    for traj in paths:
+        states = torch.from_numpy(traj["observations"]).float()
+        next_states = torch.from_numpy(traj["next_observations"]).float()
+        actions = torch.from_numpy(traj["actions"]).float()
+        bonus_cost, cost_info = reward_func.get_bonus_costs(states, actions, ensemble, next_states=next_states)  # BR:128
+        bonus_cost = bonus_cost[:, 0]
+        intrinsic_sum = -np.sum(cost_info["bonus"][:, 0].numpy())                                   # BR:135-136
+        extrinsic_sum = -np.sum(cost_info["ipm"][:, 0].numpy())
+        infos["int"].append(intrinsic_sum)
+        infos["ext"].append(extrinsic_sum)
+        infos["reward"].append(extrinsic_sum + intrinsic_sum)
+        infos["ep_len"].append(len(traj["rewards"]))
+        traj["rewards"] = -1.0 * bonus_cost.cpu().numpy()                                           # BR:144
+    infos["bonus_mmd"] = float(np.concatenate([-1.0 * t["rewards"] for t in paths], axis=0).mean()
+                               - float(reward_func.get_expert_cost()))                               # BR:169
+    return infos

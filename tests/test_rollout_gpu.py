@@ -376,3 +376,38 @@ def test_device_rollout_matches_the_reference_sampler():
         if first != n:
             t = min(n, first or n) - 1
             assert collision_margin(g["next_observations"][k, t][None])[0] < 1e-3, (k, first, n)
+
+
+def test_reward_replacement_matches_the_reference_train_step():
+    """The drop-in claim of SURVEY.md section 8(b) on the reference's own numbers: BatchREINFORCE.train_step's reward
+    replacement (batch_reinforce.py:103-169) — the lines in tests.helpers.reward_replacement — run over THIS package's
+    RBFLinearCost and DynamicsEnsemble must give what the reference's train_step gave over the reference classes
+    (tests/golden/trainstep_golden.npz): threshold, fitted w, mb_mmd, bonus_mmd, per-trajectory int / ext sums and
+    every replaced reward, to 1e-3 of each quantity's scale."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, RBFLinearCost
+    g = H.trainstep_golden()
+    S, A = 226, 28
+    N, hidden = int(g["N"]), [int(h) for h in g["hidden"]]
+    ds = AmpDataset(*H.synth_dataset(int(g["dataset_rows"]), S, A, int(g["dataset_seed"])))
+    ens = DynamicsEnsemble(S, A, ds, None, num_models=N, hidden_sizes=hidden, dense_connect=True, transform=True,
+                           base_seed=int(g["base_seed"]))
+    ens.compute_threshold()
+    assert abs(ens.threshold - float(g["threshold"])) < 1e-3 * float(g["threshold"])
+    cost = RBFLinearCost(torch.from_numpy(g["expert"]), feature_dim=int(g["feature_dim"]), input_type="ss",
+                         bw_quantile=float(g["bw_quantile"]), lambda_b=float(g["lambda_b"]), seed=int(g["cost_seed"]))
+    assert abs(cost.bw - float(g["cost_bw"])) < 1e-6 * float(g["cost_bw"])
+    paths = H.trainstep_paths(g)
+    infos = H.reward_replacement(paths, cost, ens)
+    w_scale = float(np.abs(g["cost_w"]).max())
+    assert float(np.abs(cost.w.cpu().numpy() - g["cost_w"]).max()) < 1e-3 * w_scale
+    assert abs(float(infos["mb_mmd"]) - float(g["mb_mmd"])) < 1e-3 * float(g["mb_mmd"])
+    r_scale = float(np.abs(g["rewards"]).max())
+    for k, p in enumerate(paths):
+        n = len(p["rewards"])
+        assert p["rewards"].shape == (n,)
+        assert float(np.abs(p["rewards"] - g["rewards"][k, :n]).max()) < 1e-3 * r_scale, k
+    assert infos["ep_len"] == list(g["info_ep_len"])
+    for key in ("int", "ext", "reward"):
+        ref = g[f"info_{key}"]
+        assert float(np.abs(np.asarray(infos[key]) - ref).max()) < 1e-3 * max(float(np.abs(ref).max()), r_scale), key
+    assert abs(infos["bonus_mmd"] - float(g["bonus_mmd"])) < 1e-3 * max(abs(float(g["bonus_mmd"])), r_scale)

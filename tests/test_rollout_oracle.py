@@ -92,3 +92,54 @@ def test_rollout_loop_matches_the_reference_sampler():
         np.testing.assert_allclose(res["observations"][:n, k], g["observations"][k, :n], atol=2e-5)
         np.testing.assert_allclose(res["next_observations"][:n, k], g["next_observations"][k, :n], atol=2e-5)
     assert sorted(set(int(x) for x in g["length"])) != [horizon]   # some trajectories ended on a fall
+
+
+# ---- BatchREINFORCE.train_step's reward replacement against the reference's own run (trainstep_golden.npz) -----
+
+class _OracleEnsemble:
+    def __init__(self, ws, bs, tf, threshold):
+        self.ws, self.bs, self.tf, self.threshold = ws, bs, tf, threshold
+
+    def get_action_discrepancy(self, s, a):   # DYN:154-165
+        from oracle import milo_oracle as mo
+        return mo.discrepancy_from_preds(mo.ensemble_forward(self.ws, self.bs, self.tf, s, a))
+
+
+def test_reward_replacement_matches_the_reference_train_step():
+    """tests/golden/make_trainstep_golden.py ran the reference's BatchREINFORCE.train_step (fit_cost on the rollout,
+    per-trajectory get_bonus_costs, reward = -cost, int / ext / ep_len sums, mb_mmd, bonus_mmd, then compute_returns
+    and compute_advantages) over the reference RBFLinearCost and DynamicsEnsemble.  The same lines
+    (tests.helpers.reward_replacement) over the oracle objects must reproduce every number."""
+    from oracle import milo_oracle as mo
+    from tests import helpers as H
+    g = H.trainstep_golden()
+    N, hidden = int(g["N"]), [int(h) for h in g["hidden"]]
+    s, a, s2 = H.synth_dataset(int(g["dataset_rows"]), 226, 28, int(g["dataset_seed"]))
+    ws, bs = mo.init_ensemble(226, 28, hidden, N, base_seed=int(g["base_seed"]), dense_connect=True)
+    tf = mo.get_transformations(s, a, s2)
+    threshold = mo.compute_threshold(ws, bs, tf, s, a, batch_size=256)   # over the offline dataset, DYN:145-152
+    assert abs(threshold - float(g["threshold"])) < 1e-6 * float(g["threshold"])
+
+    class Cost(mo.RffCostOracle):
+        def get_bonus_costs(self, states, actions, ensemble, next_states=None):   # the reference signature (LC:111)
+            return mo.RffCostOracle.get_bonus_costs(self, states, actions, ensemble.get_action_discrepancy(states, actions),
+                                                    ensemble.threshold, next_states=next_states)
+
+    cost = Cost(torch.from_numpy(g["expert"]), feature_dim=int(g["feature_dim"]), input_type="ss",
+                bw_quantile=float(g["bw_quantile"]), lambda_b=float(g["lambda_b"]), seed=int(g["cost_seed"]))
+    assert cost.bw == float(g["cost_bw"])
+    paths = H.trainstep_paths(g)
+    infos = H.reward_replacement(paths, cost, _OracleEnsemble(ws, bs, tf, float(g["threshold"])))
+    np.testing.assert_allclose(cost.w.numpy(), g["cost_w"], atol=1e-6)
+    assert abs(infos["mb_mmd"] - float(g["mb_mmd"])) < 1e-6
+    assert abs(infos["bonus_mmd"] - float(g["bonus_mmd"])) < 1e-6
+    assert infos["ep_len"] == list(g["info_ep_len"])
+    for key in ("int", "ext", "reward"):
+        np.testing.assert_allclose(infos[key], g[f"info_{key}"], atol=1e-5)
+    for k, p in enumerate(paths):
+        n = len(p["rewards"])
+        np.testing.assert_allclose(p["rewards"], g["rewards"][k, :n], atol=1e-6)
+        np.testing.assert_allclose(ro.discount_sum(p["rewards"], float(g["gamma"])), g["returns"][k, :n], atol=1e-6)
+        adv = ro.gae_advantages(p["rewards"], np.zeros(n), True, float(g["gamma"]), float(g["gae_lambda"]))
+        np.testing.assert_allclose(adv, g["advantages"][k, :n], atol=1e-6)
+    assert g["rewards"].min() < 0 < g["rewards"].max()   # both the pessimism bonus and the IPM term are active
