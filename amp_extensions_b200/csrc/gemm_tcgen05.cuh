@@ -30,6 +30,13 @@ namespace simstep {
 #ifndef SIMSTEP_GEMM_STAGES_CG2
 #define SIMSTEP_GEMM_STAGES_CG2 5
 #endif
+// B-resident small-K mode: when a tile's whole K fits the ring (kb_total <= kStages) the ring is shortened to kb_total
+// stages, so stage s always holds k-block s and the weight half of a stage stays valid for as long as consecutive tiles
+// of this CTA pair share their (group, n-tile) - which the tile order gives (tile_step and n_tiles are both even, the
+// group changes every m_tiles * n_tiles tiles); only the activation half is then reloaded per tile
+#ifndef SIMSTEP_GEMM_B_RESIDENT
+#define SIMSTEP_GEMM_B_RESIDENT 0
+#endif
 // staging tiles of the TMA-store epilogue (16 KB each); kOutStages - 1 stores may still be reading shared memory
 #ifndef SIMSTEP_GEMM_OUT_STAGES
 #define SIMSTEP_GEMM_OUT_STAGES 2
@@ -238,11 +245,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
   const int kb_total = args.kb_x + args.kb_h;
   const int tile0 = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
+  const bool b_resident = SIMSTEP_GEMM_B_RESIDENT != 0 && kb_total <= kStages;
+  const int ring = b_resident ? kb_total : kStages;
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair; the leader arms the barrier for both) =====
     int stage = 0;
     uint32_t phase = 0;
+    int held_b = -1;  // (group, n-tile) whose weight k-blocks sit in the stages' B halves (B-resident mode)
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_tile = tile % args.n_tiles;
       const int t2 = tile / args.n_tiles;
@@ -252,21 +262,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       const int row_ax = g * args.ax_rows_per_group + m_row;
       const int row_ah = g * args.a_rows_per_group + m_row;
       const int row_b = g * args.b_rows_per_group + n_tile * kBlockN + int(cta_rank) * S::kBRows;
+      const int this_b = g * args.n_tiles + n_tile;
+      const bool load_b = !b_resident || this_b != held_b;
+      held_b = this_b;
       for (int kb = 0; kb < kb_total; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CG);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (load_b ? S::kStageBytes : kABytes) * CG);
           if (kb < args.kb_x) {
             ptx::tma_load_2d<CG>(sa, &tmap_ax, &full_bar[stage], kb * BK, row_ax);
           } else {
             ptx::tma_load_2d<CG>(sa, &tmap_ah, &full_bar[stage], (args.kb_h0 + kb - args.kb_x) * BK, row_ah);
           }
-          ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+          if (load_b) ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == ring) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -298,7 +311,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
             if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == ring) { stage = 0; phase ^= 1; }
         }
       }
     }
