@@ -207,7 +207,50 @@ def main():
         vstates.append(st)
     out.update(vel_states=np.array(vstates), vel_done_enabled=np.array(vflags), vel_done_default=np.array(vdefault))
 
+    # ---- D: the controller-file flags the reference honours (sim_env.py:92-96, 181-186, 224-231, 264-267), set on
+    # the constructed object the way another controller file would set them
+    rng = np.random.default_rng(33)
+    flag_sets = [(1, 0), (0, 1), (1, 1)]
+    var_states = np.zeros((len(flag_sets), 48, S))
+    var_flags = np.zeros((len(flag_sets), 48), dtype=bool)
+    for k, (aw, wrp) in enumerate(flag_sets):
+        env.record_all_world, env.record_world_root_pos = bool(aw), bool(wrp)
+        for i in range(48):
+            st = base.copy()
+            st[0] += rng.normal(0, 0.05)
+            world_bodies = range(15) if aw else [0]     # bodies whose height this layout stores in world coordinates
+            for bdy in world_bodies:
+                st[9 * bdy + 2] += st[0]
+            j = int(rng.integers(0, 13))                 # one fall body near its threshold, on either side
+            body = int(env.fall_contact_bodies[j])
+            off = int(env.fall_contact_bodies_offset[j])
+            radius = 0.5 * env.fall_contact_bodies_params[j][0]
+            eps = float(rng.choice([-1e-3, -2e-6, 2e-6, 1e-3]))
+            cap = 0.0
+            if env.fall_contact_bodies_shapes[j] == "capsule":
+                cap = abs(0.5 * env.fall_contact_bodies_params[j][1] * st[off + 3 + 1])
+            y_world = radius + 1e-4 + eps + cap          # the lower cap centre (or the sphere centre) on the target
+            st[off + 1] = y_world if (aw or (wrp and j == 0)) else y_world - st[0]
+            env.set_observation(st.copy())
+            var_states[k, i] = st
+            var_flags[k, i] = bool(env.check_collision())
+    env.record_all_world, env.record_world_root_pos = False, False
+    envv.record_vel_as_pos = True                        # velocities stored as per-step displacements: v = ob / dt
+    vp_states, vp_flags = [], []
+    for idx, val in ((136, 3.3), (136, 3.34), (225, -3.4), (200, 3.333), (150, 50.0)):
+        st = base.copy()
+        st[136:] *= envv.sampling_rate                   # the base state in that convention
+        st[idx] = val
+        envv.set_observation(st.copy())
+        envv.num_steps = 1
+        vp_flags.append(bool(envv.is_done()))
+        vp_states.append(st)
+    out.update(variant_states=var_states, variant_flag_sets=np.array(flag_sets), variant_collided=var_flags,
+               velpos_states=np.array(vp_states), velpos_done=np.array(vp_flags),
+               velpos_divisor=np.float64(envv.sampling_rate))
+
     np.savez_compressed(OUT, **out)
+    print("variants collided:", var_flags.sum(1), "velpos:", vp_flags, envv.sampling_rate)
     print(OUT, os.path.getsize(OUT), "bytes; done per episode:", dones.argmax(1), "collided cases:", int(np.sum(flags)),
           "of", len(flags), "; velocity:", vflags, vdefault)
 

@@ -170,6 +170,18 @@ def test_simenv_velocity_check_matches_the_reference():
     assert g["vel_done_enabled"].any() and not g["vel_done_default"].any()
 
 
+def test_simenv_controller_flags_match_the_reference():
+    """RecordAllWorld / RecordWorldRootPos (sim_env.py:181-186, 224-231) and RecordVelAsPos (sim_env.py:264-267) set
+    on the constructed reference object; 48 states per flag set with one fall body 2e-6 / 1e-3 off its threshold."""
+    g = _simenv_golden()
+    for k, (aw, wrp) in enumerate(g["variant_flag_sets"]):
+        got = mo.simenv_collided(g["variant_states"][k], record_all_world=bool(aw), record_world_root_pos=bool(wrp))
+        assert (got == g["variant_collided"][k]).all(), (aw, wrp)
+        assert 0 < g["variant_collided"][k].sum() < 48
+    got = mo.simenv_velocity_exploded(g["velpos_states"], divisor=float(g["velpos_divisor"]))
+    assert (got == g["velpos_done"]).all() and g["velpos_done"].any() and not g["velpos_done"].all()
+
+
 def test_simenv_episodes_match_the_reference():
     """reset -> 10 steps, five episodes, horizon 8: observations, step counter, done flags and the member
     round-robin of the reference SimEnv, replayed by the oracle (ensemble rebuilt from the seed and checked

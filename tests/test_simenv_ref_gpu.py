@@ -59,7 +59,7 @@ def test_plugin_episodes_match_the_reference_simenv():
     print(f"worst per-step state error {worst:.2e}")
 
 
-def zero_delta_engine(enable_velocity_check):
+def zero_delta_engine(enable_velocity_check, **term_kw):
     """An ensemble that predicts delta = 0, so the step's termination test sees exactly the state it was given."""
     from amp_extensions_b200.engine import Engine, HumanoidTermination
     hidden = [32, 32]
@@ -69,7 +69,7 @@ def zero_delta_engine(enable_velocity_check):
     tf = (torch.zeros(S), torch.ones(S), torch.zeros(A), torch.ones(A), torch.zeros(S), torch.ones(S))
     eng = Engine(S, A, 2, hidden, dense_connect=True, activation="relu", transform=True, precision="fp16")
     eng.load_ensemble(ws, bs, tf)
-    eng.set_termination(HumanoidTermination(horizon=300, enable_velocity_check=enable_velocity_check))
+    eng.set_termination(HumanoidTermination(horizon=300, enable_velocity_check=enable_velocity_check, **term_kw))
     return eng
 
 
@@ -91,3 +91,13 @@ def test_contact_thresholds_match_the_reference_simenv():
 def test_velocity_check_matches_the_reference_simenv():
     assert (run_done(zero_delta_engine(True), GOLD["vel_states"]) == GOLD["vel_done_enabled"]).all()
     assert (run_done(zero_delta_engine(False), GOLD["vel_states"]) == GOLD["vel_done_default"]).all()
+
+
+def test_controller_flags_match_the_reference_simenv():
+    """RecordAllWorld / RecordWorldRootPos / RecordVelAsPos as the reference SimEnv honours them."""
+    for k, (aw, wrp) in enumerate(GOLD["variant_flag_sets"]):
+        eng = zero_delta_engine(False, record_all_world=bool(aw), record_world_root_pos=bool(wrp))
+        done = run_done(eng, GOLD["variant_states"][k])
+        assert (done == GOLD["variant_collided"][k]).all(), (aw, wrp, np.nonzero(done != GOLD["variant_collided"][k]))
+    eng = zero_delta_engine(True, vel_divisor=float(GOLD["velpos_divisor"]))
+    assert (run_done(eng, GOLD["velpos_states"]) == GOLD["velpos_done"]).all()
