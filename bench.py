@@ -192,9 +192,18 @@ def time_cpu_reference(batch, min_seconds, max_reps, warmup=1):
         cpu_reference_step(ctx, s, a, member, steps)
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
+    # the reference's ACTUAL mode steps one env per call (sim_env.py:155-157 unsqueezes a single state); reported
+    # beside the batched figure, which is the generous one
+    one = []
+    for i in range(60):
+        t0 = time.perf_counter()
+        cpu_reference_step(ctx, s[i:i + 1], a[i:i + 1], member[i:i + 1], steps[i:i + 1])
+        one.append(time.perf_counter() - t0)
     return dict(value=batch / med, unit=UNIT, cores=threads, kind="port",
                 sample=f"{len(times)} x {batch} env-steps (median), oracle port of the reference's PyTorch CPU path, "
-                       f"torch {torch.__version__} with {threads} intra-op threads"), med
+                       f"torch {torch.__version__} with {threads} intra-op threads",
+                per_env_mode={"value": 1.0 / statistics.median(one[10:]), "unit": UNIT,
+                              "sample": "50 single-env steps (median): the batch the reference's SimEnv.step uses"}), med
 
 
 def run_reference(args):
