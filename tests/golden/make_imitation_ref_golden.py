@@ -110,6 +110,38 @@ def main():
             lib.dmref_record_state(P(pose[e].copy()), P(vel[e].copy()), aw, wrp, wrr, vs, P(states[k, e]))
     out.update(state_flags=np.array(flag_sets), state_features=states)
 
+    # ---- two more reference clips: a non-looping one (kick: times clamp, velocity 0 past the end) and a short cycle
+    import json
+    for name in ("humanoid3d_kick", "humanoid3d_run"):
+        mfile = os.path.join(rb.DATA, "motions", name + ".txt")
+        with open(mfile) as f:
+            mj = json.load(f)
+        raw = np.array(mj["Frames"], dtype=np.float64)
+        loop = mj.get("Loop", "none")
+        assert lib.dmref_init(rb.CHAR_FILE.encode(), mfile.encode()) == 0
+        c2 = io.Clip(raw, io.HUMANOID3D, loop)
+        nf2 = lib.dmref_num_frames()
+        fr2, ve2, ti2 = np.zeros((nf2, dof)), np.zeros((nf2, dof)), np.zeros(nf2)
+        lib.dmref_clip_table(P(fr2), P(ve2), P(ti2))
+        dur = lib.dmref_duration()
+        r3 = np.random.default_rng(len(name))
+        ts2 = f32(np.concatenate([r3.uniform(-0.5, 2.5 * dur, 40), [0.0, dur, 0.5 * dur, dur + 0.25]]))
+        org2 = f32(r3.normal(0, 0.3, (ts2.size, 3)))
+        kp2, kv2 = np.zeros((ts2.size, dof)), np.zeros((ts2.size, dof))
+        for e in range(ts2.size):
+            lib.dmref_kin_pose_vel(float(ts2[e]), P(org2[e].copy()), P(kp2[e]), P(kv2[e]))
+        E2 = 48
+        pose2, vel2, t2, _ = H.perturbed_poses(E2, seed=len(name), clip=c2, t_max=2.0 * dur, with_origin=False)
+        pose2, vel2, t2 = f32(pose2), f32(vel2), f32(t2)
+        r2, terms2 = np.zeros(E2), np.zeros((E2, 5))
+        lib.dmref_reward_batch(E2, P(pose2), P(vel2), P(t2), None, P(r2), P(terms2))
+        out.update({f"{name}/raw": raw, f"{name}/loop": np.array(loop), f"{name}/frames": fr2, f"{name}/vels": ve2,
+                    f"{name}/times": ti2, f"{name}/duration": np.float64(dur), f"{name}/sample_t": ts2,
+                    f"{name}/sample_origin": org2, f"{name}/sample_pose": kp2, f"{name}/sample_vel": kv2,
+                    f"{name}/pose": pose2, f"{name}/vel": vel2, f"{name}/t": t2, f"{name}/reward": r2,
+                    f"{name}/terms": terms2})
+    assert lib.dmref_init(rb.CHAR_FILE.encode(), rb.MOTION_FILE.encode()) == 0   # back to the spin kick
+
     path = os.path.join(ROOT, "tests", "golden", "imitation_ref_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes;", "reward range", out["plain_reward"].min(), out["far_reward"].min(),

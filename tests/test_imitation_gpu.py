@@ -239,3 +239,40 @@ def test_record_state_matches_reference_golden(setup):
         np.testing.assert_allclose(st[:, :136], ref[:, :136], rtol=0, atol=5e-5)
         vscale = float(np.abs(ref[:, 136:]).mean())
         np.testing.assert_allclose(st[:, 136:], ref[:, 136:], rtol=0, atol=REL * max(vscale, 1e-3))
+
+
+@pytest.mark.parametrize("name", ["humanoid3d_kick", "humanoid3d_run"])
+def test_other_clips_match_reference_golden(name):
+    """A non-looping reference clip (kick: clamped index, zero velocity past the end, no cycle offset) and a short
+    cycle (run), loaded by the product's own MotionClip.from_raw and evaluated by both reward kernels, against the
+    compiled reference (tests/golden/imitation_ref_golden.npz)."""
+    import os
+    from amp_extensions_b200 import ImitationReward
+    from amp_extensions_b200.character import humanoid3d
+    from amp_extensions_b200.motion import MotionClip
+    g = _ref_golden()
+    raw, loop = g[f"{name}/raw"], str(g[f"{name}/loop"])
+    dur = float(g[f"{name}/duration"])
+    for generic in ("0", "1"):
+        old = os.environ.get("SIMSTEP_IMIT_GENERIC")
+        os.environ["SIMSTEP_IMIT_GENERIC"] = generic
+        try:
+            ch = humanoid3d()
+            imit = ImitationReward(character=ch, clip=MotionClip.from_raw(raw, ch, loop))
+        finally:
+            if old is None:
+                os.environ.pop("SIMSTEP_IMIT_GENERIC", None)
+            else:
+                os.environ["SIMSTEP_IMIT_GENERIC"] = old
+        t, org = g[f"{name}/sample_t"], g[f"{name}/sample_origin"]
+        pose, vel = imit.sample(torch.from_numpy(t).float(), torch.from_numpy(org).float())
+        # away from frame-0 / end-of-clip boundaries, where fp32 time may fall on the other side
+        phase = np.mod(t, dur)
+        ok = (np.minimum(phase, dur - phase) > 1e-4) & (np.abs(t) > 1e-4)
+        assert ok.sum() >= t.size - 4
+        np.testing.assert_allclose(pose.cpu().numpy()[ok], g[f"{name}/sample_pose"][ok], atol=2e-5)
+        np.testing.assert_allclose(vel.cpu().numpy()[ok], g[f"{name}/sample_vel"][ok], atol=2e-3, rtol=1e-4)
+        r, terms = imit.reward(torch.from_numpy(g[f"{name}/pose"]).float(), torch.from_numpy(g[f"{name}/vel"]).float(),
+                               torch.from_numpy(g[f"{name}/t"]).float(), None, want_terms=True)
+        close(terms.cpu().numpy(), g[f"{name}/terms"])
+        close(r.cpu().numpy(), g[f"{name}/reward"])

@@ -167,3 +167,37 @@ def test_live_quaternion_helpers(lib):
         np.testing.assert_allclose(io.lerp_poses(CH, a, b, lerp), out, atol=1e-12)
         lib.dmref_calc_vel(P(a), P(b), 1.0 / 60, P(out))
         np.testing.assert_allclose(io.calc_vel(CH, a, b, 1.0 / 60), out, atol=1e-9)
+
+
+# ---- other clips of the reference: a non-looping motion and a short cycle -----------------------------------------
+
+EXTRA_CLIPS = ["humanoid3d_kick", "humanoid3d_run"]
+
+
+@pytest.mark.parametrize("name", EXTRA_CLIPS)
+def test_other_clips_match_the_reference(name):
+    """cMotion::Load / CalcFrame / CalcFrameVel with Loop "none" (index clamp, no cycle offset) and "wrap", and the
+    reward against those clips; the restatement AND the product's host-side loader (motion.MotionClip.from_raw, the
+    tables it uploads) against what the compiled reference holds after loading the same file."""
+    from amp_extensions_b200.character import humanoid3d
+    from amp_extensions_b200.motion import MotionClip
+    raw, loop = GOLD[f"{name}/raw"], str(GOLD[f"{name}/loop"])
+    assert loop == ("none" if name == "humanoid3d_kick" else "wrap")
+    c = io.Clip(raw, CH, loop)
+    mc = MotionClip.from_raw(raw, humanoid3d(), loop)
+    for frames, vels, times, dur in ((c.frames, c.vels, c.times, c.duration),
+                                     (mc.frames, mc.frame_vels, mc.frame_times, mc.duration)):
+        np.testing.assert_allclose(times, GOLD[f"{name}/times"], atol=1e-14)
+        np.testing.assert_allclose(frames, GOLD[f"{name}/frames"], atol=1e-13)
+        np.testing.assert_allclose(vels, GOLD[f"{name}/vels"], atol=1e-10)
+        assert dur == pytest.approx(float(GOLD[f"{name}/duration"]), abs=1e-14)
+    assert mc.loop_wrap == (loop == "wrap")
+    np.testing.assert_allclose(mc.cycle_delta, c.cycle_delta, atol=1e-14)
+    t, org = GOLD[f"{name}/sample_t"], GOLD[f"{name}/sample_origin"]
+    for e in range(t.size):
+        np.testing.assert_allclose(c.kin_pose(float(t[e]), org[e]), GOLD[f"{name}/sample_pose"][e], atol=ATOL)
+        np.testing.assert_allclose(c.kin_vel(float(t[e])), GOLD[f"{name}/sample_vel"][e], atol=ATOL)
+    n = 24
+    r, terms = io.imitation_reward_batch(CH, c, GOLD[f"{name}/pose"][:n], GOLD[f"{name}/vel"][:n], GOLD[f"{name}/t"][:n])
+    np.testing.assert_allclose(terms, GOLD[f"{name}/terms"][:n], atol=ATOL)
+    np.testing.assert_allclose(r, GOLD[f"{name}/reward"][:n], atol=ATOL)
