@@ -22,6 +22,8 @@ CHAR_FILE = os.path.join(DATA, "characters", "humanoid3d.txt")
 MOTION_FILE = os.path.join(DATA, "motions", "humanoid3d_spinkick.txt")
 OUT_DIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "libdmref.so")
+# the stand-in headers, unless a real Eigen 3.3.7 tree is pointed to (none exists in the build image)
+EIGEN_INCLUDE = os.environ.get("EIGEN3_INCLUDE_DIR") or os.path.join(HERE, "eigen_shim")
 SHIPPED_CHAR = os.path.join(OUT_DIR, "data", "humanoid3d.txt")
 SHIPPED_MOTION = os.path.join(OUT_DIR, "data", "humanoid3d_spinkick.txt")
 
@@ -52,8 +54,8 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(OUT_DIR, os.path.relpath(s, CORE if s.startswith(CORE) else HERE).replace(os.sep, "_")[:-4] + ".o")
         objs.append(o)
-        cmd = ["g++", "-std=c++14", "-O2", "-fPIC", "-w", "-ffp-contract=off", "-I", os.path.join(HERE, "eigen_shim"),
-               "-I", CORE, "-c", s, "-o", o]
+        cmd = ["g++", "-std=c++14", "-O2", "-fPIC", "-w", "-ffp-contract=off", "-I", EIGEN_INCLUDE, "-I", CORE, "-c", s,
+               "-o", o]
         if verbose:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True)))
