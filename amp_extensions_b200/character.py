@@ -40,9 +40,13 @@ class Character:
         self.param_size = sizes
         self.param_offset = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
         self.dof = int(sizes.sum())
+        self.body_rotation_ignored = False
 
     @classmethod
-    def from_json(cls, path_or_dict):
+    def from_json(cls, path_or_dict, ignore_body_rotation=False):
+        """ignore_body_rotation: accept bodies with attach rotations (e.g. the reference's dog3d neck and tail).  They
+        turn the body's own frame, not its centre of mass (KinTree.cpp:1156-1166), so the imitation reward and the clip
+        sampling are unaffected; the env-state features (record_state) would be, and refuse such a character."""
         d = path_or_dict
         if not isinstance(d, dict):
             with open(d) as f:
@@ -52,10 +56,11 @@ class Character:
         for j in joints:
             if any(abs(j.get(k, 0.0)) > 0 for k in ("AttachThetaX", "AttachThetaY", "AttachThetaZ")):
                 raise NotImplementedError("joint attach rotations are not supported")
-        for b in bodies.values():
-            if any(abs(b.get(k, 0.0)) > 0 for k in ("AttachThetaX", "AttachThetaY", "AttachThetaZ")):
-                raise NotImplementedError("body attach rotations are not supported")
-        return cls(
+        rotated = any(abs(b.get(k, 0.0)) > 0 for b in bodies.values() for k in ("AttachThetaX", "AttachThetaY", "AttachThetaZ"))
+        if rotated and not ignore_body_rotation:
+            raise NotImplementedError("body attach rotations are not supported (pass ignore_body_rotation=True for the "
+                                      "imitation reward, which does not depend on them)")
+        ch = cls(
             names=[j["Name"] for j in joints],
             joint_type=[_TYPE_IDS[j["Type"]] for j in joints],
             parent=[j["Parent"] for j in joints],
@@ -65,6 +70,8 @@ class Character:
             body_mass=[float(bodies[j["ID"]]["Mass"]) if j["ID"] in bodies else 0.0 for j in joints],
             body_attach=[[bodies[j["ID"]]["AttachX"], bodies[j["ID"]]["AttachY"], bodies[j["ID"]]["AttachZ"]]
                          if j["ID"] in bodies else [0.0, 0.0, 0.0] for j in joints])
+        ch.body_rotation_ignored = rotated
+        return ch
 
     def joint_weights(self):
         """cSceneImitate::CalcJointWeights (SceneImitate.cpp:300-312): DiffWeight / sum |DiffWeight|."""

@@ -38,6 +38,8 @@ class ImitationReward:
     def record_state(self, pose, vel, **flags):
         """The env's state vector for generalized poses / velocities (CtController.cpp:378-495), e.g. 226 numbers
         for humanoid3d; flags as in Engine.record_state."""
+        if getattr(self.character, "body_rotation_ignored", False):
+            raise NotImplementedError("state features need the body attach rotations this character was loaded without")
         return self.engine.record_state(pose, vel, **flags)
 
     def reset_states(self, kin_time, kin_origin=None, **flags):

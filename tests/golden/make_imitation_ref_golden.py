@@ -140,6 +140,45 @@ def main():
                     f"{name}/sample_origin": org2, f"{name}/sample_pose": kp2, f"{name}/sample_vel": kv2,
                     f"{name}/pose": pose2, f"{name}/vel": vel2, f"{name}/t": t2, f"{name}/reward": r2,
                     f"{name}/terms": terms2})
+    # ---- a different skeleton through the same code: the reference's dog (23 joints, 83 dof, four end effectors)
+    cfile = os.path.join(rb.DATA, "characters", "dog3d.txt")
+    mfile = os.path.join(rb.DATA, "motions", "dog3d_trot.txt")
+    with open(cfile) as f:
+        cj = json.load(f)
+    with open(mfile) as f:
+        mj = json.load(f)
+    assert lib.dmref_init(cfile.encode(), mfile.encode()) == 0
+    dog = H.character_dict_from_json(cj)
+    ddof, dnj, dnf = lib.dmref_num_dof(), lib.dmref_num_joints(), lib.dmref_num_frames()
+    raw = np.array(mj["Frames"], dtype=np.float64)
+    loop = mj.get("Loop", "none")
+    cd = io.Clip(raw, dog, loop)
+    frd, ved, tid = np.zeros((dnf, ddof)), np.zeros((dnf, ddof)), np.zeros(dnf)
+    lib.dmref_clip_table(P(frd), P(ved), P(tid))
+    wd = np.zeros(dnj)
+    lib.dmref_joint_weights(P(wd))
+    dur = lib.dmref_duration()
+    r4 = np.random.default_rng(44)
+    tsd = f32(r4.uniform(-0.3, 3.0 * dur, 40))
+    orgd = f32(r4.normal(0, 0.3, (tsd.size, 3)))
+    kpd, kvd = np.zeros((tsd.size, ddof)), np.zeros((tsd.size, ddof))
+    for e in range(tsd.size):
+        lib.dmref_kin_pose_vel(float(tsd[e]), P(orgd[e].copy()), P(kpd[e]), P(kvd[e]))
+    Ed = 48
+    posed, veld, td, _ = H.perturbed_poses(Ed, seed=45, clip=cd, t_max=2.0 * dur, with_origin=False, ch=dog)
+    posed, veld, td = f32(posed), f32(veld), f32(td)
+    rd, termsd = np.zeros(Ed), np.zeros((Ed, 5))
+    lib.dmref_reward_batch(Ed, P(posed), P(veld), P(td), None, P(rd), P(termsd))
+    comd, comvd = np.zeros((8, 3)), np.zeros((8, 3))
+    for e in range(8):
+        lib.dmref_com(P(posed[e].copy()), P(veld[e].copy()), P(comd[e]), P(comvd[e]))
+    out.update({"dog/character_json": np.array(json.dumps({"Skeleton": cj["Skeleton"], "BodyDefs": cj["BodyDefs"]})),
+                "dog/raw": raw, "dog/loop": np.array(loop), "dog/frames": frd, "dog/vels": ved, "dog/times": tid,
+                "dog/duration": np.float64(dur), "dog/joint_weights": wd, "dog/sample_t": tsd, "dog/sample_origin": orgd,
+                "dog/sample_pose": kpd, "dog/sample_vel": kvd, "dog/pose": posed, "dog/vel": veld, "dog/t": td,
+                "dog/reward": rd, "dog/terms": termsd, "dog/com": comd, "dog/com_vel": comvd})
+    print("dog:", ddof, dnj, dnf, dur, loop, "reward range", rd.min(), rd.max())
+
     assert lib.dmref_init(rb.CHAR_FILE.encode(), rb.MOTION_FILE.encode()) == 0   # back to the spin kick
 
     path = os.path.join(ROOT, "tests", "golden", "imitation_ref_golden.npz")

@@ -87,23 +87,25 @@ def spinkick_raw():
     return z["frames_raw"]
 
 
-def perturbed_poses(E, seed, clip=None, t_max=None, with_origin=True):
+def perturbed_poses(E, seed, clip=None, t_max=None, with_origin=True, ch=None):
     """SURVEY.md section 8d generator: pose = clip(t) perturbed (root pos += N(0,.05), every quaternion
     <- exp(N(0,.2) axis) q, revolute += N(0,.2)), vel = clipvel(t) + N(0,.5), t ~ U(0, t_max)."""
     from oracle import imitation_oracle as io
-    clip = clip or io.Clip(spinkick_raw(), io.HUMANOID3D, "wrap")
+    ch = ch or io.HUMANOID3D
+    clip = clip or io.Clip(spinkick_raw(), ch, "wrap")
     rng = np.random.default_rng(seed)
-    offs, _ = io.param_layout(io.HUMANOID3D)
+    offs, sizes = io.param_layout(ch)
+    dof = int(sum(sizes))
     t = rng.uniform(0, t_max if t_max is not None else clip.duration, E)
     origin = rng.normal(0, 0.3, (E, 3)) if with_origin else None
-    pose, vel = np.zeros((E, 43)), np.zeros((E, 43))
+    pose, vel = np.zeros((E, dof)), np.zeros((E, dof))
     for e in range(E):
         p = clip.kin_pose(t[e], origin[e] if with_origin else (0, 0, 0))
         if with_origin:
             p[1] -= origin[e, 1]  # the simulated character stands on the real ground
-        v = clip.kin_vel(t[e]) + rng.normal(0, 0.5, 43)
+        v = clip.kin_vel(t[e]) + rng.normal(0, 0.5, dof)
         p[0:3] += rng.normal(0, 0.05, 3)
-        for j, jt in enumerate(io.HUMANOID3D["joint_type"]):
+        for j, jt in enumerate(ch["joint_type"]):
             o = offs[j] + (3 if jt == io.ROOT else 0)
             if jt in (io.ROOT, io.SPHERICAL):
                 ax = rng.normal(0, 1, 3)
@@ -155,3 +157,21 @@ def reward_replacement(paths, reward_func, ensemble):
     infos["bonus_mmd"] = float(np.concatenate([-1.0 * t["rewards"] for t in paths], axis=0).mean()
                                - float(reward_func.get_expert_cost()))                               # BR:169
     return infos
+
+
+def character_dict_from_json(d):
+    """A DeepMimic character file (parsed JSON) as the table oracle/imitation_oracle.py works on.  Body attach
+    rotations are dropped: they turn the body's own frame, not its centre of mass (KinTree.cpp:1156-1166), so the
+    imitation reward does not see them."""
+    from oracle import imitation_oracle as io
+    types = {"none": io.ROOT, "spherical": io.SPHERICAL, "revolute": io.REVOLUTE, "fixed": io.FIXED}
+    joints = d["Skeleton"]["Joints"]
+    bodies = {b["ID"]: b for b in d["BodyDefs"]}
+    attach = [(j["AttachX"], j["AttachY"], j["AttachZ"]) for j in joints]
+    attach[0] = (0.0, 0.0, 0.0)   # KinTree.cpp:1064-1067
+    return dict(joint_type=[types[j["Type"]] for j in joints], parent=[j["Parent"] for j in joints], attach=attach,
+                is_end_eff=[int(j.get("IsEndEffector", 0)) for j in joints],
+                diff_weight=[float(j.get("DiffWeight", 1.0)) for j in joints],
+                body_mass=[float(bodies[j["ID"]]["Mass"]) for j in joints],
+                body_attach=[(bodies[j["ID"]]["AttachX"], bodies[j["ID"]]["AttachY"], bodies[j["ID"]]["AttachZ"])
+                             for j in joints])

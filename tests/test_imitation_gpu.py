@@ -276,3 +276,28 @@ def test_other_clips_match_reference_golden(name):
                                torch.from_numpy(g[f"{name}/t"]).float(), None, want_terms=True)
         close(terms.cpu().numpy(), g[f"{name}/terms"])
         close(r.cpu().numpy(), g[f"{name}/reward"])
+
+
+def test_a_different_skeleton_matches_reference_golden():
+    """The any-character kernel on the reference's dog3d (23 joints, 83 dof, four end effectors) and its trot clip,
+    loaded by the product's own Character.from_json / MotionClip.from_raw, against the compiled reference."""
+    import json
+    from amp_extensions_b200 import ImitationReward
+    from amp_extensions_b200.character import Character
+    from amp_extensions_b200.motion import MotionClip
+    g = _ref_golden()
+    ch = Character.from_json(json.loads(str(g["dog/character_json"])), ignore_body_rotation=True)
+    imit = ImitationReward(character=ch, clip=MotionClip.from_raw(g["dog/raw"], ch, str(g["dog/loop"])))
+    dur = float(g["dog/duration"])
+    t, org = g["dog/sample_t"], g["dog/sample_origin"]
+    pose, vel = imit.sample(torch.from_numpy(t).float(), torch.from_numpy(org).float())
+    phase = np.mod(t, dur)
+    ok = np.minimum(phase, dur - phase) > 1e-4
+    np.testing.assert_allclose(pose.cpu().numpy()[ok], g["dog/sample_pose"][ok], atol=2e-5)
+    np.testing.assert_allclose(vel.cpu().numpy()[ok], g["dog/sample_vel"][ok], atol=2e-3, rtol=1e-4)
+    r, terms = imit.reward(torch.from_numpy(g["dog/pose"]).float(), torch.from_numpy(g["dog/vel"]).float(),
+                           torch.from_numpy(g["dog/t"]).float(), None, want_terms=True)
+    close(terms.cpu().numpy(), g["dog/terms"])
+    close(r.cpu().numpy(), g["dog/reward"])
+    with pytest.raises(NotImplementedError):
+        imit.record_state(torch.from_numpy(g["dog/pose"]).float(), torch.from_numpy(g["dog/vel"]).float())

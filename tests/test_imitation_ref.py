@@ -201,3 +201,38 @@ def test_other_clips_match_the_reference(name):
     r, terms = io.imitation_reward_batch(CH, c, GOLD[f"{name}/pose"][:n], GOLD[f"{name}/vel"][:n], GOLD[f"{name}/t"][:n])
     np.testing.assert_allclose(terms, GOLD[f"{name}/terms"][:n], atol=ATOL)
     np.testing.assert_allclose(r, GOLD[f"{name}/reward"][:n], atol=ATOL)
+
+
+def test_a_different_skeleton_matches_the_reference():
+    """The reference's dog3d character (23 joints, 83 dof, four end effectors, tails) and its trot clip through the
+    same restatement and through the product's Character.from_json / MotionClip.from_raw host loaders, against the
+    compiled reference initialised with the same two files."""
+    import json
+    from amp_extensions_b200.character import Character
+    from amp_extensions_b200.motion import MotionClip
+    cj = json.loads(str(GOLD["dog/character_json"]))
+    dog = H.character_dict_from_json(cj)
+    raw, loop = GOLD["dog/raw"], str(GOLD["dog/loop"])
+    c = io.Clip(raw, dog, loop)
+    with pytest.raises(NotImplementedError):
+        Character.from_json(cj)                      # the neck and tail bodies carry attach rotations
+    ch = Character.from_json(cj, ignore_body_rotation=True)
+    assert ch.dof == 83 and ch.n_joints == 23 and ch.body_rotation_ignored
+    np.testing.assert_allclose(ch.joint_weights(), GOLD["dog/joint_weights"], atol=1e-15)
+    mc = MotionClip.from_raw(raw, ch, loop)
+    for frames, vels, times in ((c.frames, c.vels, c.times), (mc.frames, mc.frame_vels, mc.frame_times)):
+        np.testing.assert_allclose(times, GOLD["dog/times"], atol=1e-14)
+        np.testing.assert_allclose(frames, GOLD["dog/frames"], atol=1e-13)
+        np.testing.assert_allclose(vels, GOLD["dog/vels"], atol=1e-10)
+    t, org = GOLD["dog/sample_t"], GOLD["dog/sample_origin"]
+    for e in range(t.size):
+        np.testing.assert_allclose(c.kin_pose(float(t[e]), org[e]), GOLD["dog/sample_pose"][e], atol=ATOL)
+        np.testing.assert_allclose(c.kin_vel(float(t[e])), GOLD["dog/sample_vel"][e], atol=ATOL)
+    for e in range(GOLD["dog/com"].shape[0]):
+        com, com_vel = io.calc_com(dog, GOLD["dog/pose"][e], GOLD["dog/vel"][e])
+        np.testing.assert_allclose(com, GOLD["dog/com"][e], atol=ATOL)
+        np.testing.assert_allclose(com_vel, GOLD["dog/com_vel"][e], atol=ATOL)
+    n = 12
+    r, terms = io.imitation_reward_batch(dog, c, GOLD["dog/pose"][:n], GOLD["dog/vel"][:n], GOLD["dog/t"][:n])
+    np.testing.assert_allclose(terms, GOLD["dog/terms"][:n], atol=ATOL)
+    np.testing.assert_allclose(r, GOLD["dog/reward"][:n], atol=ATOL)
