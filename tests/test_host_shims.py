@@ -156,3 +156,60 @@ def test_amp_dataset_transformations_match_the_oracle():
     mine = AmpDataset(s, a, s2).get_transformations(torch.device("cpu"))
     for x, y in zip(mine, mo.get_transformations(s, a, s2)):
         assert torch.equal(x, y)
+
+
+def test_simenv_constructor_reads_the_reference_scene_files(monkeypatch):
+    """The `deepmimic_args=` path of the plugin (sim_env.py:50-116, 270-285): the reference's own arg / controller /
+    character files parsed through the reference's ArgParser, the simulator replaced by the stand-in the golden
+    generator uses.  Needs the reference tree (build container); skipped elsewhere."""
+    import importlib.util
+    import sys
+    import types
+    ref = os.environ.get("SIMSTEP_REFERENCE", "/root/reference")
+    dm_root = os.path.join(ref, "deepmimic", "deepmimic")
+    arg_file = "args/run_amp_humanoid3d_spinkick_args.txt"
+    if not os.path.exists(os.path.join(dm_root, arg_file)):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, GOLDEN_DIR)
+    try:
+        import make_simenv_golden as msg
+    finally:
+        sys.path.remove(GOLDEN_DIR)
+    from oracle import imitation_oracle as io
+    msg.FakeSimulator.clip = io.Clip(H.spinkick_raw(), io.HUMANOID3D, "wrap")
+    spec = importlib.util.spec_from_file_location("deepmimic.util.arg_parser", os.path.join(dm_root, "util", "arg_parser.py"))
+    ap = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ap)
+    mods = {name: types.ModuleType(name) for name in ("deepmimic", "deepmimic.env", "deepmimic.env.deepmimic_env",
+                                                      "deepmimic.util")}
+    mods["deepmimic.env.deepmimic_env"].DeepMimicEnv = msg.FakeSimulator
+    mods["deepmimic.util.arg_parser"] = ap
+    for name, m in mods.items():
+        m.__path__ = [] if name in ("deepmimic", "deepmimic.env", "deepmimic.util") else getattr(m, "__path__", None)
+        monkeypatch.setitem(sys.modules, name, m)
+    monkeypatch.chdir(dm_root)   # the arg file names its character / controller files relative to this directory
+
+    c, _ = tiny_ensemble()
+    s, a, s2 = H.synth_dataset(64, 226, 28, 0)
+    ens = DynamicsEnsemble(226, 28, AmpDataset(s, a, s2), None, num_models=2, hidden_sizes=[16], dense_connect=True,
+                           transform=True, base_seed=100)
+    env = SimEnv(ens, deepmimic_args=arg_file, horizon=11, seed=7, enable_velocity_check=True)
+    assert env.deepmimic is not None and env.time_max == pytest.approx(msg.FakeSimulator.clip.duration)
+    assert set(env.reset_dict) == {"time", "resolve", "noise_bef_rot", "low", "high", "radian", "rot_vel_w_pose",
+                                   "vel_noise", "interp", "knee_rot"}
+    t = env._termination.to_struct()
+    d = HumanoidTermination(horizon=11, enable_velocity_check=True).to_struct()   # the built-in humanoid3d tables
+    assert t.n_bodies == d.n_bodies == 13 and t.horizon == 11 and t.enable_velocity_check == 1
+    assert t.record_all_world == 0 and t.record_world_root_pos == 0 and t.vel_offset == 136 and t.vel_divisor == 1.0
+    for i in range(13):
+        assert (t.body_offset[i], t.body_shape[i]) == (d.body_offset[i], d.body_shape[i])
+        assert t.body_param0[i] == pytest.approx(d.body_param0[i]) and t.body_param1[i] == pytest.approx(d.body_param1[i])
+    # reset: time ~ U(0, time_max) from the env's own RandomState, state from the simulator, member round-robin
+    rs = np.random.RandomState(7)
+    for k in range(3):
+        ob = env.reset()
+        time = rs.uniform(low=0, high=env.time_max)
+        assert env.reset_dict["time"] == time and env.deepmimic.time == time
+        clip = msg.FakeSimulator.clip
+        np.testing.assert_allclose(ob, io.record_state(io.HUMANOID3D, clip.kin_pose(time), clip.kin_vel(time)), atol=0)
+        assert ob.dtype == np.float64 and env.num_steps == 0 and env.reset_counter == (k + 1) % 2
