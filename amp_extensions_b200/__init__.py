@@ -22,3 +22,15 @@ from .sim_env import SimEnv, VecSimEnv  # noqa: F401
 from .character import Character, humanoid3d  # noqa: F401
 from .imitation import ImitationReward  # noqa: F401
 from .motion import MotionClip  # noqa: F401
+
+
+def register_gym(env_id="simenv-v0"):
+    """Register this package's SimEnv under the reference's gym id (gym-simenv/gym_simenv/__init__.py:3-6), so that
+    `gym.make('simenv-v0', deepmimic_args=..., dynamic_ensemble=..., reset_args=...)` (run.py:120) builds the B200
+    plugin.  gym (or gymnasium) is the caller's dependency: raises ImportError when neither is installed."""
+    try:
+        from gym.envs.registration import register
+    except ImportError:
+        from gymnasium.envs.registration import register
+    register(id=env_id, entry_point="amp_extensions_b200.sim_env:SimEnv")
+    return env_id

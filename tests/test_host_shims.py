@@ -213,3 +213,29 @@ def test_simenv_constructor_reads_the_reference_scene_files(monkeypatch):
         clip = msg.FakeSimulator.clip
         np.testing.assert_allclose(ob, io.record_state(io.HUMANOID3D, clip.kin_pose(time), clip.kin_vel(time)), atol=0)
         assert ob.dtype == np.float64 and env.num_steps == 0 and env.reset_counter == (k + 1) % 2
+
+
+def test_gym_registration_uses_the_reference_id(monkeypatch):
+    """gym_simenv/__init__.py:3-6 registers 'simenv-v0'; run.py:120 makes it with deepmimic_args / dynamic_ensemble /
+    reset_args keywords.  gym is not installed here: a recording stand-in for its registry shows what is registered and
+    that the entry point resolves to a class accepting exactly those keywords."""
+    import importlib
+    import inspect
+    import sys
+    import types
+    import amp_extensions_b200 as pkg
+    seen = {}
+    gym = types.ModuleType("gym")
+    envs = types.ModuleType("gym.envs")
+    reg = types.ModuleType("gym.envs.registration")
+    reg.register = lambda id, entry_point, **kw: seen.update(id=id, entry_point=entry_point)
+    gym.envs, envs.registration = envs, reg
+    for name, m in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, m)
+    assert pkg.register_gym() == "simenv-v0" and seen["id"] == "simenv-v0"
+    mod, cls = seen["entry_point"].split(":")
+    env_cls = getattr(importlib.import_module(mod), cls)
+    assert env_cls is SimEnv
+    params = inspect.signature(env_cls.__init__).parameters
+    for kw in ("dynamic_ensemble", "deepmimic_args", "enable_velocity_check", "horizon", "device", "seed", "reset_args"):
+        assert kw in params                      # sim_env.py:27-32 (note the reference's spelling `dynamic_ensemble`)
