@@ -1,13 +1,16 @@
 """In-tree build of libsimstep.so (nvcc, sm_100a only).
 
-`python -m amp_extensions_b200.build` compiles amp_extensions_b200/csrc/api.cu (which includes
-every kernel) into amp_extensions_b200/csrc/libsimstep.so.  nvcc cross-compiles without a GPU.
+`python -m amp_extensions_b200.build` compiles every translation unit under amp_extensions_b200/csrc
+(api.cu: the C ABI and most kernels; final_fused.cu: the fused final-layer kernel's instantiations) in
+parallel and links them into amp_extensions_b200/csrc/libsimstep.so.  nvcc cross-compiles without a GPU.
 """
 import hashlib
 import os
 import shutil
 import subprocess
 import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -17,8 +20,9 @@ STAMP = os.path.join(CSRC, ".libsimstep.stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+UNITS = ("api.cu", "final_fused.cu")
 
 
 def _sources():
@@ -54,12 +58,26 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libsimstep.so cannot be built")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "api.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    log = []
+
+    def compile_unit(args):
+        name, obj = args
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, name)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name}:\n" + res.stdout + res.stderr)
+        log.append(res.stderr)
+
+    with tempfile.TemporaryDirectory(prefix="simstep_build_") as tmp:
+        objs = [os.path.join(tmp, os.path.splitext(u)[0] + ".o") for u in UNITS]
+        with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+            list(pool.map(compile_unit, zip(UNITS, objs)))
+        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write("".join(log))
     with open(STAMP, "w") as f:
         f.write(_digest())
     return LIB

@@ -16,7 +16,7 @@
 #include "../../include/simstep.h"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
-#include "gemm_fused.cuh"
+#include "final_launch.h"
 #include "imitation.cuh"
 #include "imitation_h3d.cuh"
 #include "policy.cuh"
@@ -70,12 +70,15 @@ struct simstep_handle {
   void* xbuf = nullptr;
   void* hbuf = nullptr;
   float* dws = nullptr;
-  unsigned int* ready = nullptr;  // fused forward: [L + 1][N][m_tiles] completed-tile counters
+  unsigned int* tickets = nullptr;  // fused final layer: one arrival counter per 128-row block (gemm_final.cuh)
   CUtensorMap tmap_x, tmap_h, tmap_dws;
 
   // RFF cost
   bool have_rff = false;
-  int D = 0, D_pad = 0, rff_in = 0, RK = 0, RKT = 0, rff_split = 0;
+  int D = 0, D_pad = 0, rff_in = 0, RK = 0, RKT = 0;
+  int rff_split_cap = 0;  // operands were packed as hi/lo pairs: rows hold [hi | lo], weights [hi | hi | lo]
+  int rff_split = 0;      // the three-product evaluation is in use (simstep_set_rff_split; needs rff_split_cap)
+  int rff_col2 = 0;  // input_type 'ss': operand column of s' (s sits at 0); the weight columns are packed to match
   void* rff_w = nullptr;
   float* rff_b = nullptr;
   float* rff_wpad = nullptr;
@@ -196,12 +199,13 @@ int encode_operand(simstep_handle* h, CUtensorMap* map, int prec, void* base, lo
   return SIMSTEP_OK;
 }
 
-template <typename E, int MODE, int CG>
+template <typename E, int MODE, int CG, int EG>
 int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
                   const CUtensorMap& out, const GemmArgs& ga, int sm_count, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};  // function attributes are per device
-  auto kern = gemm_tcgen05_kernel<E, MODE, CG>;
-  constexpr size_t smem = GemmShape<CG>::smem_bytes();
+  auto kern = gemm_tcgen05_kernel<E, MODE, CG, EG>;
+  using Plan = GemmPlan<CG, EG, !epi_is_rff(MODE)>;
+  constexpr size_t smem = Plan::smem_bytes();
   int dev = h ? h->device : 0;  // h is null for simstep_debug_gemm: use the calling thread's current device
   if (!h) CU_TRY(h, cudaGetDevice(&dev));
   bool& attr_done = attr_set[dev % kMaxDevices];
@@ -212,10 +216,11 @@ int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& a
   const int total = ga.m_tiles * ga.n_tiles * ga.groups;
   if (total <= 0) return SIMSTEP_OK;
   // persistent: one CTA (CG = 1) or one CTA pair (CG = 2) per tile slot, at most one CTA per SM
-  const int slots = std::min(total, sm_count / CG);
+  const int n_inner = ga.n_inner > 1 ? ga.n_inner : 1;
+  const int slots = std::min(total / n_inner, sm_count / CG);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(slots * CG));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(Plan::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -232,12 +237,26 @@ int launch_gemm_t(simstep_handle* h, const CUtensorMap& ax, const CUtensorMap& a
   return SIMSTEP_OK;
 }
 
+// SIMSTEP_GEMM_WIDE_EPI=0: one epilogue group everywhere (the round-1 kernels), for A/B runs
+bool wide_epilogue_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_GEMM_WIDE_EPI"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int MODE>
 int launch_gemm(simstep_handle* h, int prec, int cg, const CUtensorMap& ax, const CUtensorMap& ah, const CUtensorMap& b,
                 const CUtensorMap& out, const GemmArgs& ga, int sm_count, cudaStream_t st) {
-#define SIMSTEP_GEMM_CASE(ELEM)                                                                   \
-  return cg == 2 ? launch_gemm_t<ELEM, MODE, 2>(h, ax, ah, b, out, ga, sm_count, st)               \
-                 : launch_gemm_t<ELEM, MODE, 1>(h, ax, ah, b, out, ga, sm_count, st)
+  // Two epilogue groups where the epilogue, not the MMAs, bounds a tile: the cost-feature modes (a cosine per
+  // element, no store staging), and store modes whose whole K fits the shortened ring (the first layer).
+  constexpr bool kStore = !epi_is_rff(MODE);
+  const bool wide = wide_epilogue_enabled() && cg == 2 && MODE != kEpiFinal &&
+                    (!kStore || ga.kb_x + ga.kb_h <= GemmPlan<2, 2, true>::kStages);
+#define SIMSTEP_GEMM_CASE(ELEM)                                                                    \
+  if constexpr (MODE != kEpiFinal) {                                                               \
+    if (wide) return launch_gemm_t<ELEM, MODE, 2, 2>(h, ax, ah, b, out, ga, sm_count, st);          \
+  }                                                                                                \
+  return cg == 2 ? launch_gemm_t<ELEM, MODE, 2, 1>(h, ax, ah, b, out, ga, sm_count, st)             \
+                 : launch_gemm_t<ELEM, MODE, 1, 1>(h, ax, ah, b, out, ga, sm_count, st)
   switch (prec) {
     case SIMSTEP_PREC_TF32: SIMSTEP_GEMM_CASE(ElemTF32);
     case SIMSTEP_PREC_FP16: SIMSTEP_GEMM_CASE(ElemF16);
@@ -286,7 +305,7 @@ void free_workspace(simstep_handle* h) {
   cudaFree(h->xbuf); h->xbuf = nullptr;
   cudaFree(h->hbuf); h->hbuf = nullptr;
   cudaFree(h->dws); h->dws = nullptr;
-  cudaFree(h->ready); h->ready = nullptr;
+  cudaFree(h->tickets); h->tickets = nullptr;
   cudaFree(h->rffin); h->rffin = nullptr;
   cudaFree(h->rff_part); h->rff_part = nullptr;
   h->cap_rows = 0;
@@ -310,7 +329,8 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     CU_TRY(h, cudaMalloc(&h->xbuf, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMalloc(&h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
     CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&h->ready, size_t(h->L + 1) * h->N * (rows / h->row_align + 1) * sizeof(unsigned int)));
+    CU_TRY(h, cudaMalloc(&h->tickets, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
+    CU_TRY(h, cudaMemset(h->tickets, 0, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
     CU_TRY(h, cudaMemset(h->xbuf, 0, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMemset(h->hbuf, 0, size_t(h->N) * rows * h->HT * h->esize));
     int rc = encode_operand(h, &h->tmap_x, prec, h->xbuf, h->XP, rows, h->XP, kBlockM);
@@ -330,7 +350,7 @@ int ensure_workspace(simstep_handle* h, long long rows) {
   if (h->have_rff && h->feat_net) {
     CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));  // A operand = hbuf
   } else if (h->have_rff) {
-    const int rka = h->rff_split ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
+    const int rka = h->rff_split_cap ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
     CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * rka * h->esize));
     CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * rka * h->esize));
     CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));
@@ -355,93 +375,85 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
   g_launches++;
 }
 
-// SIMSTEP_FUSED_LAYERS=1: all layers of the forward pass in one persistent launch (gemm_fused.cuh)
-bool fused_layers_enabled() {
-  static const bool on = [] { const char* e = std::getenv("SIMSTEP_FUSED_LAYERS"); return e && e[0] == '1'; }();
+// The env step's tail for a chunk (caller tensors, chunk-local row 0): given to run_ensemble_chunk it is fused into
+// the final layer's launch (gemm_final.cuh) when final_fused_ok() says so; otherwise launch_post() runs it.
+struct StepTail {
+  const float* state = nullptr;
+  float* next_state = nullptr;
+  const int32_t* member = nullptr;
+  int32_t* num_steps = nullptr;
+  float* disc = nullptr;
+  uint8_t* done = nullptr;
+  bool rff = false;  // also write the cost features' operand rows of [s; s'] (input_type 'ss')
+};
+
+// SIMSTEP_FINAL_FUSED=0 keeps the round-1 sequence (final-layer GEMM, then the post-step kernel) for A/B runs
+bool final_fused_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_FINAL_FUSED"); return !(e && e[0] == '0'); }();
   return on;
 }
 
-template <typename E>
-int launch_fused_t(simstep_handle* h, const FusedMaps& maps, const FusedArgs& fa, cudaStream_t st) {
-  static bool attr_set[kMaxDevices] = {};
-  auto kern = ensemble_fused_kernel<E>;
-  constexpr size_t smem = GemmShape<2>::smem_bytes();
-  bool& done = attr_set[h->device % kMaxDevices];
-  if (!done) {
-    CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    done = true;
+bool final_fused_ok(const simstep_handle* h, const StepTail& t) {
+  const Layer& fin = h->layers[h->L];
+  return final_fused_enabled() && h->cg == 2 && h->S % 2 == 0 && h->S <= kBlockN && fin.o_pad == kBlockN &&
+         reinterpret_cast<uintptr_t>(t.state) % 16 == 0 && reinterpret_cast<uintptr_t>(t.next_state) % 16 == 0 &&
+         (t.next_state == nullptr || t.state != nullptr) && final_smem_bytes(h->S, h->N) <= 227 * 1024;
+}
+
+int launch_final(simstep_handle* h, long long n, long long rows_pad, const StepTail& t, cudaStream_t st) {
+  const Layer& ly = h->layers[h->L];
+  FinalLaunch fl;
+  fl.ax = h->tmap_x;
+  fl.ah = h->tmap_h;
+  fl.b = ly.tmap_w;
+  FinalArgs& fa = fl.args;
+  fa = FinalArgs{};
+  fa.m_tiles = int(rows_pad / (kBlockM * 2));
+  fa.groups = h->N;
+  fa.kb_x = ly.kb_x;
+  fa.kb_h0 = ly.kb_h0;
+  fa.kb_h = ly.kb_h;
+  fa.a_rows_per_group = int(h->cap_rows);
+  fa.b_rows_per_group = ly.o_pad;
+  fa.bias = ly.bias;
+  fa.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
+  fa.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
+  fa.dws_t = reinterpret_cast<float4*>(h->dws);
+  fa.n_blocks = int(rows_pad / kBlockM);
+  fa.counters = h->tickets;
+  fa.state = t.state;
+  fa.next_state = t.next_state;
+  fa.member = t.member;
+  fa.num_steps = t.num_steps;
+  fa.disc = t.disc;
+  fa.done = t.done;
+  fa.n_rows = n;
+  fa.S = h->S;
+  fa.tc = h->term;
+  if (t.rff) {
+    fa.rff_out = h->rffin;
+    fa.rff_pitch = h->rff_split_cap ? 2 * h->RK : h->RK;
+    fa.rff_col2 = h->rff_col2;
+    fa.rff_lo_off = h->rff_split ? h->RK : 0;
   }
-  const int slots = std::min(fa.total_tiles, h->sm_count / 2);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(slots * 2));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, maps, fa));
+  static const int dbg = [] { const char* e = std::getenv("SIMSTEP_FINAL_DEBUG"); return e ? std::atoi(e) : 0; }();
+  fa.debug = dbg;
+  CU_TRY(h, launch_final_fused(h->cfg.precision, fl, h->sm_count, h->device, st));
   g_launches++;
   return SIMSTEP_OK;
 }
 
-int launch_fused_forward(simstep_handle* h, long long rows_pad, cudaStream_t st) {
-  FusedMaps maps;
-  FusedArgs fa{};
-  maps.x = h->tmap_x;
-  maps.h = h->tmap_h;
-  maps.out_final = h->tmap_dws;
-  fa.n_layers = h->L + 1;
-  fa.m_tiles = int(rows_pad / (kBlockM * 2));
-  fa.groups = h->N;
-  fa.a_rows_per_group = int(h->cap_rows);
-  fa.ax_rows_per_group = 0;
-  fa.out_rows_per_group = int(h->cap_rows);
-  fa.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
-  fa.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
-  fa.ready = h->ready;
-  int tile = 0;
-  for (int l = 0; l <= h->L; ++l) {
-    const Layer& ly = h->layers[l];
-    maps.w[l] = ly.tmap_w;
-    FusedLayer& fl = fa.layer[l];
-    fl.tile0 = tile;
-    fl.n_tiles = ly.o_pad / kBlockN;
-    fl.kb_x = ly.kb_x;
-    fl.kb_h0 = ly.kb_h0;
-    fl.kb_h = ly.kb_h;
-    fl.b_rows_per_group = ly.o_pad;
-    fl.out_col0 = l < h->L ? ly.out_col0 : 0;
-    fl.mode = l < h->L ? (h->cfg.activation == SIMSTEP_ACT_RELU ? int(kEpiHidden) : int(kEpiHiddenTanh)) : int(kEpiFinal);
-    fl.bias = ly.bias;
-    tile += fa.m_tiles * fl.n_tiles * fa.groups;
-  }
-  for (int l = h->L + 1; l < kFusedMaxLayers; ++l) maps.w[l] = h->layers[h->L].tmap_w;
-  fa.total_tiles = tile;
-  switch (h->cfg.precision) {
-    case SIMSTEP_PREC_TF32: return launch_fused_t<ElemTF32>(h, maps, fa, st);
-    case SIMSTEP_PREC_FP16: return launch_fused_t<ElemF16>(h, maps, fa, st);
-    default: return launch_fused_t<ElemBF16>(h, maps, fa, st);
-  }
-}
-
-// prep + all layer GEMMs for rows [0, n) of a chunk; leaves un-normalised member
-// deltas in h->dws[N][cap_rows][SP].
+// prep + all layer GEMMs for rows [0, n) of a chunk.  Without a tail (or when the tail cannot be fused) the
+// un-normalised member deltas are left in h->dws[N][cap_rows][DP]; with a fusable tail the final layer's launch
+// also runs the env step's tail and *tail_done is set.
 // w_stage != nullptr: the prep kernel also copies the cost weights into h->rff_wpad (no separate memcpy node
 // between the step's kernels).
 int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long long n, cudaStream_t st,
-                       const float* w_stage = nullptr, int last_layer = -2) {
+                       const float* w_stage = nullptr, int last_layer = -2, const StepTail* tail = nullptr,
+                       bool* tail_done = nullptr) {
   if (last_layer == -2) last_layer = h->L;  // -1: input preparation only
   const long long rows_pad = round_up(n, h->row_align);
-  const bool fused = fused_layers_enabled() && h->cg == 2 && last_layer == h->L;
-  if (fused)  // tile-completion counters of the fused forward; ordered before the prep kernel, hence before the GEMM
-    CU_TRY(h, cudaMemsetAsync(h->ready, 0, size_t(h->L + 1) * h->N * (rows_pad / h->row_align) * sizeof(unsigned int), st));
+  if (tail_done) *tail_done = false;
   {
   ProfScope ps(h, SIMSTEP_PROF_PREP, st);
   switch (h->cfg.precision) {
@@ -452,9 +464,13 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
-  if (fused) return launch_fused_forward(h, rows_pad, st);
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
+    if (l == h->L && tail != nullptr && final_fused_ok(h, *tail)) {
+      if (int rc = launch_final(h, n, rows_pad, *tail, st)) return rc;
+      if (tail_done) *tail_done = true;
+      break;
+    }
     GemmArgs ga{};
     ga.m_tiles = int(rows_pad / (kBlockM * h->cg));
     ga.n_tiles = ly.o_pad / kBlockN;
@@ -506,6 +522,8 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
     rff.prec = h->cfg.precision;
     rff.RK = h->RK;
     rff.split = h->rff_split;
+    rff.col2 = h->rff_col2;
+    rff.pitch = h->rff_split_cap ? 2 * h->RK : h->RK;
   }
   // TMA-staged persistent kernel (post_tma.cuh) whenever rows pair up into 16-byte granular spans
   const PostTmaPlan plan = post_tma_plan(h->S, h->DP, h->N);
@@ -554,17 +572,18 @@ int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStrea
   ProfScope ps(h, SIMSTEP_PROF_RFF_PACK, st);
   const long long rows_pad = round_up(n, h->row_align);
   const int grid = int(std::min<long long>(rows_pad, static_cast<long long>(h->sm_count) * 16));
+  const int pitch = h->rff_split_cap ? 2 * h->RK : h->RK;
   switch (h->cfg.precision) {
     case SIMSTEP_PREC_TF32:
-      launch_pdl(rff_pack_kernel<ElemTF32>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+      launch_pdl(rff_pack_kernel<ElemTF32>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->RK, h->rff_split, pitch, n,
                  rows_pad, static_cast<float*>(h->rffin));
       break;
     case SIMSTEP_PREC_FP16:
-      launch_pdl(rff_pack_kernel<ElemF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+      launch_pdl(rff_pack_kernel<ElemF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->RK, h->rff_split, pitch, n,
                  rows_pad, static_cast<__half*>(h->rffin));
       break;
     default:
-      launch_pdl(rff_pack_kernel<ElemBF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->rff_in, h->RK, h->rff_split, n,
+      launch_pdl(rff_pack_kernel<ElemBF16>, dim3(grid), dim3(kPrepThreads), 0, st, src, h->RK, h->rff_split, pitch, n,
                  rows_pad, static_cast<__nv_bfloat16*>(h->rffin));
   }
   g_launches++;
@@ -572,14 +591,44 @@ int launch_rff_pack(simstep_handle* h, const RffSrc& src, long long n, cudaStrea
   return SIMSTEP_OK;
 }
 
-// RFF GEMM over the packed rows of the chunk.  w_pad == nullptr: features only.
-int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* phi, cudaStream_t st) {
+// What happens to a row's feature dot product (see CombineArgs).
+CombineArgs make_combine(const simstep_handle* h, const float* disc, float lambda_b, float threshold, float c_min,
+                         float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus) {
+  CombineArgs c{};
+  c.enabled = 1;
+  c.disc = disc;
+  c.lambda_b = lambda_b;
+  c.threshold = threshold;
+  c.c_min = c_min;
+  c.c_max = c_max;
+  c.clamp_cost = clamp_cost;
+  c.transform = h->cost_transform;
+  c.dot_scale = (h->feat_net && h->feat_mode == SIMSTEP_HEAD_LINEAR) ? 1.f : float(std::sqrt(2.0 / h->D));
+  c.dot_out = dot;
+  c.cost = cost;
+  c.ipm = ipm;
+  c.bonus = bonus;
+  return c;
+}
+
+// SIMSTEP_RFF_FUSED_COMBINE=0: partial dots per n-tile + cost_combine_kernel (the round-1 sequence), for A/B runs
+bool rff_fused_combine() {
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_RFF_FUSED_COMBINE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// RFF GEMM over the packed rows of the chunk.  w_pad == nullptr: features only.  comb != nullptr: the epilogue
+// finishes cost / ipm / bonus itself (a CTA pair then runs all n-tiles of its rows back to back and carries the dot
+// product in registers); otherwise the per-n-tile partial dots go to h->rff_part for cost_combine_kernel.
+int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* phi, cudaStream_t st,
+                    const CombineArgs* comb = nullptr) {
   ProfScope ps(h, SIMSTEP_PROF_RFF_GEMM, st);
   GemmArgs ga{};
   ga.m_tiles = int(round_up(n, h->row_align) / (kBlockM * h->cg));
   ga.n_tiles = h->D_pad / kBlockN;
   ga.groups = 1;
-  // K loop: [hi | lo] through the first map, then the hi block again (x_hi * W_lo) through the second
+  // K loop: [hi | lo] through the first map, then the hi block again (x_hi * W_lo) through the second; without the
+  // split only the hi block (the first RK columns of the row operand and of the packed weight)
   ga.kb_x = (h->rff_split ? 2 * h->RK : h->RK) / h->bk;
   ga.kb_h0 = 0;
   ga.kb_h = h->rff_split ? h->RK / h->bk : 0;
@@ -594,6 +643,11 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
   ga.rff_part = w_pad ? h->rff_part : nullptr;
   ga.rff_part_stride = h->cap_rows;
   ga.rff_phi_scale = float(std::sqrt(2.0 / h->D));
+  if (comb != nullptr && w_pad != nullptr) {
+    ga.comb = *comb;
+    ga.n_inner = ga.n_tiles;
+    ga.rff_part = nullptr;
+  }
   if (h->feat_net) {
     // the head reads the last hidden layer's slice of the activation buffer
     const Layer& fin = h->layers[h->L];
@@ -610,12 +664,13 @@ int launch_rff_gemm(simstep_handle* h, long long n, const float* w_pad, float* p
                               h->sm_count, st);
 }
 
-int launch_combine(simstep_handle* h, const float* disc, long long n, float lambda_b, float threshold, float c_min,
-                   float c_max, int clamp_cost, float* dot, float* cost, float* ipm, float* bonus, cudaStream_t st) {
+// RFF GEMM + bonus combine for the packed rows of a chunk (one launch, or two with SIMSTEP_RFF_FUSED_COMBINE=0)
+int launch_rff_cost(simstep_handle* h, long long n, const CombineArgs& comb, cudaStream_t st) {
+  if (rff_fused_combine()) return launch_rff_gemm(h, n, h->rff_wpad, nullptr, st, &comb);
+  if (int rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st)) return rc;
   ProfScope ps(h, SIMSTEP_PROF_COMBINE, st);
   launch_pdl(cost_combine_kernel, dim3(grid_for(n, 256, h->sm_count)), dim3(256), 0, st, h->rff_part, h->cap_rows,
-             h->D_pad / kBlockN, (h->feat_net && h->feat_mode == SIMSTEP_HEAD_LINEAR) ? 1.f : float(std::sqrt(2.0 / h->D)),
-             disc, n, lambda_b, threshold, c_min, c_max, clamp_cost, h->cost_transform, dot, cost, ipm, bonus);
+             h->D_pad / kBlockN, n, comb);
   g_launches++;
   CU_TRY(h, cudaGetLastError());
   return SIMSTEP_OK;
@@ -626,16 +681,37 @@ int stage_w(simstep_handle* h, const float* w_dev, cudaStream_t st) {
   return SIMSTEP_OK;
 }
 
+// Operand-row sources for the cost features of (s, a, s').  Operand columns follow the reference's concatenation
+// order (linear_cost.py:115-126) except for input_type 'ss', where s' starts at column rff_col2 (see load_rff).
 int rff_sources(simstep_handle* h, const float* s, const float* a, const float* s2, RffSrc* out) {
   RffSrc r{};
   const int S = h->S, A = h->A, in = h->rff_in;
-  if (in == 2 * S && s2) { r.n = 2; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = s2; r.width[1] = S; }
-  else if (in == S) { r.n = 1; r.ptr[0] = s; r.width[0] = S; }
-  else if (in == S + A) { r.n = 2; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = a; r.width[1] = A; }
-  else if (in == 2 * S + A && s2) { r.n = 3; r.ptr[0] = s; r.width[0] = S; r.ptr[1] = a; r.width[1] = A; r.ptr[2] = s2; r.width[2] = S; }
+  auto seg = [&](const float* p, int width, int pitch, int dst0) {
+    r.ptr[r.n] = p; r.width[r.n] = width; r.pitch[r.n] = pitch; r.dst0[r.n] = dst0; r.n++;
+  };
+  if (in == 2 * S && s2) { seg(s, S, S, 0); seg(s2, S, S, h->rff_col2); }
+  else if (in == S) { seg(s, S, S, 0); }
+  else if (in == S + A) { seg(s, S, S, 0); seg(a, A, A, S); }
+  else if (in == 2 * S + A && s2) { seg(s, S, S, 0); seg(a, A, A, S); seg(s2, S, S, S + A); }
   else return fail(h, SIMSTEP_EINVAL, "rff in_dim does not match an input_type of s/ss/sa/sas");
   *out = r;
   return SIMSTEP_OK;
+}
+
+// Operand-row source for explicit feature-input rows x [n][rff_in] (get_rep / get_costs on caller-built inputs).
+RffSrc rff_row_source(const simstep_handle* h, const float* x) {
+  RffSrc r{};
+  const int in = h->rff_in;
+  if (h->rff_col2 > 0) {  // 'ss' layout: the two halves of a row go to columns 0 and rff_col2
+    const int half = in / 2;
+    r.n = 2;
+    r.ptr[0] = x; r.width[0] = half; r.pitch[0] = in; r.dst0[0] = 0;
+    r.ptr[1] = x + half; r.width[1] = half; r.pitch[1] = in; r.dst0[1] = h->rff_col2;
+  } else {
+    r.n = 1;
+    r.ptr[0] = x; r.width[0] = in; r.pitch[0] = in; r.dst0[0] = 0;
+  }
+  return r;
 }
 
 // Packs layer l of every member (weights_host[m * stride + l], nn.Linear layout) into the operand format.
@@ -820,7 +896,7 @@ int simstep_query(const simstep_handle* h, int32_t* n_layers, int32_t* layer_in,
   if (workspace_bytes) {
     const long long r = h->cap_rows;
     *workspace_bytes = r * h->XP * h->esize + static_cast<long long>(h->N) * r * h->HT * h->esize +
-                       static_cast<long long>(h->N) * r * h->DP * 4 + (h->have_rff ? r * (h->rff_split ? 2 * h->RK : h->RK) * h->esize : 0);
+                       static_cast<long long>(h->N) * r * h->DP * 4 + (h->have_rff ? r * (h->rff_split_cap ? 2 * h->RK : h->RK) * h->esize : 0);
   }
   return SIMSTEP_OK;
 }
@@ -896,9 +972,13 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   h->D = feature_dim;
   h->D_pad = int(round_up(feature_dim, kBlockN));
   h->rff_in = in_dim;
-  h->RK = int(round_up(in_dim, 64));
-  h->rff_split = split ? 1 : 0;
-  h->RKT = h->rff_split ? 3 * h->RK : h->RK;  // K of the packed weight; the row operand stores 2*RK
+  // input_type 'ss' on an ensemble handle (in_dim == 2 S): s' starts at column S rounded up to 8 instead of S, so the
+  // step's fused tail writes both halves of an operand row with aligned 16-byte stores; weight columns follow
+  h->rff_col2 = (h->S > 0 && in_dim == 2 * h->S && !h->feat_net) ? int(round_up(h->S, 8)) : 0;
+  h->RK = int(round_up(h->rff_col2 > 0 ? h->rff_col2 + h->S : in_dim, 64));
+  h->rff_split_cap = split ? 1 : 0;
+  h->rff_split = h->rff_split_cap;
+  h->RKT = h->rff_split_cap ? 3 * h->RK : h->RK;  // K of the packed weight; the row operand stores 2*RK
   const size_t wbytes = size_t(h->D_pad) * h->RKT * h->esize;
   CU_TRY(h, cudaMalloc(&h->rff_w, wbytes));
   CU_TRY(h, cudaMemset(h->rff_w, 0, wbytes));
@@ -913,12 +993,17 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   CU_TRY(h, cudaMemcpy(h->rff_b, bias_host, size_t(feature_dim) * sizeof(float), cudaMemcpyHostToDevice));
   PackSegs sg{};
   sg.n = 1; sg.src0[0] = 0; sg.width[0] = in_dim;
+  if (h->rff_col2 > 0) {
+    sg.n = 2; sg.width[0] = h->S;
+    sg.src0[1] = h->S; sg.width[1] = h->S;
+  }
   // operand triple on the A side is [hi | lo | hi]; B side is [hi | hi | lo]
   const int modes[3] = {1, 1, 2};
-  for (int part = 0; part < (h->rff_split ? 3 : 1); ++part) {
+  for (int part = 0; part < (h->rff_split_cap ? 3 : 1); ++part) {
     sg.dst0[0] = part * h->RK;
+    sg.dst0[1] = part * h->RK + h->rff_col2;
     int rc = pack_matrix(h, h->cfg.precision, tmp, in_dim, feature_dim, h->rff_w, h->RKT, sg,
-                         h->rff_split ? modes[part] : 0, nullptr);
+                         h->rff_split_cap ? modes[part] : 0, nullptr);
     if (rc) { cudaFree(tmp); return rc; }
   }
   CU_TRY(h, cudaDeviceSynchronize());
@@ -959,6 +1044,8 @@ int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host
   h->rff_in = in_dim;
   h->RK = (fin.kb_x + fin.kb_h) * h->bk;  // the padded width of the last hidden layer's slice (or of the input)
   h->rff_split = 0;
+  h->rff_split_cap = 0;
+  h->rff_col2 = 0;
   h->RKT = h->RK;
   const size_t wbytes = size_t(h->D_pad) * h->RKT * h->esize;
   CU_TRY(h, cudaMalloc(&h->rff_w, wbytes));
@@ -995,6 +1082,15 @@ int simstep_set_cost_transform(simstep_handle* h, int32_t transform) {
   return SIMSTEP_OK;
 }
 
+int simstep_set_rff_split(simstep_handle* h, int32_t split) {
+  if (!h) return SIMSTEP_EINVAL;
+  if (!h->have_rff || h->feat_net) return fail(h, SIMSTEP_EINVAL, "simstep_load_rff has not been called");
+  if (split && !h->rff_split_cap)
+    return fail(h, SIMSTEP_EINVAL, "the random-feature layer was loaded without hi/lo operand pairs (split = 0)");
+  h->rff_split = split ? 1 : 0;
+  return SIMSTEP_OK;
+}
+
 int simstep_forward(simstep_handle* h, const float* state_dev, const float* action_dev, int64_t n_envs,
                     float* delta_dev, void* stream) {
   int rc = check_step_ready(h, n_envs);
@@ -1025,8 +1121,12 @@ int simstep_discrepancy(simstep_handle* h, const float* state_dev, const float* 
   if ((rc = ensure_workspace(h, n_envs))) return rc;
   for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
     const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
-    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
-    if ((rc = launch_post(h, nullptr, nullptr, nullptr, n, nullptr, disc_dev + r0, nullptr, st))) return rc;
+    StepTail tail;
+    tail.disc = disc_dev + r0;
+    bool tail_done = false;
+    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st, nullptr, -2, &tail, &tail_done)))
+      return rc;
+    if (!tail_done && (rc = launch_post(h, nullptr, nullptr, nullptr, n, nullptr, disc_dev + r0, nullptr, st))) return rc;
   }
   return SIMSTEP_OK;
 }
@@ -1042,10 +1142,17 @@ int simstep_step(simstep_handle* h, const float* state_dev, const float* action_
   if ((rc = ensure_workspace(h, n_envs))) return rc;
   for (long long r0 = 0; r0 < n_envs; r0 += h->cap_rows) {
     const long long n = std::min<long long>(h->cap_rows, n_envs - r0);
-    if ((rc = run_ensemble_chunk(h, state_dev + r0 * h->S, action_dev + r0 * h->A, n, st))) return rc;
-    if ((rc = launch_post(h, state_dev + r0 * h->S, member_dev ? member_dev + r0 : nullptr,
-                          num_steps_dev ? num_steps_dev + r0 : nullptr, n, next_state_dev + r0 * h->S,
-                          disc_dev ? disc_dev + r0 : nullptr, done_dev ? done_dev + r0 : nullptr, st)))
+    StepTail tail;
+    tail.state = state_dev + r0 * h->S;
+    tail.next_state = next_state_dev + r0 * h->S;
+    tail.member = member_dev ? member_dev + r0 : nullptr;
+    tail.num_steps = num_steps_dev ? num_steps_dev + r0 : nullptr;
+    tail.disc = disc_dev ? disc_dev + r0 : nullptr;
+    tail.done = done_dev ? done_dev + r0 : nullptr;
+    bool tail_done = false;
+    if ((rc = run_ensemble_chunk(h, tail.state, action_dev + r0 * h->A, n, st, nullptr, -2, &tail, &tail_done))) return rc;
+    if (!tail_done && (rc = launch_post(h, tail.state, tail.member, tail.num_steps, n, tail.next_state, tail.disc,
+                                        tail.done, st)))
       return rc;
   }
   return SIMSTEP_OK;
@@ -1069,23 +1176,31 @@ int simstep_step_cost(simstep_handle* h, const float* state_dev, const float* ac
     const float* s = state_dev + r0 * h->S;
     const float* a = action_dev + r0 * h->A;
     float* s2 = next_state_dev + r0 * h->S;
-    if ((rc = run_ensemble_chunk(h, s, a, n, st, r0 == 0 ? w_dev : nullptr))) return rc;
-    // input_type 'ss' with float2-able rows: the post kernel writes the cost features' operand rows itself
-    const bool fuse = h->rff_in == 2 * h->S && h->S % 2 == 0 && reinterpret_cast<uintptr_t>(s) % 8 == 0 &&
+    // input_type 'ss' with float2-able rows: the step's tail writes the cost features' operand rows itself
+    const bool fuse = h->rff_col2 > 0 && h->S % 2 == 0 && reinterpret_cast<uintptr_t>(s) % 8 == 0 &&
                       reinterpret_cast<uintptr_t>(s2) % 8 == 0;
-    if ((rc = launch_post(h, s, member_dev ? member_dev + r0 : nullptr, num_steps_dev ? num_steps_dev + r0 : nullptr,
-                          n, s2, disc_dev + r0, done_dev ? done_dev + r0 : nullptr, st, fuse)))
+    StepTail tail;
+    tail.state = s;
+    tail.next_state = s2;
+    tail.member = member_dev ? member_dev + r0 : nullptr;
+    tail.num_steps = num_steps_dev ? num_steps_dev + r0 : nullptr;
+    tail.disc = disc_dev + r0;
+    tail.done = done_dev ? done_dev + r0 : nullptr;
+    tail.rff = fuse;
+    bool tail_done = false;
+    if ((rc = run_ensemble_chunk(h, s, a, n, st, r0 == 0 ? w_dev : nullptr, -2, &tail, &tail_done))) return rc;
+    if (!tail_done &&
+        (rc = launch_post(h, s, tail.member, tail.num_steps, n, s2, tail.disc, tail.done, st, fuse)))
       return rc;
     if (!fuse) {
       RffSrc src;
       if ((rc = rff_sources(h, s, a, s2, &src))) return rc;
       if ((rc = launch_rff_pack(h, src, n, st))) return rc;
     }
-    if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
-    if ((rc = launch_combine(h, disc_dev + r0, n, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
-                             cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
-                             bonus_dev ? bonus_dev + r0 : nullptr, st)))
-      return rc;
+    const CombineArgs comb = make_combine(h, disc_dev + r0, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
+                                          cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
+                                          bonus_dev ? bonus_dev + r0 : nullptr);
+    if ((rc = launch_rff_cost(h, n, comb, st))) return rc;
   }
   return SIMSTEP_OK;
 }
@@ -1105,9 +1220,7 @@ int simstep_rff_features(simstep_handle* h, const float* x_dev, int64_t n_rows, 
       if (h->feat_net) {
         if ((rc = run_ensemble_chunk(h, x_dev + r0 * h->S, nullptr, n, st, nullptr, h->L - 1))) return rc;
       } else {
-        RffSrc src{};
-        src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
-        if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+        if ((rc = launch_rff_pack(h, rff_row_source(h, x_dev + r0 * h->rff_in), n, st))) return rc;
       }
       if ((rc = launch_rff_gemm(h, n, nullptr, phi_dev + r0 * h->D, st))) return rc;
     }
@@ -1147,21 +1260,16 @@ int simstep_bonus_cost(simstep_handle* h, const float* x_dev, const float* disc_
     if (h->feat_net) {
       if ((rc = run_ensemble_chunk(h, x_dev + r0 * h->S, nullptr, n, st, nullptr, h->L - 1))) return rc;
     } else {
-      RffSrc src{};
-      src.n = 1; src.ptr[0] = x_dev + r0 * h->rff_in; src.width[0] = h->rff_in;
-      if ((rc = launch_rff_pack(h, src, n, st))) return rc;
+      if ((rc = launch_rff_pack(h, rff_row_source(h, x_dev + r0 * h->rff_in), n, st))) return rc;
     }
-    if ((rc = launch_rff_gemm(h, n, h->rff_wpad, nullptr, st))) return rc;
-    if (disc_dev == nullptr) {
-      // raw dot only (simstep_rff_dot): cost_dev receives phi.w
-      rc = launch_combine(h, nullptr, n, 0.f, 1.f, 0.f, 0.f, 0, cost_dev ? cost_dev + r0 : nullptr, nullptr, nullptr,
-                          nullptr, st);
-    } else {
-      rc = launch_combine(h, disc_dev + r0, n, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
-                          cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
-                          bonus_dev ? bonus_dev + r0 : nullptr, st);
-    }
-    if (rc) return rc;
+    // disc_dev == nullptr (simstep_rff_dot): cost_dev receives the raw phi . w
+    const CombineArgs comb =
+        disc_dev == nullptr
+            ? make_combine(h, nullptr, 0.f, 1.f, 0.f, 0.f, 0, cost_dev ? cost_dev + r0 : nullptr, nullptr, nullptr, nullptr)
+            : make_combine(h, disc_dev + r0, lambda_b, threshold, c_min, c_max, clamp_cost, nullptr,
+                           cost_dev ? cost_dev + r0 : nullptr, ipm_dev ? ipm_dev + r0 : nullptr,
+                           bonus_dev ? bonus_dev + r0 : nullptr);
+    if ((rc = launch_rff_cost(h, n, comb, st))) return rc;
   }
   return SIMSTEP_OK;
 }

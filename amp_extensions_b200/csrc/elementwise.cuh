@@ -139,41 +139,39 @@ prep_input_kernel(const float* __restrict__ state, const float* __restrict__ act
 // [hi | lo | hi] operand triple (see simstep_load_rff).
 struct RffSrc {
   int n;
-  const float* ptr[3];
-  int width[3];
+  const float* ptr[3];   // first element of the segment in row 0
+  int width[3];          // columns taken from the segment
+  int pitch[3];          // floats between consecutive rows of the segment's source
+  int dst0[3];           // operand column of the segment's first element (segments may leave gaps: zero padding)
 };
 
 // out row = [hi(x) | lo(x)] (split) or [hi(x)] with x the concatenation of the sources zero-padded to RK; the
 // GEMM re-reads the hi block for the third product (x_hi * W_lo), so it is stored once.
 template <typename E>
 __global__ void __launch_bounds__(kPrepThreads)
-rff_pack_kernel(RffSrc src, int in_dim, int RK, int split, long long n_rows, long long rows_pad,
+rff_pack_kernel(RffSrc src, int RK, int split, int pitch, long long n_rows, long long rows_pad,
                 typename E::storage* __restrict__ out) {
   using P = typename Pair<typename E::storage>::type;
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();
-  const int pitch = split ? 2 * RK : RK;
   for (int c0 = 2 * threadIdx.x; c0 < RK; c0 += 2 * kPrepThreads) {
     const float* base[2] = {nullptr, nullptr};
-    int width[2] = {0, 0}, off[2] = {0, 0};
+    int spitch[2] = {0, 0};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      int c = c0 + i;
-      if (c < in_dim) {
+      const int c = c0 + i;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (k < src.n && base[i] == nullptr) {
-            if (c < src.width[k]) { base[i] = src.ptr[k]; width[i] = src.width[k]; off[i] = c; }
-            c -= src.width[k];
-          }
+      for (int k = 0; k < 3; ++k)
+        if (k < src.n && c >= src.dst0[k] && c < src.dst0[k] + src.width[k]) {
+          base[i] = src.ptr[k] + (c - src.dst0[k]);
+          spitch[i] = src.pitch[k];
         }
-      }
     }
     for (long long row = blockIdx.x; row < rows_pad; row += gridDim.x) {
       float v[2] = {0.f, 0.f};
       if (row < n_rows) {
-        if (base[0]) v[0] = base[0][row * width[0] + off[0]];
-        if (base[1]) v[1] = base[1][row * width[1] + off[1]];
+        if (base[0]) v[0] = base[0][row * spitch[0]];
+        if (base[1]) v[1] = base[1][row * spitch[1]];
       }
       const P hi = make_pair_cvt<E>(v[0], v[1]);
       typename E::storage* orow = out + row * pitch;
@@ -232,21 +230,23 @@ struct PostVec<2> {
   }
 };
 
-// RFF operand row of the fused step: [hi(s) | hi(s') | 0][lo(s) | lo(s') | 0] (see rff_pack_kernel), written by
+// RFF operand row of the fused step: [hi(s) | 0 | hi(s') | 0][lo(s) | 0 | lo(s') | 0] (see rff_pack_kernel; s' starts at
+// column col2 = S rounded up to 8, so both halves can be written with 16-byte stores), written by
 // the same warp that produced s'.  prec: SIMSTEP_PREC_*; out == nullptr: not fused.
 struct PostRff {
   void* out;
   int prec;
   int RK;
   int split;
+  int col2;  // operand column of s' (s starts at column 0)
+  int pitch; // elements per operand row (2 RK when the rows were allocated for hi/lo pairs, whether or not split is on)
 };
 
 template <typename E>
 __device__ __forceinline__ void post_rff_store(const PostRff& r, long long row, int col, float2 v) {
   using T = typename E::storage;
   using P = typename Pair<T>::type;
-  const int pitch = r.split ? 2 * r.RK : r.RK;
-  T* orow = static_cast<T*>(r.out) + row * pitch;
+  T* orow = static_cast<T*>(r.out) + row * r.pitch;
   const P hi = make_pair_cvt<E>(v.x, v.y);
   *reinterpret_cast<P*>(orow + col) = hi;
   if (r.split)
@@ -350,13 +350,13 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
             if (j < nvec) {
               if (rff.prec == SIMSTEP_PREC_FP16) {
                 post_rff_store<ElemF16>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemF16>(rff, row, S + 2 * j, nxt[i]);
+                post_rff_store<ElemF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
               } else if (rff.prec == SIMSTEP_PREC_TF32) {
                 post_rff_store<ElemTF32>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemTF32>(rff, row, S + 2 * j, nxt[i]);
+                post_rff_store<ElemTF32>(rff, row, rff.col2 + 2 * j, nxt[i]);
               } else {
                 post_rff_store<ElemBF16>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemBF16>(rff, row, S + 2 * j, nxt[i]);
+                post_rff_store<ElemBF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
               }
             }
           }
@@ -399,7 +399,7 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
 }
 
 // delta workspace -> dense [NM][E][S] rows (DynamicsModel.forward's return value)
-__global__ void extract_delta_kernel(const float* __restrict__ ws, long long ws_rows, int SP, int NM, int S,
+static __global__ void extract_delta_kernel(const float* __restrict__ ws, long long ws_rows, int SP, int NM, int S,
                                      long long n_rows, float* __restrict__ out, long long out_rows,
                                      long long out_row0) {
   const long long total = static_cast<long long>(NM) * n_rows * S;
@@ -416,46 +416,15 @@ __global__ void extract_delta_kernel(const float* __restrict__ ws, long long ws_
 
 // ---- cost combine (reference milo/milo/linear_cost.py:96-103, 130-147) ------
 
-__global__ void cost_combine_kernel(const float* __restrict__ part, long long part_stride, int n_parts,
-                                    float phi_scale, const float* __restrict__ disc, long long n_rows, float lambda_b,
-                                    float threshold, float c_min, float c_max, int clamp_cost, int transform,
-                                    float* __restrict__ dot_out, float* __restrict__ cost, float* __restrict__ ipm,
-                                    float* __restrict__ bonus) {
+static __global__ void cost_combine_kernel(const float* __restrict__ part, long long part_stride, int n_parts,
+                                           long long n_rows, const CombineArgs comb) {
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < n_rows;
        row += static_cast<long long>(gridDim.x) * blockDim.x) {
     float dot = 0.f;
     for (int t = 0; t < n_parts; ++t) dot += part[t * part_stride + row];
-    dot *= phi_scale;
-    if (transform == SIMSTEP_COST_GAIL_LS) {
-      // GAILCost.get_ls_costs (gail_cost.py:232-238): rewards = 1 - 0.25 (1 - d)^2, clipped at 0; cost = -rewards
-      const float u = 1.f - dot;
-      float r = fmaf(-0.25f * u, u, 1.f);
-      if (r < 0.f) r = 0.f;
-      dot = -r;
-    } else if (transform == SIMSTEP_COST_GAIL_LL) {
-      // GAILCost.get_ll_costs (gail_cost.py:240-246): logsigmoid(d) = min(d, 0) - log1p(exp(-|d|))
-      dot = fminf(dot, 0.f) - log1pf(expf(-fabsf(dot)));
-    }
-    if (dot_out) dot_out[row] = dot;
-    if (disc == nullptr) continue;
-    float c = dot;
-    float b;
-    if (clamp_cost) {
-      c = fminf(fmaxf(c, c_min), c_max);
-      if (dot != dot) c = dot;  // torch.clamp keeps NaN
-      float dh = disc[row] / threshold;
-      if (dh > 1.0f) dh = 1.0f;
-      b = dh * c_min;
-    } else {
-      b = disc[row];
-    }
-    const float i_ = (1.f - lambda_b) * c;
-    const float wb = lambda_b * b;
-    if (ipm) ipm[row] = i_;
-    if (bonus) bonus[row] = wb;
-    if (cost) cost[row] = i_ - wb;
+    combine_row(comb, row, dot);
   }
 }
 
@@ -463,7 +432,7 @@ __global__ void cost_combine_kernel(const float* __restrict__ part, long long pa
 
 // column sums of a [n_rows][D] fp32 matrix, fp64 accumulate, two passes so the
 // result does not depend on scheduling: partial[b][d] then final.
-__global__ void colsum_partial_kernel(const float* __restrict__ x, long long n_rows, int D, int rows_per_block,
+static __global__ void colsum_partial_kernel(const float* __restrict__ x, long long n_rows, int D, int rows_per_block,
                                       double* __restrict__ partial) {
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(r0 + rows_per_block, n_rows);
@@ -473,7 +442,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long n_r
     partial[static_cast<long long>(blockIdx.x) * D + dcol] = s;
   }
 }
-__global__ void colsum_final_kernel(const double* __restrict__ partial, int n_blocks, int D, double* __restrict__ out,
+static __global__ void colsum_final_kernel(const double* __restrict__ partial, int n_blocks, int D, double* __restrict__ out,
                                     int accumulate) {
   for (int dcol = blockIdx.x * blockDim.x + threadIdx.x; dcol < D; dcol += gridDim.x * blockDim.x) {
     double s = 0.0;
@@ -483,7 +452,7 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int n_bl
 }
 
 // out[0] = max, out[1] = sum; single block, deterministic.
-__global__ void reduce_max_sum_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+static __global__ void reduce_max_sum_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
   __shared__ double s_sum[32];
   __shared__ float s_max[32];
   double sum = 0.0;

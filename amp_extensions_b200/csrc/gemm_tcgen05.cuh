@@ -43,13 +43,17 @@ namespace simstep {
 #endif
 constexpr int kBlockM = 128;   // accumulator rows per CTA
 constexpr int kBlockN = 256;   // accumulator columns (output features per tile)
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 4;      // per epilogue group
 constexpr int kNumEpiThreads = kNumEpiWarps * 32;
 constexpr int kGemmThreads = 64 + kNumEpiThreads;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kTmemCols = 512;                     // two 128x256 fp32 accumulators
 constexpr int kABytes = kBlockM * 128;             // one swizzle atom (128 B) per row
 constexpr int kOutStageBytes = kBlockM * 128;      // staging tile of the TMA-store epilogue: 128 rows x 128 B
-constexpr int kOutStages = SIMSTEP_GEMM_OUT_STAGES;
+// per-tile epilogue constants staged in shared memory, double-buffered: bias | scale (or cost weights) | shift for
+// the tile's kBlockN columns.  Read straight from global memory (one broadcast load per 4 columns per chunk) they
+// showed up as the epilogue's dominant stall (long scoreboard on the first use of every chunk).
+constexpr int kEpiConstFloats = 3 * kBlockN;
+constexpr int kEpiConstBytes = 2 * kEpiConstFloats * 4;
 
 template <int CG>
 struct GemmShape {
@@ -57,8 +61,21 @@ struct GemmShape {
   static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = CG == 2 ? SIMSTEP_GEMM_STAGES_CG2 : 4;
+};
+
+// Shared-memory plan of one kernel variant.  EG = epilogue warp GROUPS (4 warps each: one per TMEM lane quarter).
+// A single epilogue warp per quarter issues about one instruction every five cycles (its chains are dependent), so
+// short-K tiles - the first layer, the cost features - are bound by the epilogue, not by the MMAs: with EG = 2 a
+// second group takes the upper half of the tile's columns.  Store-tile variants with EG = 2 give every group its own
+// pair of staging tiles and pay for them with one ring stage (they are only used where the whole K fits the ring).
+template <int CG, int EG, bool STORE>
+struct GemmPlan {
+  static constexpr int kStages = (CG == 2 && EG == 2 && STORE) ? 4 : GemmShape<CG>::kStages;
+  static constexpr int kOutStages = STORE ? SIMSTEP_GEMM_OUT_STAGES * EG : 0;
+  static constexpr int kThreads = 64 + 128 * EG;  // warp 0 TMA, warp 1 MMA, then the epilogue groups
   static constexpr size_t smem_bytes() {
-    return 1024 /*align slack*/ + size_t(kStages) * kStageBytes + size_t(kOutStages) * kOutStageBytes + 256;
+    return 1024 /*align slack*/ + size_t(kStages) * GemmShape<CG>::kStageBytes + size_t(kOutStages) * kOutStageBytes +
+           kEpiConstBytes + kBlockM * sizeof(float) /*dot hand-over*/ + 256;
   }
 };
 
@@ -132,8 +149,57 @@ struct ElemDims {
 enum EpiMode : int { kEpiHidden = 0, kEpiFinal = 1, kEpiRff = 2, kEpiHiddenTanh = 3, kEpiFeat = 4 };
 __host__ __device__ constexpr bool epi_is_rff(int mode) { return mode == kEpiRff || mode == kEpiFeat; }
 
+// Bonus combine of MILO's cost (reference milo/milo/linear_cost.py:96-103, 130-147; GAILCost variants
+// gail_cost.py:232-246), applied to one row's feature dot product.  Used by the random-feature GEMM's epilogue
+// (fused: the dot never leaves registers) and by cost_combine_kernel (explicit partial dots).
+struct CombineArgs {
+  int enabled;            // epilogue: finish the row here (needs n_inner == n_tiles)
+  const float* disc;      // nullptr: only dot_out is written
+  float lambda_b, threshold, c_min, c_max;
+  int clamp_cost;
+  int transform;          // SIMSTEP_COST_*
+  float dot_scale;        // sqrt(2/D), or 1 for a linear head
+  float* dot_out;
+  float* cost;
+  float* ipm;
+  float* bonus;
+};
+
+__device__ __forceinline__ void combine_row(const CombineArgs& c, long long row, float dot) {
+  dot *= c.dot_scale;
+  if (c.transform == 1 /*SIMSTEP_COST_GAIL_LS*/) {
+    // GAILCost.get_ls_costs (gail_cost.py:232-238): rewards = 1 - 0.25 (1 - d)^2, clipped at 0; cost = -rewards
+    const float u = 1.f - dot;
+    float r = fmaf(-0.25f * u, u, 1.f);
+    if (r < 0.f) r = 0.f;
+    dot = -r;
+  } else if (c.transform == 2 /*SIMSTEP_COST_GAIL_LL*/) {
+    // GAILCost.get_ll_costs (gail_cost.py:240-246): logsigmoid(d) = min(d, 0) - log1p(exp(-|d|))
+    dot = fminf(dot, 0.f) - log1pf(expf(-fabsf(dot)));
+  }
+  if (c.dot_out) c.dot_out[row] = dot;
+  if (c.disc == nullptr) return;
+  float cc = dot;
+  float b;
+  if (c.clamp_cost) {
+    cc = fminf(fmaxf(cc, c.c_min), c.c_max);
+    if (dot != dot) cc = dot;  // torch.clamp keeps NaN
+    float dh = c.disc[row] / c.threshold;
+    if (dh > 1.0f) dh = 1.0f;
+    b = dh * c.c_min;
+  } else {
+    b = c.disc[row];
+  }
+  const float i_ = (1.f - c.lambda_b) * cc;
+  const float wb = c.lambda_b * b;
+  if (c.ipm) c.ipm[row] = i_;
+  if (c.bonus) c.bonus[row] = wb;
+  if (c.cost) c.cost[row] = i_ - wb;
+}
+
 struct GemmArgs {
   // tile space: tile -> (group, m_tile, n_tile), n fastest; an m_tile is CG * 128 rows
+  int n_inner;            // consecutive n-tiles of one (group, m_tile) a CTA pair runs back to back (0 / 1: none)
   int m_tiles;
   int n_tiles;
   int groups;
@@ -159,6 +225,7 @@ struct GemmArgs {
   float rff_phi_scale;    // sqrt(2/D)
   int rff_tanh;           // kEpiRff: phi = cos(tanh(pre-activation)) (MLPCost, linear_cost.py:208-221)
   int rff_linear;         // kEpiRff: phi = pre-activation (discriminator output, gail_cost.py:18-43)
+  CombineArgs comb;       // kEpiRff: finish cost / ipm / bonus in the epilogue
 };
 
 template <typename E, int CG>
@@ -185,8 +252,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.f - __fdividef(2.f, t + 1.f);
 }
 
-template <typename E, int MODE, int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <typename E, int MODE, int CG, int EG = 1>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_constant__ CUtensorMap tmap_ah,
                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                     const GemmArgs args) {
@@ -194,15 +261,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
   constexpr int BK = ElemDims<E>::kBlockK;
   constexpr int UK = ElemDims<E>::kUmmaK;
   constexpr int kMmasPerBlock = BK / UK;  // 4
-  constexpr int kStages = S::kStages;
   constexpr bool kStoreTile = !epi_is_rff(MODE);
+  using Plan = GemmPlan<CG, EG, kStoreTile>;
+  constexpr int kStages = Plan::kStages;
+  constexpr int kOutStages = Plan::kOutStages;
+  constexpr int kEpiWarps = 4 * EG;
+  constexpr int kEpiThreads = 128 * EG;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_tiles = smem;                                           // kStages * (A | B)
   uint8_t* smem_out = smem + size_t(kStages) * S::kStageBytes;          // kOutStages staging tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + size_t(kOutStages) * kOutStageBytes);
+  float* smem_const = reinterpret_cast<float*>(smem_out + size_t(kOutStages) * kOutStageBytes);  // [2][kEpiConstFloats]
+  float* smem_dot = smem_const + 2 * kEpiConstFloats;  // [kBlockM] second group's partial dots (kEpiRff, EG = 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dot + kBlockM);
   uint64_t* full_bar = bars;                   // [kStages]   (the leader's copy is the one in use)
   uint64_t* empty_bar = bars + kStages;        // [kStages]
   uint64_t* tmem_full_bar = bars + 2 * kStages;      // [2]
@@ -221,7 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], kNumEpiWarps * CG);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps * CG);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmap_ax);
@@ -243,8 +316,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
 
   const int total_tiles = args.m_tiles * args.n_tiles * args.groups;
   const int kb_total = args.kb_x + args.kb_h;
+  // a CTA pair's iteration `it` runs tile  (tile0 + (it / n_inner) * tile_step) * n_inner + it % n_inner
+  const int n_inner = args.n_inner > 1 ? args.n_inner : 1;
+  const int total_super = total_tiles / n_inner;
   const int tile0 = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
+  auto tile_of = [&](int it) {
+    const int super = tile0 + (it / n_inner) * tile_step;
+    return super < total_super ? super * n_inner + it % n_inner : -1;
+  };
   const bool b_resident = SIMSTEP_GEMM_B_RESIDENT != 0 && kb_total <= kStages;
   const int ring = b_resident ? kb_total : kStages;
 
@@ -253,7 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     int held_b = -1;  // (group, n-tile) whose weight k-blocks sit in the stages' B halves (B-resident mode)
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
       const int n_tile = tile % args.n_tiles;
       const int t2 = tile / args.n_tiles;
       const int m_tile = t2 % args.m_tiles;
@@ -288,8 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       constexpr uint32_t idesc = make_idesc<E, CG>();
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      for (int it = 0; tile_of(it) >= 0; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -320,14 +399,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - 64;
+    const int grp = epi_tid >> 7;           // epilogue group: owns the columns [grp, grp + 1) * kBlockN / EG of a tile
+    const int gtid = epi_tid & 127;
+    const uint32_t bar_base = 1 + 3 * grp;  // named barriers of this group (id 3 * EG + 1.. are CTA-wide)
     using T = typename E::storage;
     constexpr bool kFinal = (MODE == kEpiFinal);
     // columns per staging tile (128 bytes per row) and TMEM chunks (32 columns) that fill one
     constexpr int kTileCols = kFinal ? 32 : int(128 / sizeof(T));
     constexpr int kChunksPerStore = kTileCols / 32;
     int store_it = 0;
-    int it = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+    float dot = 0.f;  // kEpiRff: feature dot product of this thread's row (carried across a pair's n_inner tiles)
+    for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
       const int n_tile = tile % args.n_tiles;
       const int t2 = tile / args.n_tiles;
       const int m_tile = t2 % args.m_tiles;
@@ -337,49 +419,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       const int n0 = n_tile * kBlockN;
       const int m_row = (m_tile * CG + int(cta_rank)) * kBlockM;
       const float* bias_g = args.bias ? args.bias + size_t(g) * args.n_tiles * kBlockN + n0 : nullptr;
+      // stage the tile's per-column constants while the MMAs of this tile are still running: thread t brings
+      // columns 2t, 2t + 1 of each vector
+      float* cst = smem_const + (it & 1) * kEpiConstFloats;
+      if (epi_tid < kBlockN / 2) {
+        const int c0 = 2 * epi_tid;
+        const float2 bv = bias_g ? __ldg(reinterpret_cast<const float2*>(bias_g + c0)) : make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(cst + c0) = bv;
+        if constexpr (kFinal || epi_is_rff(MODE)) {
+          const float fill = kFinal ? 1.f : 0.f;
+          const float2 sv = args.scale ? __ldg(reinterpret_cast<const float2*>(args.scale + n0 + c0))
+                                       : make_float2(fill, fill);
+          *reinterpret_cast<float2*>(cst + kBlockN + c0) = sv;
+        }
+        if constexpr (kFinal) {
+          const float2 hv = args.shift ? __ldg(reinterpret_cast<const float2*>(args.shift + n0 + c0))
+                                       : make_float2(0.f, 0.f);
+          *reinterpret_cast<float2*>(cst + 2 * kBlockN + c0) = hv;
+        }
+      }
+      ptx::named_bar_sync(3 * EG + 1, kEpiThreads);
 
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
       constexpr int kChunks = kBlockN / 32;
+      const int c_begin = grp * (kChunks / EG), c_end = c_begin + kChunks / EG;
 
       // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is processed, and the
       // accumulator is handed back to the MMA warp as soon as the last chunk sits in registers.
       uint32_t ra[32], rb[32];
-      ptx::tmem_ld_32x32(taddr, ra);
+      ptx::tmem_ld_32x32(taddr + c_begin * 32, ra);
 
-      float dot = 0.f;  // kEpiRff
+      if (!(args.comb.enabled && it % n_inner != 0)) dot = 0.f;
       auto process = [&](const uint32_t (&r)[32], int c) {
         float v[32];
-        if (bias_g != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_g + c * 32);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(cst + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);  // same address in every lane: one broadcast L1 hit
+            const float4 b = b4[j];  // same address in every lane: a shared-memory broadcast
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
         if constexpr (kStoreTile) {
           constexpr int kWords = kFinal ? 32 : E::kWords32;  // 32-bit words this chunk contributes to a row
           uint32_t w[kWords];
           if constexpr (kFinal) {
-            if (args.scale != nullptr) {
-              const float4* s4 = reinterpret_cast<const float4*>(args.scale + n0 + c * 32);
-              const float4* h4 = reinterpret_cast<const float4*>(args.shift + n0 + c * 32);
+            const float4* s4 = reinterpret_cast<const float4*>(cst + kBlockN + c * 32);
+            const float4* h4 = reinterpret_cast<const float4*>(cst + 2 * kBlockN + c * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 sc = __ldg(s4 + j), sh = __ldg(h4 + j);
-                v[4 * j + 0] = fmaf(v[4 * j + 0], sc.x, sh.x);
-                v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
-                v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z);
-                v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float4 sc = s4[j], sh = h4[j];
+              v[4 * j + 0] = fmaf(v[4 * j + 0], sc.x, sh.x);
+              v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z);
+              v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
@@ -392,11 +490,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           }
           // staging tile: row r holds 128 bytes, 16-byte unit j sits at unit j ^ (r & 7) (TMA SWIZZLE_128B)
           const int sub = c % kChunksPerStore;            // position of this chunk inside the staging row
-          const int buf = store_it % kOutStages;
+          constexpr int kGroupStages = SIMSTEP_GEMM_OUT_STAGES;  // staging tiles owned by one group
+          const int buf = grp * kGroupStages + store_it % kGroupStages;
           if (sub == 0) {
             // the TMA store that last read this staging buffer must have finished reading shared memory
-            if (epi_tid == 0) ptx::tma_store_wait_read<kOutStages - 1>();
-            ptx::named_bar_sync(1, kNumEpiThreads);
+            if (gtid == 0) ptx::tma_store_wait_read<kGroupStages - 1>();
+            ptx::named_bar_sync(bar_base, 128);
           }
           uint8_t* srow = smem_out + size_t(buf) * kOutStageBytes + row_in_tile * 128;
           constexpr int kUnits = kWords / 4;              // 16-byte units written per chunk
@@ -408,8 +507,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           }
           if (sub == kChunksPerStore - 1) {
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(2, kNumEpiThreads);
-            if (epi_tid == 0) {
+            ptx::named_bar_sync(bar_base + 1, 128);
+            if (gtid == 0) {
               const int col = args.out_col0 + n0 + (c / kChunksPerStore) * kTileCols;
               ptx::tma_store_2d(&tmap_out, smem_out + size_t(buf) * kOutStageBytes, col,
                                 g * args.out_rows_per_group + m_row);
@@ -419,7 +518,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           }
         } else {  // kEpiRff: phi = cos(pre-activation); dot with w (padded columns carry w == 0)
           const long long row = static_cast<long long>(m_row) + row_in_tile;
-          const float4* w4 = reinterpret_cast<const float4*>(args.scale + n0 + c * 32);
+          const float4* w4 = reinterpret_cast<const float4*>(cst + kBlockN + c * 32);
           float f[32];
           if constexpr (MODE == kEpiFeat) {
             if (args.rff_linear) {
@@ -436,7 +535,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
           if (args.scale != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 w = __ldg(w4 + j);
+              const float4 w = w4[j];
               dot = fmaf(f[4 * j + 0], w.x, dot);
               dot = fmaf(f[4 * j + 1], w.y, dot);
               dot = fmaf(f[4 * j + 2], w.z, dot);
@@ -454,12 +553,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       };
 
 #pragma unroll 1
-      for (int c = 0; c < kChunks; c += 2) {
+      for (int c = c_begin; c < c_end; c += 2) {
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
         process(ra, c);
         ptx::tmem_ld_wait();
-        if (c + 2 < kChunks) {
+        if (c + 2 < c_end) {
           ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
         } else {
           // accumulator drained: the MMA warp (leader CTA) may overwrite it
@@ -471,11 +570,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       }
       if constexpr (epi_is_rff(MODE)) {
         const long long row = static_cast<long long>(m_row) + row_in_tile;
-        if (args.rff_part != nullptr && row < args.rows_valid)
-          args.rff_part[size_t(n_tile) * args.rff_part_stride + row] = dot;
+        const bool finish = !args.comb.enabled || it % n_inner == n_inner - 1;  // the row's dot leaves registers
+        float total = dot;
+        if constexpr (EG == 2) {
+          if (finish && args.scale != nullptr) {  // the upper group hands its part of the dot product over
+            if (grp == 1) smem_dot[row_in_tile] = dot;
+            ptx::named_bar_sync(3 * EG + 2, kEpiThreads);
+            total = dot + smem_dot[row_in_tile];
+            // the next hand-over is behind the next tile's constants barrier, which every group-0 thread passes
+            // only after this read
+          }
+        }
+        if (grp == 0 && finish) {
+          if (args.comb.enabled) {
+            if (row < args.rows_valid) combine_row(args.comb, row, total);
+          } else if (args.rff_part != nullptr && row < args.rows_valid) {
+            args.rff_part[size_t(n_tile) * args.rff_part_stride + row] = total;
+          }
+        }
       }
     }
-    if (kStoreTile && epi_tid == 0) ptx::tma_store_wait<0>();  // shared memory must outlive the last store's read
+    if (kStoreTile && gtid == 0) ptx::tma_store_wait<0>();  // shared memory must outlive the last store's read
   }
 
   ptx::tcgen05_fence_before();

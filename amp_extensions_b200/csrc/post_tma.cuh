@@ -209,13 +209,12 @@ __device__ __forceinline__ void post_tma_row(float* srow, const float* drow0, in
     }
     if (rff.out != nullptr) {  // cost features' operand row for input_type 'ss' (linear_cost.py:119)
       using T = typename E::storage;
-      const int pitch = rff.split ? 2 * rff.RK : rff.RK;
-      T* orow = static_cast<T*>(rff.out) + row * pitch + 2 * lane;
+      T* orow = static_cast<T*>(rff.out) + row * rff.pitch + 2 * lane;
 #pragma unroll
       for (int i = 0; i < kSlots; ++i) {
         if (in[i]) {
           post_tma_rff_store<E>(orow, rff.RK, rff.split != 0, 64 * i, sv[i]);
-          post_tma_rff_store<E>(orow, rff.RK, rff.split != 0, S + 64 * i, nxt[i]);
+          post_tma_rff_store<E>(orow, rff.RK, rff.split != 0, rff.col2 + 64 * i, nxt[i]);
         }
       }
     }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace simstep {
 namespace ptx {

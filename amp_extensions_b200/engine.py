@@ -164,6 +164,13 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.simstep_load_rff(self._h, w.shape[0], w.shape[1], _ptr(w), _ptr(b), int(bool(split))))
         self.rff_dim, self.rff_in = int(w.shape[0]), int(w.shape[1])
+        self.rff_split_loaded = bool(split)
+        self.rff_split = bool(split)
+
+    def set_rff_split(self, split):
+        """Turn the hi/lo (three-product) evaluation of the random-feature layer on or off (simstep_set_rff_split)."""
+        self._check(self.lib.simstep_set_rff_split(self._h, int(bool(split))))
+        self.rff_split = bool(split)
 
     HEAD_TANH_COS, HEAD_LINEAR = 1, 2
     COST_IDENTITY, COST_GAIL_LS, COST_GAIL_LL = 0, 1, 2

@@ -14,7 +14,8 @@ from . import engine as _engine
 
 class RBFLinearCost:
     def __init__(self, expert_data, feature_dim=1024, input_type="ss", cost_range=[-1.0, 0.0], bw_quantile=0.1,
-                 bw_samples=100000, lambda_b=1.0, lr=0.0, seed=100, precision=None, device=None, split=True):
+                 bw_samples=100000, lambda_b=1.0, lr=0.0, seed=100, precision=None, device=None, split="auto",
+                 split_tol=3e-4):
         torch.manual_seed(seed)  # linear_cost.py:33-35
         np.random.seed(seed)
         self.expert_data = expert_data
@@ -30,7 +31,12 @@ class RBFLinearCost:
         self.bw_samples = bw_samples
         self._precision = precision
         self._device = device
+        # hi/lo operand pairs for the feature GEMM (three products, ~21 mantissa bits into the cosine): True / False, or
+        # "auto": loaded, and switched off by fit_cost when plain operands measurably meet the budget (split_decision)
         self._split = split
+        self._split_tol = float(split_tol)
+        self.split_active = bool(split)  # "auto" starts with the split on
+        self.split_report = None
         self._eng = None
         self.bw = self.fit_bandwidth(expert_data)
         # linear_cost.py:53-55 (the nn.Linear default init consumes RNG before rand_like, as in the reference)
@@ -56,11 +62,50 @@ class RBFLinearCost:
             self._eng = _engine.Engine(state_dim=d, action_dim=0, num_models=1, hidden_sizes=[], dense_connect=True,
                                        transform=False, precision=self._precision, device=self._device)
             self._rff_stamp = None
-        stamp = (self.rff.weight._version, self.rff.bias._version, id(self.rff.weight.data), id(self.rff.bias.data))
+        # (storage address, in-place version) per parameter: `.data` hands out a fresh wrapper on every access, so
+        # its id() is not a stamp; an assignment to `.data` changes data_ptr()
+        stamp = tuple((p.data_ptr(), p._version) for p in (self.rff.weight, self.rff.bias))
         if stamp != self._rff_stamp:
-            self._eng.load_rff(self.rff.weight.data, self.rff.bias.data, split=self._split)
+            self._eng.load_rff(self.rff.weight.data, self.rff.bias.data, split=bool(self._split))
             self._rff_stamp = stamp
+        if self._eng.rff_split_loaded and self._eng.rff_split != self.split_active:
+            self._eng.set_rff_split(self.split_active)
         return self._eng
+
+    def mark_dirty(self):
+        """Force a re-upload of the rff layer on the next use (after replacing a parameter in a way the
+        (data_ptr, version) stamp cannot see)."""
+        self._rff_stamp = None
+
+    @staticmethod
+    def _round_operand(t, precision):
+        """float64 copy of `t` rounded to the tensor-core operand format of `precision`."""
+        t = t.detach().to(torch.float32)
+        if precision == "bf16":
+            return t.to(torch.bfloat16).to(torch.float64)
+        if precision == "tf32":  # 10 explicit mantissa bits, round to nearest (cvt.rna.tf32)
+            bits = t.contiguous().view(torch.int32)
+            bits = (bits + 0x1000) & ~0x1FFF
+            return bits.view(torch.float32).to(torch.float64)
+        return t.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float64)
+
+    def split_decision(self, x, w=None, max_rows=512):
+        """Measured error of the PLAIN (single-product) operand format on rows `x`: the cost phi(x).w evaluated in
+        float64 from exact operands and from operands rounded to the engine's format.  The split stays on where the
+        worst row error exceeds split_tol * max|cost| (3e-4: a third of the north star's 1e-3, the rest is left to
+        the ensemble's own rounding).  Returns {"err", "scale", "split"}."""
+        w = self.w if w is None else w
+        prec = self._precision or _engine.DEFAULT_PRECISION
+        x = torch.as_tensor(x)[:max_rows].detach().cpu()
+        W, b = self.rff.weight.data.cpu(), self.rff.bias.data.cpu().double()
+        scale_phi = float(np.sqrt(2.0 / self.feature_dim))
+        wd = w.detach().cpu().double()
+        exact = (torch.cos(x.double() @ W.double().t() + b) * scale_phi) @ wd
+        plain = (torch.cos(self._round_operand(x, prec) @ self._round_operand(W, prec).t() + b) * scale_phi) @ wd
+        err = float((plain - exact).abs().max())
+        scale = float(exact.abs().max())
+        return {"err": err, "scale": scale, "split": bool(err > self._split_tol * max(scale, 1e-30)),
+                "rows": int(x.shape[0]), "precision": prec, "tol": self._split_tol}
 
     def _expert_features(self, expert_data):
         """(phi(expert) as a CPU tensor, its mean): the mean comes from the device's fp64 column sums."""
@@ -78,6 +123,10 @@ class RBFLinearCost:
         phi = (psum / max(int(data_pi.shape[0]), 1)).float().cpu()
         feat_diff = phi - self.phi_e
         self.w = feat_diff
+        if self._split == "auto":
+            sample = torch.cat([torch.as_tensor(data_pi)[:384].cpu().float(), self.expert_data[:128].cpu().float()])
+            self.split_report = self.split_decision(sample)
+            self.split_active = self.split_report["split"]
         return torch.dot(self.w, feat_diff).item()
 
     def get_costs(self, x):
@@ -157,6 +206,7 @@ class MLPCost(RBFLinearCost):
         self._precision = precision
         self._device = device
         self._eng = None
+        self._split, self.split_active, self.split_report = False, False, None  # no hi/lo pairs for MLP features
         # linear_cost.py:200-216, layer for layer
         self.activation_name = "relu" if activation == "relu" else "tanh"
         self.activation = nn.ReLU() if activation == "relu" else nn.Tanh()

@@ -57,11 +57,25 @@ class VecSimEnv:
     def attach_cost(self, cost):
         """Fuse an RBFLinearCost into the step: loads its rff layer into the ensemble's handle."""
         self.cost = cost
-        self.dynamic_ensemble.engine().load_rff(cost.rff.weight.data, cost.rff.bias.data, split=cost._split)
+        eng = self.dynamic_ensemble.engine()
+        eng.load_rff(cost.rff.weight.data, cost.rff.bias.data, split=bool(cost._split))
         self.set_cost_weights(cost.w)
 
     def set_cost_weights(self, w):
-        self._w_dev = None if w is None else w.detach().to(self.device, torch.float32).contiguous()
+        """Device copy of the cost weights, refreshed IN PLACE (captured CUDA graphs keep pointing at it), and the
+        cost's current hi/lo decision (RBFLinearCost.fit_cost measures it)."""
+        if w is None:
+            self._w_dev = None
+            return
+        w = w.detach().to(self.device, torch.float32).contiguous()
+        if self._w_dev is not None and self._w_dev.shape == w.shape:
+            self._w_dev.copy_(w)
+        else:
+            self._w_dev = w.clone()
+        eng = self.dynamic_ensemble.engine()
+        active = getattr(self.cost, "split_active", None)
+        if active is not None and getattr(eng, "rff_split_loaded", False) and eng.rff_split != bool(active):
+            eng.set_rff_split(bool(active))
 
     # -- gym-like surface -------------------------------------------------------------------
     @staticmethod

@@ -317,6 +317,13 @@ def run_ours(args):
     # cost weights: fit on the first 1024 rollout rows (batch_reinforce.py:113), global mean over ranks
     eng.step(states[0], actions[0], member, steps.clone(), next_state=nxt, disc=disc, done=done)
     w = parallel.global_fit_cost(cost, torch.cat([states[0][:1024], nxt[:1024]], dim=1)).to(device)
+    # hi/lo operand pairs of the cost-feature GEMM only where plain operands measurably miss the budget
+    split_report = cost.split_decision(torch.cat([states[0][:384], nxt[:384]], dim=1).cpu(), w.cpu())
+    use_split = {"auto": split_report["split"], "on": True, "off": False}[args.rff_split]
+    eng.set_rff_split(use_split)
+    split_report["used"] = bool(use_split)
+    if rank == 0:
+        print("rff split decision:", split_report, file=sys.stderr)
     stats = torch.zeros(4, device=device, dtype=torch.float64)
     gathered = torch.zeros(world * 4, device=device, dtype=torch.float64)
 
@@ -491,6 +498,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: no host-buffer pass")
+    ap.add_argument("--rff-split", default="auto", choices=["auto", "on", "off"],
+                    help="hi/lo operand pairs in the cost-feature GEMM: measured decision (auto), always, never")
     ap.add_argument("--graph-check", action="store_true", help="also time the steps replayed from CUDA graphs")
     args = ap.parse_args()
     if args.warmup < 3:

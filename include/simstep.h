@@ -44,8 +44,8 @@ extern "C" {
 #define SIMSTEP_MAX_JOINTS 32
 
 /* operand formats of the tensor-core GEMMs (fp32 accumulate in TMEM) */
-#define SIMSTEP_PREC_TF32 0   /* 10-bit mantissa, 8-bit exponent (default)  */
-#define SIMSTEP_PREC_FP16 1   /* 10-bit mantissa, 5-bit exponent, saturating */
+#define SIMSTEP_PREC_TF32 0   /* 10-bit mantissa, 8-bit exponent: any range    */
+#define SIMSTEP_PREC_FP16 1   /* 10-bit mantissa, 5-bit exponent, saturating: twice the tf32 rate; the host mirror's default */
 #define SIMSTEP_PREC_BF16 2   /* 7-bit mantissa, 8-bit exponent              */
 
 #define SIMSTEP_ACT_RELU 0
@@ -123,6 +123,14 @@ int simstep_set_termination(simstep_handle* h, const simstep_termination* t);
  * running the GEMM on hi/lo operand pairs. */
 int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim,
                      const float* weight_host, const float* bias_host, int32_t split);
+
+/* Switches the hi/lo evaluation of a layer loaded with split != 0 off (one
+ * product, a third of the tensor work, half of the operand-row bytes) or back
+ * on, without re-uploading anything.  The pre-activation W_r x + b_r feeds a
+ * cosine (LC:64-71), so what matters is its ABSOLUTE error: callers measure it
+ * on their own data (amp_extensions_b200.RBFLinearCost does in fit_cost) and
+ * keep the split only where plain operands would miss the 1e-3 budget. */
+int simstep_set_rff_split(simstep_handle* h, int32_t split);
 
 /* ---- ensemble forward --------------------------------------------------- */
 
