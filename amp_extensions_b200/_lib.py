@@ -123,6 +123,8 @@ _SIGNATURES = {
     "simstep_train_export": (C.c_int, [_c_void_p, C.c_int32, C.POINTER(_c_void_p), C.POINTER(_c_void_p)]),
     "simstep_histogram": (C.c_int, [_c_void_p, _c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, _c_void_p,
                                     _c_void_p]),
+    "simstep_quantile_op": (C.c_int, [_c_void_p, C.c_int32, _c_void_p, C.c_int64, C.c_int32, _c_void_p, _c_void_p,
+                                      _c_void_p, _c_void_p]),
     "simstep_reduce_max_sum": (C.c_int, [_c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
     "simstep_profile_enable": (C.c_int, [_c_void_p, C.c_int32]),
     "simstep_profile_read": (C.c_int, [_c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),

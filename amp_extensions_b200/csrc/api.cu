@@ -387,9 +387,12 @@ struct StepTail {
   bool rff = false;  // also write the cost features' operand rows of [s; s'] (input_type 'ss')
 };
 
-// SIMSTEP_FINAL_FUSED=0 keeps the round-1 sequence (final-layer GEMM, then the post-step kernel) for A/B runs
+// SIMSTEP_FINAL_FUSED=1 selects the single-launch final layer + env-step tail (gemm_final.cuh).  It is correct
+// (the parity suite passes with it) but NOT the default: measured on B200 it is slower than the final-layer GEMM
+// followed by the post-step kernel - the final layer is HBM-bound, and the tails' L2 round
+// trips queue behind the operand stream.
 bool final_fused_enabled() {
-  static const bool on = [] { const char* e = std::getenv("SIMSTEP_FINAL_FUSED"); return !(e && e[0] == '0'); }();
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_FINAL_FUSED"); return e && e[0] == '1'; }();
   return on;
 }
 
@@ -496,6 +499,12 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
       ga.out_col0 = 0;
       ga.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
       ga.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
+      // the final layer is HBM-bound (every member re-reads its whole concat row for 226 outputs): run the members
+      // of an env tile side by side (x comes from HBM once) and start with the rows whose last hidden slice the
+      // previous launch wrote last (still in L2).  SIMSTEP_FINAL_ORDER=0 restores the plain order for A/B runs.
+      static const bool order = [] { const char* e = std::getenv("SIMSTEP_FINAL_ORDER"); return !(e && e[0] == '0'); }();
+      ga.group_fastest = order ? 1 : 0;
+      ga.reverse = order ? 1 : 0;
       rc = launch_gemm<kEpiFinal>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_dws, ga,
                                   h->sm_count, st);
     }

@@ -567,6 +567,7 @@ final_fused_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_con
     uint32_t slab_phase = 0;
     bool store_pending = false;
     int next = 0;
+    long long t_idle = clock64();
     while (true) {
       int head = *q_head;
       if (head <= next) {
@@ -575,9 +576,14 @@ final_fused_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_con
           if (head <= next) break;
         } else {
           __nanosleep(200);
+          if (clock64() - t_idle > 8000000000LL) {  // a protocol bug must not hang the GPU: fail the launch instead
+            if (lane == 0) printf("simstep: tail warp %d of block %d starved\n", tq, blockIdx.x);
+            __trap();
+          }
           continue;
         }
       }
+      t_idle = clock64();
       const int block = q_blocks[next % kFinalQueue];
       ++next;
       // acquire: the other CTAs' scratch stores are ordered before their tickets, the last ticket before the

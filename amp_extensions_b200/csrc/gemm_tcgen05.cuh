@@ -200,6 +200,9 @@ __device__ __forceinline__ void combine_row(const CombineArgs& c, long long row,
 struct GemmArgs {
   // tile space: tile -> (group, m_tile, n_tile), n fastest; an m_tile is CG * 128 rows
   int n_inner;            // consecutive n-tiles of one (group, m_tile) a CTA pair runs back to back (0 / 1: none)
+  int group_fastest;      // tile -> (m_tile, group, n_tile): the members of an env tile run side by side on
+                          // neighbouring CTA pairs, so the shared x tile is read from HBM once instead of per member
+  int reverse;            // walk the tile space backwards: the rows the previous layer wrote LAST (still in L2) first
   int m_tiles;
   int n_tiles;
   int groups;
@@ -322,8 +325,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
   const int tile0 = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
   auto tile_of = [&](int it) {
-    const int super = tile0 + (it / n_inner) * tile_step;
-    return super < total_super ? super * n_inner + it % n_inner : -1;
+    int super = tile0 + (it / n_inner) * tile_step;
+    if (super >= total_super) return -1;
+    if (args.reverse) super = total_super - 1 - super;
+    return super * n_inner + it % n_inner;
+  };
+  auto decode = [&](int tile, int& g, int& m_tile, int& n_tile) {
+    n_tile = tile % args.n_tiles;
+    const int t2 = tile / args.n_tiles;
+    if (args.group_fastest) { g = t2 % args.groups; m_tile = t2 / args.groups; }
+    else { m_tile = t2 % args.m_tiles; g = t2 / args.m_tiles; }
   };
   const bool b_resident = SIMSTEP_GEMM_B_RESIDENT != 0 && kb_total <= kStages;
   const int ring = b_resident ? kb_total : kStages;
@@ -334,10 +345,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     uint32_t phase = 0;
     int held_b = -1;  // (group, n-tile) whose weight k-blocks sit in the stages' B halves (B-resident mode)
     for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
-      const int n_tile = tile % args.n_tiles;
-      const int t2 = tile / args.n_tiles;
-      const int m_tile = t2 % args.m_tiles;
-      const int g = t2 / args.m_tiles;
+      int g, m_tile, n_tile;
+      decode(tile, g, m_tile, n_tile);
       const int m_row = (m_tile * CG + int(cta_rank)) * kBlockM;
       const int row_ax = g * args.ax_rows_per_group + m_row;
       const int row_ah = g * args.a_rows_per_group + m_row;
@@ -410,10 +419,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     int store_it = 0;
     float dot = 0.f;  // kEpiRff: feature dot product of this thread's row (carried across a pair's n_inner tiles)
     for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
-      const int n_tile = tile % args.n_tiles;
-      const int t2 = tile / args.n_tiles;
-      const int m_tile = t2 % args.m_tiles;
-      const int g = t2 / args.m_tiles;
+      int g, m_tile, n_tile;
+      decode(tile, g, m_tile, n_tile);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n0 = n_tile * kBlockN;

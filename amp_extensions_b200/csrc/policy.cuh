@@ -291,4 +291,123 @@ histogram_kernel(const float* __restrict__ x, long long n, double lo, double hi,
     if (sh_bins[b]) atomicAdd(&counts[b], static_cast<unsigned long long>(sh_bins[b]));
 }
 
+
+// ---- device-side steps of the distributed quantile (parallel.global_quantile) --------------------------------
+// qstate: per order statistic i in {0, 1}: [4i] window lo, [4i + 1] window hi, [4i + 2] samples below the window,
+// [4i + 3] rank k of the order statistic (all doubles, resident on the device: no host round trip per refinement).
+
+// out[0] = -min(x), out[1] = max(x): one MAX all-reduce makes both global.  Single block, deterministic.
+__global__ void __launch_bounds__(1024)
+quantile_minmax_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  __shared__ float s_mn[32], s_mx[32];
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x + 31) / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    out[0] = -static_cast<double>(mn);
+    out[1] = static_cast<double>(mx);
+  }
+}
+
+// counts[i * bins + b] += samples of window i in bin b (both windows in one pass over x)
+__global__ void __launch_bounds__(256)
+quantile_hist_kernel(const float* __restrict__ x, long long n, const double* __restrict__ qstate, int bins,
+                     unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int sh_bins[];  // [2][bins]
+  for (int b = threadIdx.x; b < 2 * bins; b += blockDim.x) sh_bins[b] = 0u;
+  __syncthreads();
+  double lo[2], hi[2], inv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    lo[i] = qstate[4 * i];
+    hi[i] = qstate[4 * i + 1];
+    inv[i] = hi[i] > lo[i] ? bins / (hi[i] - lo[i]) : 0.0;
+  }
+  for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < n;
+       j += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double v = x[j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (v >= lo[i] && v <= hi[i]) {
+        int b = static_cast<int>(floor((v - lo[i]) * inv[i]));
+        b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+        atomicAdd(&sh_bins[i * bins + b], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2 * bins; b += blockDim.x)
+    if (sh_bins[b]) atomicAdd(&counts[b], static_cast<unsigned long long>(sh_bins[b]));
+}
+
+// Narrows window i to the bin that holds its order statistic: the first bin whose cumulative count (plus the samples
+// below the window) exceeds k.  One block; thread t scans a contiguous run of bins, then a serial pass over the runs.
+__global__ void __launch_bounds__(256)
+quantile_select_kernel(const long long* __restrict__ counts, int bins, double* __restrict__ qstate) {
+  __shared__ long long run_sum[256];
+  for (int i = 0; i < 2; ++i) {
+    const long long* c = counts + static_cast<long long>(i) * bins;
+    const int per = (bins + 255) / 256;
+    const int b0 = threadIdx.x * per, b1 = min(bins, b0 + per);
+    long long s = 0;
+    for (int b = b0; b < b1; ++b) s += c[b];
+    run_sum[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double lo = qstate[4 * i], hi = qstate[4 * i + 1];
+      const long long k = static_cast<long long>(qstate[4 * i + 3]);
+      long long cum = static_cast<long long>(qstate[4 * i + 2]);
+      if (hi > lo) {
+        int t = 0;
+        while (t < 255 && cum + run_sum[t] <= k) cum += run_sum[t++];
+        int b = t * per;
+        const int bend = min(bins, b + per);
+        while (b < bend - 1 && cum + c[b] <= k) cum += c[b++];
+        if (b >= bins) b = bins - 1;
+        const double width = (hi - lo) / bins;
+        qstate[4 * i] = lo + b * width;
+        qstate[4 * i + 1] = lo + (b + 1) * width;
+        qstate[4 * i + 2] = static_cast<double>(cum);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// out[i] = -min{x in window i} (-(+inf) when the window holds none of this rank's samples); single block
+__global__ void __launch_bounds__(1024)
+quantile_winmin_kernel(const float* __restrict__ x, long long n, const double* __restrict__ qstate,
+                       double* __restrict__ out) {
+  __shared__ float s_mn[2][32];
+  float mn[2] = {INFINITY, INFINITY};
+  const double lo0 = qstate[0], hi0 = qstate[1], lo1 = qstate[4], hi1 = qstate[5];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    const double d = v;
+    if (d >= lo0 && d <= hi0) mn[0] = fminf(mn[0], v);
+    if (d >= lo1 && d <= hi1) mn[1] = fminf(mn[1], v);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    for (int off = 16; off > 0; off >>= 1) mn[i] = fminf(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], off));
+    if ((threadIdx.x & 31) == 0) s_mn[i][threadIdx.x >> 5] = mn[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float m = INFINITY;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fminf(m, s_mn[threadIdx.x][w]);
+    out[threadIdx.x] = -static_cast<double>(m);
+  }
+}
+
 }  // namespace simstep

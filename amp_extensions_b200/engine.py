@@ -114,6 +114,9 @@ class Engine:
             _lib.check(self.lib.simstep_create(C.byref(cfg), C.byref(self._h)))
         self.rff_dim = 0
         self.rff_in = 0
+        # bumped by every call that re-allocates device parameters or changes what the step's launches bake in
+        # (load_* / set_*): captured CUDA graphs of an older generation must not be replayed
+        self.generation = 0
 
     # -- lifetime -----------------------------------------------------------------------
     def close(self):
@@ -153,16 +156,19 @@ class Engine:
             tp = (C.c_void_p * 6)(*[t.data_ptr() for t in tfs])
         with torch.cuda.device(self.device):
             self._check(self.lib.simstep_load_ensemble(self._h, wp, bp, tp))
+            self.generation += 1
 
     def set_termination(self, term):
         t = term.to_struct()
         self._check(self.lib.simstep_set_termination(self._h, C.byref(t)))
+        self.generation += 1
 
     def load_rff(self, weight, bias, split=True):
         w = weight.detach().to("cpu", torch.float32).contiguous()
         b = bias.detach().to("cpu", torch.float32).contiguous()
         with torch.cuda.device(self.device):
             self._check(self.lib.simstep_load_rff(self._h, w.shape[0], w.shape[1], _ptr(w), _ptr(b), int(bool(split))))
+            self.generation += 1
         self.rff_dim, self.rff_in = int(w.shape[0]), int(w.shape[1])
         self.rff_split_loaded = bool(split)
         self.rff_split = bool(split)
@@ -170,6 +176,7 @@ class Engine:
     def set_rff_split(self, split):
         """Turn the hi/lo (three-product) evaluation of the random-feature layer on or off (simstep_set_rff_split)."""
         self._check(self.lib.simstep_set_rff_split(self._h, int(bool(split))))
+        self.generation += 1
         self.rff_split = bool(split)
 
     HEAD_TANH_COS, HEAD_LINEAR = 1, 2
@@ -179,6 +186,7 @@ class Engine:
         """What rff_dot / bonus_cost apply to phi(x).w before the bonus combine (COST_*: identity, or GAILCost's
         least-squares / log-likelihood costs of a discriminator output, gail_cost.py:232-246)."""
         self._check(self.lib.simstep_set_cost_transform(self._h, int(transform)))
+        self.generation += 1
 
     def load_feature_net(self, weights, biases, head_weight, head_bias, head_tanh=True, head_mode=None):
         """MLPCost's feature map (linear_cost.py:200-236): hidden nn.Linear layers + the last nn.Linear whose
@@ -195,6 +203,7 @@ class Engine:
             mode = head_mode if head_mode is not None else (self.HEAD_TANH_COS if head_tanh else self.HEAD_LINEAR)
             self._check(self.lib.simstep_load_feature_net(self._h, wp, bp, int(hw.shape[0]), _ptr(hw), _ptr(hb),
                                                           int(mode)))
+            self.generation += 1
         self.rff_dim, self.rff_in = int(hw.shape[0]), self.S
 
     # -- ensemble -----------------------------------------------------------------------
@@ -276,6 +285,14 @@ class Engine:
                                                _stream(self.device)))
         return out
 
+    QOP_MINMAX, QOP_HIST, QOP_SELECT, QOP_WINMIN = 0, 1, 2, 3
+
+    def quantile_op(self, op, x=None, bins=0, qstate=None, counts=None, out=None):
+        """One device-side step of the distributed quantile (simstep_quantile_op); x: contiguous fp32 CUDA vector."""
+        n = 0 if x is None else x.numel()
+        self._check(self.lib.simstep_quantile_op(self._h, int(op), _ptr(x), n, int(bins), _ptr(qstate), _ptr(counts),
+                                                 _ptr(out), _stream(self.device)))
+
     def reduce_max_sum(self, x, out=None):
         """[max, sum] of a device vector as fp64 (written into `out` when given)."""
         x = _dev_f32(x, self.device)
@@ -306,6 +323,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.simstep_load_clip(self._h, C.byref(ch), fr.shape[0], _ptr(fr), _ptr(fv), _ptr(ft),
                                                    float(clip.duration), int(bool(clip.loop_wrap)), _ptr(cd)))
+            self.generation += 1
         self.dof = int(fr.shape[1])
         self.n_joints = int(ch.n_joints)
 
@@ -363,6 +381,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.simstep_load_policy(self._h, nl, lin, lout, wp, bp, int(nonlinearity == "tanh"),
                                                      *[_ptr(x) for x in extra]))
+            self.generation += 1
         self.policy_obs_dim, self.policy_act_dim = int(ws[0].shape[1]), int(ws[-1].shape[0])
 
     def policy_act(self, obs, noise=None, action=None, mean=None, want_mean=True):

@@ -72,6 +72,15 @@ class RBFLinearCost:
             self._eng.set_rff_split(self.split_active)
         return self._eng
 
+    def _precise_engine(self):
+        """The engine with the hi/lo split forced on when it was loaded with that capability: feature MEANS (phi_e,
+        fit_cost's w, get_expert_cost) are differences of nearly equal averages, where a rounding bias that is
+        harmless per row is not; they are computed once per iteration on a few thousand rows."""
+        eng = self.engine()
+        if getattr(eng, "rff_split_loaded", False) and not eng.rff_split:
+            eng.set_rff_split(True)
+        return eng
+
     def mark_dirty(self):
         """Force a re-upload of the rff layer on the next use (after replacing a parameter in a way the
         (data_ptr, version) stamp cannot see)."""
@@ -109,7 +118,7 @@ class RBFLinearCost:
 
     def _expert_features(self, expert_data):
         """(phi(expert) as a CPU tensor, its mean): the mean comes from the device's fp64 column sums."""
-        phi, psum = self.engine().rff_features(expert_data, want_sum=True)
+        phi, psum = self._precise_engine().rff_features(expert_data, want_sum=True)
         return phi.cpu(), (psum / max(int(expert_data.shape[0]), 1)).float().cpu()
 
     def get_rep(self, x):
@@ -119,7 +128,7 @@ class RBFLinearCost:
 
     def fit_cost(self, data_pi):
         """linear_cost.py:84-94: w = mean phi(pi) - mean phi(expert); returns w.w."""
-        _, psum = self.engine().rff_features(data_pi, want_sum=True)
+        _, psum = self._precise_engine().rff_features(data_pi, want_sum=True)
         phi = (psum / max(int(data_pi.shape[0]), 1)).float().cpu()
         feat_diff = phi - self.phi_e
         self.w = feat_diff
@@ -139,7 +148,7 @@ class RBFLinearCost:
     def get_expert_cost(self):
         """linear_cost.py:105-109: (1 - lambda_b) * mean(clamp(phi(expert) . w)), evaluated on the device: the combine
         kernel's `ipm` output is (1 - lambda_b) * clamp(.), its mean comes from the fp64 moments kernel."""
-        eng = self.engine()
+        eng = self._precise_engine()
         x = self.expert_data.float()
         zeros = torch.zeros(x.shape[0], device=eng.device, dtype=torch.float32)
         clamp = self.cost_range is not None

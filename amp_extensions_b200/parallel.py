@@ -91,7 +91,7 @@ def global_threshold(ensemble):
 
 def global_fit_cost(cost, data_pi_local):
     """RBFLinearCost.fit_cost with the rollout rows sharded across ranks: w = global mean phi - phi_e."""
-    eng = cost.engine()
+    eng = cost._precise_engine() if hasattr(cost, "_precise_engine") else cost.engine()
     n_local = int(data_pi_local.shape[0])
     if n_local > 0:
         _, psum = eng.rff_features(data_pi_local, want_sum=True)
@@ -155,13 +155,53 @@ def rollout_stats(cost, ipm, bonus, done, num_steps):
     }
 
 
+def _global_quantile_device(x32, q, bins, refine, engine):
+    """Device-resident variant: the windows around the two bracketing order statistics live in device memory
+    (simstep_quantile_op), so the call issues 1 all-gather of [-min, max, count], refine + 1 all-reduces of the
+    two histograms and 1 all-reduce of the window minima - and synchronises with the host ONCE, for the result."""
+    dev = x32.device
+    f64 = dict(device=dev, dtype=torch.float64)
+    bins = min(int(bins), 4096)
+    head = torch.empty(3, **f64)
+    engine.quantile_op(engine.QOP_MINMAX, x32, out=head)
+    head[2] = float(x32.numel())
+    if is_dist():
+        allh = torch.empty(world_size() * 3, **f64)
+        dist.all_gather_into_tensor(allh, head)
+        allh = allh.view(-1, 3)
+        mm, n = allh[:, :2].max(dim=0).values, allh[:, 2].sum()
+    else:
+        mm, n = head[:2], head[2]
+    lo, hi = -mm[0], mm[1]
+    pos = q * (n - 1.0)
+    k0 = torch.floor(pos).clamp_min(0.0)
+    frac = (pos - k0).clamp(0.0, 1.0)
+    k1 = torch.minimum(k0 + 1.0, (n - 1.0).clamp_min(0.0))
+    zero = torch.zeros((), **f64)
+    qstate = torch.stack([lo, hi, zero, k0, lo, hi, zero, k1]).contiguous()
+    counts = torch.empty(2 * bins, device=dev, dtype=torch.int64)
+    for _ in range(int(refine) + 1):
+        engine.quantile_op(engine.QOP_HIST, x32, bins=bins, qstate=qstate, counts=counts)
+        _all_reduce(counts, dist.ReduceOp.SUM)
+        engine.quantile_op(engine.QOP_SELECT, None, bins=bins, qstate=qstate, counts=counts)
+    out = torch.empty(2, **f64)
+    engine.quantile_op(engine.QOP_WINMIN, x32, qstate=qstate, out=out)
+    _all_reduce(out, dist.ReduceOp.MAX)
+    v0, v1 = -out[0], -out[1]
+    res = torch.where(n > 0, v0 + frac * (v1 - v0), torch.full((), float("nan"), **f64))
+    return float(res.item())
+
+
 def global_quantile(x_local, q, bins=4096, refine=2, engine=None):
     """q-quantile (linear interpolation between order statistics, as torch.quantile) of the union of every
     rank's x_local, without gathering the samples: all-reduce of min/max and of fixed-range histograms, refined
     `refine` times around the two order statistics that bracket the quantile.  Exact up to the final bin width
     (range / bins**(refine+1)); used for threshold_mode='quantile', an extension over the reference's dataset
-    maximum.  With `engine` (and a CUDA fp32 vector) the histograms are taken by libsimstep's histogram kernel;
-    without it (CPU tensors in the gloo tests) by torch."""
+    maximum.  With `engine` and a CUDA fp32 vector everything but the final read stays on the device
+    (_global_quantile_device); CPU tensors (the gloo tests) take the torch path below."""
+    xt = torch.as_tensor(x_local)
+    if engine is not None and xt.is_cuda and xt.dtype == torch.float32:
+        return _global_quantile_device(xt.reshape(-1).contiguous(), float(q), bins, refine, engine)
     x32 = torch.as_tensor(x_local).reshape(-1) if engine is not None else None
     x = torch.as_tensor(x_local).to(torch.float64).reshape(-1)
     dev = x.device

@@ -194,11 +194,18 @@ class DeviceRollout:
         env = self.env
         E, S, A = env.num_envs, env.state_size, env.action_size
         c = env.cost
-        key = (T, bool(eval_mode), use_cost, float(env.dynamic_ensemble.threshold or 0.0) if use_cost else 0.0,
-               float(c.lambda_b) if use_cost else 0.0, env._w_dev.data_ptr() if use_cost else 0, env.ob.data_ptr(),
-               env.member.data_ptr(), env.num_steps.data_ptr())
+        clamp = use_cost and c.cost_range is not None
+        # everything a captured launch bakes in: shapes, scalar arguments, the buffers it points at, and the
+        # engine's parameter generation (load_policy / load_rff / set_rff_split re-allocate or re-plan)
+        key = (T, bool(eval_mode), use_cost, self.eng.generation,
+               float(env.dynamic_ensemble.threshold or 0.0) if use_cost else 0.0,
+               float(c.lambda_b) if use_cost else 0.0, bool(clamp),
+               (float(c.c_min), float(c.c_max)) if clamp else (0.0, 0.0),
+               env._w_dev.data_ptr() if use_cost else 0, env.ob.data_ptr(), env.member.data_ptr(),
+               env.num_steps.data_ptr(), self.pool.data_ptr())
         ent = self._graphs.get(key)
         if ent is None:
+            self._graphs.clear()  # one entry: a stale graph pins a whole T x E batch and may point at freed memory
             batch = RolloutBatch(self.eng, T, E, S, A, use_cost)
             s_noise = None if eval_mode else torch.zeros((T, E, A), device=self.device, dtype=torch.float32)
             s_pick = torch.zeros((T, E), device=self.device, dtype=torch.int32)

@@ -360,6 +360,21 @@ int simstep_train_export(simstep_handle* h, int32_t what, float* const* weights_
 int simstep_histogram(simstep_handle* h, const float* x_dev, int64_t n, double lo, double hi, int32_t bins,
                       int64_t* counts_dev, void* stream);
 
+/* Device-side steps of the distributed q-quantile (amp_extensions_b200.parallel.global_quantile): the windows that
+ * bracket the two order statistics live in device memory, so a refinement costs no host round trip.
+ * qstate_dev: 8 doubles, for order statistic i in {0, 1}: [4i] window lo, [4i+1] window hi, [4i+2] number of
+ * samples below the window, [4i+3] rank k of the order statistic.  Every op only enqueues work on `stream`.
+ *   MINMAX: out_dev[0] = -min(x), out_dev[1] = max(x)              (one all-reduce MAX makes both global)
+ *   HIST:   counts_dev[i*bins + b] (int64, overwritten) = samples of window i in bin b, 1 <= bins <= 4096
+ *   SELECT: narrows both windows to the bin that holds their order statistic, given the (all-reduced) counts
+ *   WINMIN: out_dev[i] = -min{x in window i}                       (all-reduce MAX, negate: the order statistic) */
+#define SIMSTEP_QOP_MINMAX 0
+#define SIMSTEP_QOP_HIST 1
+#define SIMSTEP_QOP_SELECT 2
+#define SIMSTEP_QOP_WINMIN 3
+int simstep_quantile_op(simstep_handle* h, int32_t op, const float* x_dev, int64_t n, int32_t bins, double* qstate_dev,
+                        int64_t* counts_dev, double* out_dev, void* stream);
+
 /* out_dev[0] = max_e x[e], out_dev[1] = sum_e x[e] (fp64 accumulate), n may be 0. */
 int simstep_reduce_max_sum(simstep_handle* h, const float* x_dev, int64_t n, double* out_dev, void* stream);
 

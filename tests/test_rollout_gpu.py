@@ -291,6 +291,56 @@ def test_graph_replay_equals_eager_loop():
             assert torch.equal(v, outs[1][k][n]), (k, n)
 
 
+def test_graph_replay_survives_policy_and_cost_reloads():
+    """load_policy() frees and re-allocates the packed policy, attach_cost() / set_cost_weights() the rff
+    buffers and weights - a graph captured before must not be replayed afterwards.  The cache key carries the engine's
+    parameter generation and holds one entry: collect(graph=True) after a reload equals the eager loop with the NEW
+    parameters, and the cache does not grow."""
+    from amp_extensions_b200 import (AmpDataset, DynamicsEnsemble, HumanoidTermination, RBFLinearCost, VecSimEnv)
+    from amp_extensions_b200.rollout import DeviceRollout
+    c = H.tiny_case("tiny_dense")
+    S, A = c["S"], c["A"]
+    s, a, s2 = c["ds"]
+    ens = DynamicsEnsemble(S, A, AmpDataset(s, a, s2), None, num_models=c["N"], hidden_sizes=c["hidden"],
+                           dense_connect=True, transform=True, base_seed=100)
+    ens.threshold = 0.5
+    cost = RBFLinearCost(torch.cat([s[:64], s2[:64]], dim=1), feature_dim=64, input_type="ss", bw_quantile=0.1,
+                         lambda_b=0.1, seed=3)
+    cost.fit_cost(torch.cat([s[64:128], s2[64:128]], dim=1))
+    g = torch.Generator().manual_seed(0)
+
+    def policy(scale):
+        ws = [torch.randn(8, S, generator=g) * scale, torch.randn(A, 8, generator=g) * scale]
+        return _Policy(_FC(ws, [torch.zeros(8), torch.zeros(A)], "tanh"), np.full(A, -1.0, np.float32))
+
+    T, E = 5, 40
+    noise = torch.randn(3, T, E, A, generator=g).cuda()
+    pick = torch.randint(0, 32, (3, T, E), generator=g, dtype=torch.int32).cuda()
+    pols = [policy(0.1), policy(0.3), policy(0.2)]
+    ws_cost = [cost.w.clone(), cost.w * -2.0, cost.w * 0.5]
+    outs = []
+    for use_graph in (False, True):
+        env = VecSimEnv(ens, E, termination=HumanoidTermination(horizon=4, fall_contact_bodies=()),
+                        reset_states=s[:32], seed=0, cost=cost)
+        env.reset(initial_states=s[:E])
+        ro_dev = DeviceRollout(env, pols[0], seed=0)
+        got = []
+        for k in range(3):
+            ro_dev.load_policy(pols[k])            # re-allocates the packed policy on the device
+            if k == 1:
+                env.attach_cost(cost)              # re-allocates the rff buffers
+            env.set_cost_weights(ws_cost[k])       # in place after the first call
+            b = ro_dev.collect(T, noise=noise[k], pick=pick[k], graph=use_graph)
+            got.append({n: getattr(b, n).clone() for n in ("observations", "actions", "cost", "done")})
+            if use_graph:
+                assert len(ro_dev._graphs) == 1
+        outs.append(got)
+    for k in range(3):
+        for n, v in outs[0][k].items():
+            assert torch.equal(v, outs[1][k][n]), (k, n)
+    assert not torch.equal(outs[1][0]["actions"], outs[1][1]["actions"])  # the reloads did change the results
+
+
 def test_moments_and_whitening_match_numpy():
     """compute_advantages(normalize=True) (process_samples.py:14-19): numpy float64 mean / population std."""
     _, eng = _tiny_engine()
