@@ -327,12 +327,12 @@ class Engine:
         self.dof = int(fr.shape[1])
         self.n_joints = int(ch.n_joints)
 
-    def imitation_reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False):
+    def imitation_reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False, out=None):
         pose, vel = _dev_f32(pose, self.device), _dev_f32(vel, self.device)
         kin_time = _dev_f32(kin_time, self.device)
         kin_origin = _dev_f32(kin_origin, self.device) if kin_origin is not None else None
         E = pose.shape[0]
-        reward = torch.empty((E,), device=self.device, dtype=torch.float32)
+        reward = out if out is not None else torch.empty((E,), device=self.device, dtype=torch.float32)
         terms = torch.empty((E, 5), device=self.device, dtype=torch.float32) if want_terms else None
         self._check(self.lib.simstep_imitation_reward(self._h, _ptr(pose), _ptr(vel), _ptr(kin_time),
                                                       _ptr(kin_origin), E, _ptr(reward), _ptr(terms),

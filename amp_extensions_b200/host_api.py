@@ -134,10 +134,49 @@ class HostStepPipeline:
         return self.collect()
 
 
+class _Record:
+    """One env group's device state + step outputs as ONE contiguous byte buffer per chunk, mirrored by one pinned
+    host buffer: a chunk's results leave the device with a single copy.  Chunk layout (n rows):
+    [next_state n x S f32 | cost n f32 | disc n f32 | num_steps n i32 | done n u8 | pad to 256 B]; the optional
+    blocks (disc, num_steps) are dropped when the caller does not want them back."""
+
+    def __init__(self, eng, bounds, with_cost, want_disc, want_steps, pinned_mirror):
+        S = eng.S
+        self.bounds = bounds
+        self.chunks = []
+        off = 0
+        for (r0, r1) in bounds:
+            n = r1 - r0
+            lay, o = {}, 0
+            lay["next"] = (o, n * S * 4); o += n * S * 4
+            if with_cost:
+                lay["cost"] = (o, n * 4); o += n * 4
+            if want_disc:
+                lay["disc"] = (o, n * 4); o += n * 4
+            if want_steps:
+                lay["steps"] = (o, n * 4); o += n * 4
+            lay["done"] = (o, n); o += n
+            size = -(-o // 256) * 256
+            self.chunks.append((off, size, lay))
+            off += size
+        self.nbytes = off
+        self.dev = torch.empty(off, device=eng.device, dtype=torch.uint8)
+        self.host = torch.empty(off, dtype=torch.uint8, pin_memory=True) if pinned_mirror else None
+        self.payload_bytes = sum(sum(sz for (_, sz) in lay.values()) for (_, _, lay) in self.chunks)
+
+    def view(self, buf, ci, name, dtype, shape):
+        off, _, lay = self.chunks[ci]
+        if name not in lay:
+            return None
+        o, sz = lay[name]
+        return buf[off + o: off + o + sz].view(dtype).view(shape)
+
+
 class HostEnvPipeline:
     """The reference plugin's own call shape, batched: `step(actions) -> (obs, cost, done, ...)` with the env state
     RESIDENT on the device (gym-simenv/gym_simenv/envs/sim_env.py:140-162 keeps `self.ob` inside the env and takes
-    only the action).  Per step only the actions cross PCIe host->device; observations, costs and flags come back.
+    only the action).  Per step only the actions cross PCIe host->device; observations, costs and flags come back
+    as one packed record per chunk (one device->host copy each; disc / step counters only on request).
 
     `groups` independent groups of E envs alternate (submit / collect), so group g+1's action upload and group
     g-1's result download overlap group g's compute — a sampler that steps two sets of environments in turn.
@@ -148,7 +187,7 @@ class HostEnvPipeline:
         obs_h, cost_h, done_h, disc_h, steps_h = pipe.collect()       # group 0's results
     """
 
-    def __init__(self, engine, num_envs, groups=2, n_chunks=2, with_cost=True):
+    def __init__(self, engine, num_envs, groups=2, n_chunks=2, with_cost=True, want_disc=True, want_steps=True):
         self.eng, self.E, self.with_cost = engine, int(num_envs), with_cost
         dev, S, A, E = engine.device, engine.S, engine.A, self.E
         n_chunks = max(1, min(int(n_chunks), (E + 255) // 256))
@@ -157,13 +196,36 @@ class HostEnvPipeline:
         self.groups = []
         f32 = dict(device=dev, dtype=torch.float32)
         for _ in range(int(groups)):
-            g = _Slot(engine, E)
-            g.d_state2 = torch.empty((E, S), **f32)   # ping-pong partner of d_state
+            g = type("Group", (), {})()
+            # two records alternate: the step reads its state from one and writes s' (+ outputs) into the other
+            g.rec = [_Record(engine, self.bounds, with_cost, True, True, pinned_mirror=False) for _ in range(2)]
+            g.cur = 0
+            g.d_action = torch.empty((E, A), **f32)
+            g.d_member = torch.zeros((E,), device=dev, dtype=torch.int32)
+            g.d_steps = torch.zeros((E,), device=dev, dtype=torch.int32)
+            g.d_ipm = torch.empty((E,), **f32)
+            g.d_bonus = torch.empty((E,), **f32)
+            g.host = torch.empty(g.rec[0].nbytes, dtype=torch.uint8, pin_memory=True)
+            g.ev_compute_done = None
+            g.ev_out_done = None
             self.groups.append(g)
+        self.want_disc, self.want_steps = bool(want_disc), bool(want_steps)
         self._inflight = collections.deque()
         self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.h2d_bytes_per_step = E * A * 4
-        self.d2h_bytes_per_step = E * (S * 4 + 4 + 1 + 4 + (4 if with_cost else 0))
+        # bytes a step actually brings back: the record's payload minus the blocks the caller opted out of
+        self.d2h_bytes_per_step = E * (S * 4 + 1 + (4 if with_cost else 0) + (4 if want_disc else 0) +
+                                       (4 if want_steps else 0))
+
+    def _views(self, g, r, ci, buf):
+        (r0, r1) = self.bounds[ci]
+        n, S = r1 - r0, self.eng.S
+        rec = g.rec[r]
+        return dict(next=rec.view(buf, ci, "next", torch.float32, (n, S)),
+                    cost=rec.view(buf, ci, "cost", torch.float32, (n,)),
+                    disc=rec.view(buf, ci, "disc", torch.float32, (n,)),
+                    steps=rec.view(buf, ci, "steps", torch.int32, (n,)),
+                    done=rec.view(buf, ci, "done", torch.uint8, (n,)))
 
     def reset(self, group, state_h, member_h=None, steps_h=None):
         """(Re)start every env of a group from host-supplied initial states (the reference draws them from the
@@ -172,7 +234,8 @@ class HostEnvPipeline:
         cur = torch.cuda.current_stream(self.eng.device)
         for s in (self.s_in, self.s_compute, self.s_out):
             cur.wait_stream(s)
-        g.d_state.copy_(state_h, non_blocking=True)
+        for ci, (r0, r1) in enumerate(self.bounds):
+            self._views(g, g.cur, ci, g.rec[g.cur].dev)["next"].copy_(state_h[r0:r1], non_blocking=True)
         if member_h is None:
             g.d_member.zero_()
         else:
@@ -190,45 +253,72 @@ class HostEnvPipeline:
         eng, g = self.eng, self.groups[group]
         if g in self._inflight:
             raise RuntimeError("HostEnvPipeline: collect() this group's previous step before submitting the next")
-        if g.ev_out_done is not None:          # the previous results must have left d_next / d_cost ...
+        if g.ev_out_done is not None:          # the previous results must have left the record ...
             self.s_compute.wait_event(g.ev_out_done)
         if g.ev_compute_done is not None:      # ... and the previous step must have consumed its actions
             self.s_in.wait_event(g.ev_compute_done)
+        src, dst = g.cur, 1 - g.cur
         ev_c = None
-        for (r0, r1) in self.bounds:
+        for ci, (r0, r1) in enumerate(self.bounds):
             with torch.cuda.stream(self.s_in):
                 g.d_action[r0:r1].copy_(action_h[r0:r1], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
+            vin = self._views(g, src, ci, g.rec[src].dev)
+            vout = self._views(g, dst, ci, g.rec[dst].dev)
             with torch.cuda.stream(self.s_compute):
                 self.s_compute.wait_event(ev_in)
                 if self.with_cost:
-                    eng.step_cost(g.d_state[r0:r1], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1], w_dev,
-                                  lambda_b, threshold, c_min, c_max, clamp_cost, next_state=g.d_state2[r0:r1],
-                                  disc=g.d_disc[r0:r1], done=g.d_done[r0:r1], cost=g.d_cost[r0:r1],
-                                  ipm=g.d_ipm[r0:r1], bonus=g.d_bonus[r0:r1])
+                    eng.step_cost(vin["next"], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1], w_dev,
+                                  lambda_b, threshold, c_min, c_max, clamp_cost, next_state=vout["next"],
+                                  disc=vout["disc"], done=vout["done"], cost=vout["cost"], ipm=g.d_ipm[r0:r1],
+                                  bonus=g.d_bonus[r0:r1])
                 else:
-                    eng.step(g.d_state[r0:r1], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1],
-                             next_state=g.d_state2[r0:r1], disc=g.d_disc[r0:r1], done=g.d_done[r0:r1])
+                    eng.step(vin["next"], g.d_action[r0:r1], g.d_member[r0:r1], g.d_steps[r0:r1],
+                             next_state=vout["next"], disc=vout["disc"], done=vout["done"])
+                if self.want_steps:
+                    vout["steps"].copy_(g.d_steps[r0:r1], non_blocking=True)
                 ev_c = torch.cuda.Event()
                 ev_c.record(self.s_compute)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_c)
-                g.h_next[r0:r1].copy_(g.d_state2[r0:r1], non_blocking=True)
-                g.h_disc[r0:r1].copy_(g.d_disc[r0:r1], non_blocking=True)
-                g.h_done[r0:r1].copy_(g.d_done[r0:r1], non_blocking=True)
-                g.h_steps[r0:r1].copy_(g.d_steps[r0:r1], non_blocking=True)
-                if self.with_cost:
-                    g.h_cost[r0:r1].copy_(g.d_cost[r0:r1], non_blocking=True)
-        g.d_state, g.d_state2 = g.d_state2, g.d_state   # s' is the next step's state; it never left the device
+                off, size, lay = g.rec[dst].chunks[ci]
+                if self.want_disc and self.want_steps:
+                    g.host[off:off + size].copy_(g.rec[dst].dev[off:off + size], non_blocking=True)  # ONE copy
+                else:  # opted-out blocks stay on the device: copy the blocks around them
+                    for name in ("next", "cost", "disc", "steps", "done"):
+                        if name in lay and (name != "disc" or self.want_disc) and (name != "steps" or self.want_steps):
+                            o, sz = lay[name]
+                            g.host[off + o: off + o + sz].copy_(g.rec[dst].dev[off + o: off + o + sz],
+                                                               non_blocking=True)
+        g.cur = dst   # s' is the next step's state; it never left the device
         g.ev_compute_done = ev_c
         g.ev_out_done = torch.cuda.Event()
         g.ev_out_done.record(self.s_out)
         self._inflight.append(g)
 
     def collect(self):
-        """Wait for the oldest in-flight step.  Returns pinned host tensors (obs [E,S], cost [E] or None, done [E]
-        uint8, disc [E], num_steps [E]), valid until that group is submitted again."""
+        """Wait for the oldest in-flight step.  Returns pinned host tensors (obs, cost or None, done uint8, disc or
+        None, num_steps or None), each a list-free view when the batch is one chunk and otherwise per-chunk views
+        concatenated lazily: use `collect_chunks()` to avoid the concatenation.  Valid until that group is submitted
+        again."""
+        chunks = self.collect_chunks()
+        if len(chunks) == 1:
+            c = chunks[0]
+            return c["next"], c["cost"], c["done"], c["disc"], c["steps"]
+        cat = lambda k: None if chunks[0][k] is None else torch.cat([c[k] for c in chunks])  # noqa: E731
+        return cat("next"), cat("cost"), cat("done"), cat("disc"), cat("steps")
+
+    def collect_chunks(self):
+        """Per-chunk views (dicts with next / cost / done / disc / steps) into the group's pinned record: no copy."""
         g = self._inflight.popleft()
         g.ev_out_done.synchronize()
-        return g.h_next, (g.h_cost if self.with_cost else None), g.h_done, g.h_disc, g.h_steps
+        out = []
+        for ci in range(len(self.bounds)):
+            v = self._views(g, g.cur, ci, g.host)
+            if not self.want_disc:
+                v["disc"] = None
+            if not self.want_steps:
+                v["steps"] = None
+            out.append(v)
+        return out

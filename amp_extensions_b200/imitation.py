@@ -26,10 +26,11 @@ class ImitationReward:
         self.engine.load_clip(self.character, self.clip)
         self.dof = self.character.dof
 
-    def reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False):
+    def reward(self, pose, vel, kin_time, kin_origin=None, want_terms=False, out=None):
         """pose, vel: [E, dof]; kin_time: [E] seconds; kin_origin: [E, 3] or None.
-        Returns reward [E] (and the five sub-rewards pose, vel, end-effector, root, com as [E, 5])."""
-        return self.engine.imitation_reward(pose, vel, kin_time, kin_origin, want_terms=want_terms)
+        Returns reward [E] (written into `out` when given; and the five sub-rewards pose, vel, end-effector, root,
+        com as [E, 5])."""
+        return self.engine.imitation_reward(pose, vel, kin_time, kin_origin, want_terms=want_terms, out=out)
 
     def sample(self, kin_time, kin_origin=None):
         """Pose and velocity of the kinematic character at the given clip times: ([E, dof], [E, dof])."""

@@ -159,8 +159,79 @@ def _make_box(dim):
         return _Box(low, high, np.float64)
 
 
-class SimEnv:
+def _env_base():
+    """gym.Env (or gymnasium.Env) when one of them is importable, so that gym.make / wrappers accept the class;
+    a plain object otherwise.  The reference subclasses gym.Env and EzPickle (sim_env.py:13)."""
+    for mod in ("gym", "gymnasium"):
+        try:  # pragma: no cover - optional dependency
+            return __import__(mod).Env
+        except Exception:
+            continue
+    return object
+
+
+class _SingleStep:
+    """SimEnv.step's device side for ONE env: a packed pinned record in (ob | action | step counter | member), the
+    step's launches, a packed pinned record out (next state | disc | done) - one host->device copy, one
+    device->host copy, one synchronisation, and the three replayed from a CUDA graph."""
+
+    def __init__(self, ensemble, termination, use_graph=True):
+        self.eng = eng = ensemble.engine()
+        eng.set_termination(termination)
+        S, A, dev = eng.S, eng.A, eng.device
+        self.S, self.A = S, A
+        self.h_in = torch.zeros(S + A + 2, dtype=torch.float32, pin_memory=True)
+        self.d_in = torch.zeros(S + A + 2, device=dev, dtype=torch.float32)
+        self.h_out = torch.zeros((S + 2) * 4, dtype=torch.uint8, pin_memory=True)
+        self.d_out = torch.zeros((S + 2) * 4, device=dev, dtype=torch.uint8)
+        self.np_in = self.h_in.numpy()
+        self.np_in_i = self.h_in.view(torch.int32).numpy()
+        self.np_out_f = self.h_out.view(torch.float32).numpy()
+        self.np_out_b = self.h_out.numpy()
+        self.v_ob = self.d_in[:S].view(1, S)
+        self.v_act = self.d_in[S:S + A].view(1, A)
+        ints = self.d_in[S + A:].view(torch.int32)
+        self.v_steps, self.v_member = ints[0:1], ints[1:2]
+        outf = self.d_out.view(torch.float32)
+        self.v_next = outf[:S].view(1, S)
+        self.v_disc = outf[S:S + 1]
+        self.v_done = self.d_out[(S + 1) * 4:(S + 1) * 4 + 1]
+        self.stream = torch.cuda.Stream(dev)
+        self.use_graph = use_graph
+        self.graph, self.graph_gen = None, -1
+
+    def _enqueue(self):
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self.eng.step(self.v_ob, self.v_act, self.v_member, self.v_steps, next_state=self.v_next, disc=self.v_disc,
+                      done=self.v_done)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def step(self, ob, action, num_steps, member):
+        S, A = self.S, self.A
+        self.np_in[:S] = ob
+        self.np_in[S:S + A] = action
+        self.np_in_i[S + A] = num_steps
+        self.np_in_i[S + A + 1] = member
+        with torch.cuda.stream(self.stream):
+            if self.use_graph and (self.graph is None or self.graph_gen != self.eng.generation):
+                self._enqueue()                      # eager once: workspace allocation, kernel attributes
+                self.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._enqueue()
+                self.graph, self.graph_gen = g, self.eng.generation
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+        self.stream.synchronize()
+        return (self.np_out_f[:S].astype(np.float64), float(self.np_out_f[S]), bool(self.np_out_b[(S + 1) * 4]))
+
+
+class SimEnv(_env_base()):
     """Single-environment surface of the reference SimEnv (sim_env.py:13-288), same kwargs."""
+
+    metadata = {"render.modes": ["human"], "render_modes": ["human"]}
 
     def __init__(self, dynamic_ensemble, deepmimic_args=None, enable_velocity_check=False, horizon=300,
                  device=torch.device("cpu"), seed=None,
@@ -195,6 +266,7 @@ class SimEnv:
         self.dynamics = dynamic_ensemble.models[0]
         self.dynamics.model.eval()
         self._vec = None
+        self._fast = None
 
     # The reference builds its termination tables from the DeepMimic arg/character/controller files
     # (sim_env.py:84-116); do the same when they are available.
@@ -244,18 +316,18 @@ class SimEnv:
     def step(self, action):
         """sim_env.py:140-162: ob += member forward; reward 0; done from is_done(); info tolerates ['valid']."""
         assert self.ob is not None
-        vec = self._vec_env()
-        vec.ob.copy_(torch.from_numpy(np.asarray(self.ob, dtype=np.float64)).float().unsqueeze(0))
-        vec.num_steps.fill_(self.num_steps)
-        vec.member.fill_(self.reset_counter)
-        ob, _, done, info = vec.step(torch.from_numpy(np.asarray(action, dtype=np.float64)).float().unsqueeze(0),
-                                     with_cost=False)
-        self.num_steps += 1
+        if self._fast is None:
+            term = self._termination or HumanoidTermination(horizon=self.horizon,
+                                                            enable_velocity_check=self.enable_velocity_check)
+            self._fast = _SingleStep(self.dynamic_ensemble, term)
         # device state is fp32; the observation handed back is its exact float64 widening (the reference keeps a
         # float64 accumulator, sim_env.py:158, but feeds the model the fp32 cast of it, sim_env.py:155)
-        self.ob = ob[0].double().cpu().numpy()
-        self._last_done = bool(done[0].item())
-        self._last_disc = float(info["disc"][0].item())
+        ob, disc, done = self._fast.step(np.asarray(self.ob, dtype=np.float64), np.asarray(action, dtype=np.float64),
+                                         self.num_steps, self.reset_counter)
+        self.num_steps += 1
+        self.ob = ob
+        self._last_done = done
+        self._last_disc = disc
         return copy.deepcopy(self.ob), 0, self._last_done, {"valid": True, "disc": self._last_disc}
 
     def is_done(self):
@@ -271,7 +343,9 @@ class SimEnv:
             self.deepmimic.reset_time(**self.reset_dict)
             self.ob = np.asarray(self.deepmimic.record_state(0), dtype=np.float64)
         elif self._reset_fn is not None:
-            self.ob = np.asarray(self._reset_fn(1, self.np_random), dtype=np.float64).reshape(-1).copy()
+            s0 = self._reset_fn(1, self.np_random)   # may be a CUDA tensor (VecSimEnv.clip_reset_fn)
+            s0 = s0.detach().cpu().numpy() if torch.is_tensor(s0) else np.asarray(s0)
+            self.ob = np.asarray(s0, dtype=np.float64).reshape(-1).copy()
         elif self._reset_states is not None:
             i = self.np_random.randint(0, len(self._reset_states))
             self.ob = np.asarray(self._reset_states[i], dtype=np.float64).copy()
@@ -286,9 +360,13 @@ class SimEnv:
     def render(self, mode="human", close=False):
         pass
 
+    def close(self):
+        self._fast = None
+        self._vec = None
+
     # EzPickle-equivalent: re-create from ctor args, dropping device state (sim_env.py:48)
     def __getstate__(self):
-        return self._ctor
+        return self._ctor  # the device handle, streams and graphs are re-created lazily in the new process
 
     def __setstate__(self, d):
         self.__init__(**d)

@@ -428,6 +428,44 @@ def test_device_rollout_matches_the_reference_sampler():
             assert collision_margin(g["next_observations"][k, t][None])[0] < 1e-3, (k, first, n)
 
 
+def test_sampler_shim_matches_the_reference_sampler_on_gpu():
+    """amp_extensions_b200.sampler.get_samples (the drop-in for milo/milo/sampler.py) with its default device backend:
+    the reference's own get_samples run (tests/golden/sampler_golden.npz) reproduced through SimEnv + DeviceRollout,
+    same seeds, same numpy draws, to 1e-3 per step; lengths equal unless the deciding height is within 1e-3 of its
+    threshold.  (tests/test_sampler_shim.py checks the host logic exactly, on the CPU oracle.)"""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, SimEnv, sampler
+    from tests.test_parity_gpu import collision_margin
+    from tests.test_rollout_oracle import sampler_golden
+    g = sampler_golden()
+    S, A = 226, 28
+    N, hidden, horizon = int(g["N"]), [int(h) for h in g["hidden"]], int(g["horizon"])
+    ds = AmpDataset(*H.synth_dataset(int(g["dataset_rows"]), S, A, int(g["dataset_seed"])))
+    ens = DynamicsEnsemble(S, A, ds, None, num_models=N, hidden_sizes=hidden, dense_connect=True, transform=True,
+                           base_seed=int(g["base_seed"]))
+    calls = []
+
+    def reset_fn(n, rng):   # the reference drew these from its simulator; trajectory k starts where the golden one did
+        calls.append(1)
+        return g["observations"][len(calls) - 1, 0][None]
+
+    env = SimEnv(ens, horizon=horizon, reset_fn=reset_fn, seed=1)
+    ws = [torch.from_numpy(g[f"pol_w{i}"]) for i in range(3)]
+    bs = [torch.from_numpy(g[f"pol_b{i}"]) for i in range(3)]
+    pol = _Policy(_FC(ws, bs, "tanh"), g["log_std"])
+    n_traj = g["actions"].shape[0]
+    paths, n = sampler.get_samples(env, pol, n_traj, int(g["seed"]), mode="trajectories")
+    assert len(paths) == n_traj and n == sum(len(p["rewards"]) for p in paths)
+    for k, p in enumerate(paths):
+        n_ref, n_got = int(g["length"][k]), len(p["rewards"])
+        m = min(n_ref, n_got)
+        for name, ref in (("observations", g["observations"]), ("next_observations", g["next_observations"]),
+                          ("actions", g["actions"])):
+            err = np.abs(p[name][:m] - ref[k, :m]).max(axis=1)
+            assert (err < 1e-3 * np.arange(1, m + 1)).all(), (k, name, err)
+        if n_ref != n_got:
+            assert collision_margin(g["next_observations"][k, m - 1][None])[0] < 1e-3, (k, n_got, n_ref)
+
+
 def test_reward_replacement_matches_the_reference_train_step():
     """The drop-in claim of SURVEY.md section 8(b) on the reference's own numbers: BatchREINFORCE.train_step's reward
     replacement (batch_reinforce.py:103-169) — the lines in tests.helpers.reward_replacement — run over THIS package's
