@@ -61,6 +61,7 @@ struct simstep_handle {
   int XP = 0, HT = 0, SP = 0;
   int DP = 0;  // pitch (floats) of the fp32 delta workspace rows: S rounded up to 4, so a row is 16-byte granular
   std::vector<Layer> layers;  // L hidden + 1 final
+  unsigned long long* sat_dev = nullptr;  // normalised inputs beyond the fp16 range seen so far (prep kernel)
   float* tf_dev = nullptr;         // mean_s | scale_s | mean_a | scale_a
   float* out_scale_dev = nullptr;  // [SP]
   float* out_shift_dev = nullptr;  // [SP]
@@ -371,7 +372,7 @@ void launch_prep(simstep_handle* h, const float* s, const float* a, long long n,
   auto kern = vec ? prep_input_kernel<E, true> : prep_input_kernel<E, false>;
   launch_pdl(kern, dim3(grid), dim3(kPrepThreads), 0, st, s, a, h->S, h->A, h->XP, n, rows_pad,
              h->cfg.transform ? h->tf_dev : nullptr, static_cast<typename E::storage*>(h->xbuf), w_src,
-             w_src ? h->rff_wpad : nullptr, h->D);
+             w_src ? h->rff_wpad : nullptr, h->D, h->sat_dev);
   g_launches++;
 }
 
@@ -862,6 +863,11 @@ int simstep_create(const simstep_config* cfg, simstep_handle** out) {
       sg.src0[0] = 0; sg.width[0] = cfg->hidden[l - 1]; sg.dst0[0] = 0; sg.n = 1;
     }
   }
+  if (cudaMalloc(&h->sat_dev, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(h->sat_dev, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, SIMSTEP_ENOMEM, "cudaMalloc failed");
+  }
   // default termination model: none (horizon only) until simstep_set_termination
   h->term.horizon = 300;
   h->term.vel_inv_divisor = 1.f;
@@ -879,6 +885,7 @@ int simstep_destroy(simstep_handle* h) {
     cudaFree(ly.w);
     cudaFree(ly.bias);
   }
+  cudaFree(h->sat_dev);
   cudaFree(h->tf_dev);
   cudaFree(h->out_scale_dev);
   cudaFree(h->out_shift_dev);
@@ -1088,6 +1095,15 @@ int simstep_set_cost_transform(simstep_handle* h, int32_t transform) {
   if (!h) return SIMSTEP_EINVAL;
   if (transform < SIMSTEP_COST_IDENTITY || transform > SIMSTEP_COST_GAIL_LL) return fail(h, SIMSTEP_EINVAL, "bad cost transform");
   h->cost_transform = transform;
+  return SIMSTEP_OK;
+}
+
+int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t reset) {
+  if (!h || !count_out) return fail(h, SIMSTEP_EINVAL, "null argument");
+  unsigned long long v = 0;
+  CU_TRY(h, cudaMemcpy(&v, h->sat_dev, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with the device
+  if (reset) CU_TRY(h, cudaMemset(h->sat_dev, 0, sizeof(v)));
+  *count_out = static_cast<int64_t>(v);
   return SIMSTEP_OK;
 }
 

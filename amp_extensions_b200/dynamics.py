@@ -254,7 +254,7 @@ class DynamicsEnsemble:
             dev = self.device if self.device.type == "cuda" else None
             self._eng = _engine.Engine(self.state_dim, self.action_dim, self.num_models, self.hidden_sizes,
                                        dense_connect=self.dense_connect, activation=self.activation,
-                                       transform=self.transform, precision=self.precision, device=dev,
+                                       transform=self.transform, precision=self.operand_precision(), device=dev,
                                        max_chunk_envs=self.max_chunk_envs)
             self._param_stamp = None
         stamp = self._stamp()
@@ -264,6 +264,26 @@ class DynamicsEnsemble:
             self._eng.load_ensemble(ws, bs, self.transformations)
             self._param_stamp = stamp
         return self._eng
+
+    # A dataset column that never varies gets scale 1e-8 (datasets.py:35-40); the reference then feeds its fp32 MLP
+    # (s - mean) / 1e-8, which leaves the fp16 range (65 504) as soon as a state is 1e-3 away from that constant.
+    DEGENERATE_SCALE = 1e-6
+
+    def operand_precision(self):
+        """The tensor-core operand format of this ensemble's handle: the caller's choice when one was given;
+        otherwise fp16 (twice the tf32 rate) unless the normalisation has a degenerate input scale, in which case
+        tf32 (fp32's exponent range) is used and the choice is recorded in `self.precision_note`."""
+        if self.precision is not None:
+            return self.precision
+        self.precision_note = None
+        if self.transform and self.transformations is not None:
+            scales = torch.cat([torch.as_tensor(self.transformations[1]).reshape(-1).float(),
+                                torch.as_tensor(self.transformations[3]).reshape(-1).float()])
+            if bool((scales < self.DEGENERATE_SCALE).any()):
+                self.precision_note = (f"{int((scales < self.DEGENERATE_SCALE).sum())} input scale(s) below "
+                                       f"{self.DEGENERATE_SCALE:g}: tf32 operands instead of fp16")
+                return "tf32"
+        return _engine.DEFAULT_PRECISION
 
     def forward_all(self, state, action):
         """Every member's un-normalised prediction, CUDA [N, B, S]."""

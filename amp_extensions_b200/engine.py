@@ -173,6 +173,13 @@ class Engine:
         self.rff_split_loaded = bool(split)
         self.rff_split = bool(split)
 
+    def saturation_count(self, reset=False):
+        """Normalised inputs beyond the fp16 range seen by this (fp16) handle so far; 0 for tf32 / bf16 handles.
+        Synchronises."""
+        n = C.c_int64(0)
+        self._check(self.lib.simstep_saturation_count(self._h, C.byref(n), int(bool(reset))))
+        return int(n.value)
+
     def set_rff_split(self, split):
         """Turn the hi/lo (three-product) evaluation of the random-feature layer on or off (simstep_set_rff_split)."""
         self._check(self.lib.simstep_set_rff_split(self._h, int(bool(split))))

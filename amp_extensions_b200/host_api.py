@@ -137,8 +137,9 @@ class HostStepPipeline:
 class _Record:
     """One env group's device state + step outputs as ONE contiguous byte buffer per chunk, mirrored by one pinned
     host buffer: a chunk's results leave the device with a single copy.  Chunk layout (n rows):
-    [next_state n x S f32 | cost n f32 | disc n f32 | num_steps n i32 | done n u8 | pad to 256 B]; the optional
-    blocks (disc, num_steps) are dropped when the caller does not want them back."""
+    [next_state n x S f32 | cost n f32 | done n u8 (padded) | disc n f32 | num_steps n i32 | pad to 256 B]; the
+    optional blocks (disc, num_steps) sit at the end, so a caller that does not want them back still gets its
+    results with one copy (of the record's prefix)."""
 
     def __init__(self, eng, bounds, with_cost, want_disc, want_steps, pinned_mirror):
         S = eng.S
@@ -151,18 +152,19 @@ class _Record:
             lay["next"] = (o, n * S * 4); o += n * S * 4
             if with_cost:
                 lay["cost"] = (o, n * 4); o += n * 4
+            lay["done"] = (o, n); o += -(-n // 16) * 16
+            self_core = o                      # what every caller wants back: one copy of the record's prefix
             if want_disc:
                 lay["disc"] = (o, n * 4); o += n * 4
             if want_steps:
                 lay["steps"] = (o, n * 4); o += n * 4
-            lay["done"] = (o, n); o += n
+            lay["_core"] = (0, self_core)
             size = -(-o // 256) * 256
             self.chunks.append((off, size, lay))
             off += size
         self.nbytes = off
         self.dev = torch.empty(off, device=eng.device, dtype=torch.uint8)
         self.host = torch.empty(off, dtype=torch.uint8, pin_memory=True) if pinned_mirror else None
-        self.payload_bytes = sum(sum(sz for (_, sz) in lay.values()) for (_, _, lay) in self.chunks)
 
     def view(self, buf, ci, name, dtype, shape):
         off, _, lay = self.chunks[ci]
@@ -285,9 +287,11 @@ class HostEnvPipeline:
                 off, size, lay = g.rec[dst].chunks[ci]
                 if self.want_disc and self.want_steps:
                     g.host[off:off + size].copy_(g.rec[dst].dev[off:off + size], non_blocking=True)  # ONE copy
-                else:  # opted-out blocks stay on the device: copy the blocks around them
-                    for name in ("next", "cost", "disc", "steps", "done"):
-                        if name in lay and (name != "disc" or self.want_disc) and (name != "steps" or self.want_steps):
+                else:  # the optional blocks sit behind the core: one copy of the prefix, plus the one that is wanted
+                    core = lay["_core"][1]
+                    g.host[off:off + core].copy_(g.rec[dst].dev[off:off + core], non_blocking=True)
+                    for name in ("disc", "steps"):
+                        if (name == "disc" and self.want_disc) or (name == "steps" and self.want_steps):
                             o, sz = lay[name]
                             g.host[off + o: off + o + sz].copy_(g.rec[dst].dev[off + o: off + o + sz],
                                                                non_blocking=True)

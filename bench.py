@@ -414,12 +414,14 @@ class RolloutStats:
         self.torch.cuda.current_stream().wait_stream(self.side)
 
 
-def pcie_probe(device, nbytes=36 << 20, reps=5):
-    """GB/s of a pinned device->host copy of one step's result size, all ranks at once (the e2e ceiling of the box)."""
+def pcie_probe(device, nbytes=36 << 20, reps=10):
+    """GB/s of back-to-back pinned device->host copies of one step's result size, all ranks at once: what the box's
+    PCIe gives a rank while its neighbours copy too."""
     import torch
     d = torch.empty(nbytes, device=device, dtype=torch.uint8)
     h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    h.copy_(d, non_blocking=True)
+    for _ in range(2):
+        h.copy_(d, non_blocking=True)
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -750,7 +752,7 @@ def run_ours(args):
             dist.all_gather_into_tensor(allg, gbs)
             gbs = allg
         e2e["pcie_d2h_probe_gbs_per_rank"] = [round(float(x), 2) for x in gbs.tolist()]
-        e2e["pcie_ceiling_env_steps_per_s"] = float(gbs.min()) * 1e9 / (envp.d2h_bytes_per_step / E) * world
+        e2e["pcie_probe_implied_env_steps_per_s"] = float(gbs.min()) * 1e9 / (envp.d2h_bytes_per_step / E) * world
         del envp
 
     # ---- device-resident policy: the supported large-scale calling mode (no per-step PCIe at all) ------------

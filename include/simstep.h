@@ -117,6 +117,12 @@ int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host,
 
 int simstep_set_termination(simstep_handle* h, const simstep_termination* t);
 
+/* Number of normalised inputs (s - mean) / scale whose magnitude exceeded the fp16 range (65 504) since the last
+ * reset - only counted for SIMSTEP_PREC_FP16 handles, which saturate there while the fp32 reference carries on
+ * (DYN:225-227 divides by a scale that DS:35-40 lets be 1e-8 for a constant dataset column).  Synchronises with
+ * the device.  A non-zero count means: use SIMSTEP_PREC_TF32 for this data. */
+int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t reset);
+
 /* Replaces the rff layer of RBFLinearCost (LC:53-55): weight_host [D,in_dim],
  * bias_host [D].  in_dim must be S (input_type 's'), 2S ('ss'), S+A ('sa') or
  * 2S+A ('sas').  split != 0 keeps ~21 mantissa bits of the pre-activation by

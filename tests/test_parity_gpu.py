@@ -26,8 +26,10 @@ def assert_close(x, ref, scale, rel=REL, what=""):
     tol = rel * torch.maximum(ref.abs(), torch.as_tensor(scale, dtype=torch.float64).expand_as(ref))
     bad = (x - ref).abs() > tol
     assert torch.isfinite(x).all(), f"{what}: non-finite output"
+    l2 = float((x - ref).norm() / ref.norm().clamp_min(1e-300))   # the plain relative L2 error, for the record
     assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.numel()} outside {rel:g} relative; worst abs err "
-                           f"{float((x - ref).abs().max()):.3e} at ref {float(ref.flatten()[(x - ref).abs().argmax()]):.3e}")
+                           f"{float((x - ref).abs().max()):.3e} at ref {float(ref.flatten()[(x - ref).abs().argmax()]):.3e}; "
+                           f"relative L2 {l2:.3e}")
 
 
 def make_engine(case, precision, **kw):
