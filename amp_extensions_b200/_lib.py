@@ -157,6 +157,8 @@ def load(build_if_missing=True):
         if not build_if_missing:
             raise SimstepError(f"{path} is missing; run `python -m amp_extensions_b200.build`")
         _build.build()
+    elif build_if_missing and os.path.exists(_build.STAMP) and _build.needs_build() and _build.have_nvcc():
+        _build.build()   # the sources changed since the library was built: never run stale kernels silently
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means the .so does not match simstep.h

@@ -44,6 +44,10 @@ def _digest():
     return h.hexdigest()
 
 
+def have_nvcc():
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
 def needs_build():
     if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True

@@ -133,6 +133,20 @@ struct ProfScope {
   }
 };
 
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards (the load_*
+// entry points allocate on the handle's device but must not change the calling thread's current device).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) cudaSetDevice(device);
+    else prev = -1;
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 int fail(simstep_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
   return code;
@@ -921,7 +935,7 @@ int simstep_load_ensemble(simstep_handle* h, const float* const* weights_host, c
                           const float* const* transforms_host) {
   if (!h || !weights_host || !biases_host) return fail(h, SIMSTEP_EINVAL, "null argument");
   if (h->cfg.transform && !transforms_host) return fail(h, SIMSTEP_EINVAL, "transform set but no transforms given");
-  CU_TRY(h, cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);  // parameters live on the handle's device; the caller's current device is restored
   const int nl = h->L + 1;
   for (int l = 0; l < nl; ++l) {
     int rc = upload_layer(h, l, weights_host, biases_host, nl);
@@ -978,7 +992,7 @@ int simstep_set_termination(simstep_handle* h, const simstep_termination* t) {
 int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, const float* weight_host,
                      const float* bias_host, int32_t split) {
   if (!h || !weight_host || !bias_host || feature_dim < 1 || in_dim < 1) return fail(h, SIMSTEP_EINVAL, "bad argument");
-  CU_TRY(h, cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);  // parameters live on the handle's device; the caller's current device is restored
   CU_TRY(h, cudaDeviceSynchronize());
   cudaFree(h->rff_w); cudaFree(h->rff_b); cudaFree(h->rff_wpad); cudaFree(h->colsum_partial);
   cudaFree(h->rffin); cudaFree(h->rff_part);
@@ -1040,7 +1054,7 @@ int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host
   if (h->N != 1 || h->A != 0 || h->cfg.transform || h->cfg.dense_connect)
     return fail(h, SIMSTEP_EINVAL,
                 "a feature net needs a handle with n_models = 1, action_dim = 0, transform = 0 and dense_connect = 0");
-  CU_TRY(h, cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);  // parameters live on the handle's device; the caller's current device is restored
   CU_TRY(h, cudaDeviceSynchronize());
   for (int l = 0; l < h->L; ++l) {
     int rc = upload_layer(h, l, weights_host, biases_host, h->L);

@@ -215,6 +215,7 @@ template <>
 struct PostVec<1> {
   using type = float;
   __device__ static __forceinline__ float zero() { return 0.f; }
+  __device__ static __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
   __device__ static __forceinline__ float sub_sq(float a, float b, float acc) { const float t = a - b; return fmaf(t, t, acc); }
   __device__ static __forceinline__ float add(float a, float b) { return a + b; }
   __device__ static __forceinline__ bool vel_over(float v, int j, int off, float inv_div, float thr) {
@@ -225,6 +226,7 @@ template <>
 struct PostVec<2> {
   using type = float2;
   __device__ static __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+  __device__ static __forceinline__ float2 nan() { return make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); }
   __device__ static __forceinline__ float sub_sq(float2 a, float2 b, float acc) {
     const float t0 = a.x - b.x, t1 = a.y - b.y;
     return fmaf(t1, t1, fmaf(t0, t0, acc));
@@ -338,7 +340,7 @@ post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, 
 #pragma unroll
       for (int i = 0; i < kPerLane; ++i) {
         const int j = lane + 32 * i;
-        V dm = PostVec<VEC>::zero();
+        V dm = PostVec<VEC>::nan();  // a member index outside [0, N) (the reference raises IndexError): NaN next state
 #pragma unroll
         for (int m = 0; m < NM; ++m) dm = (m == mem) ? d[m][i] : dm;
         nxt[i] = PostVec<VEC>::add(sv[i], dm);

@@ -196,11 +196,15 @@ __device__ __forceinline__ void post_tma_row(float* srow, const float* drow0, in
   if (next_state != nullptr) {
     float2 nxt[kSlots];
     float2* nrow_g = reinterpret_cast<float2*>(next_state + row * S) + lane;
-    const float2* dm2 = d2 + mem * dstride2;  // the active member's row (sim_env.py:157)
+    // the active member's row (sim_env.py:157); an index outside [0, N) (the reference raises IndexError) makes the
+    // row's next state NaN instead of reading another env's deltas
+    const bool mem_ok = mem >= 0 && mem < NM;
+    const float2* dm2 = d2 + (mem_ok ? mem : 0) * dstride2;
+    const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
     for (int i = 0; i < kSlots; ++i) {
       if (in[i]) {
-        nxt[i] = __fadd2_rn(sv[i], dm2[32 * i]);
+        nxt[i] = mem_ok ? __fadd2_rn(sv[i], dm2[32 * i]) : make_float2(qnan, qnan);
         nrow_g[32 * i] = nxt[i];
         const_cast<float2*>(s2)[32 * i] = nxt[i];
       } else {

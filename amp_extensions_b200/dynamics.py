@@ -174,6 +174,13 @@ class DynamicsEnsemble:
         optional clip_grad_norm_, SGD-Nesterov or Adam (dynamics.py:236-250, 198-203) on a tf32 training handle.
         After training each member holds the parameters of its best-training-loss epoch (dynamics.py:370-372).
         Returns [(train_min_loss, first_epoch_loss)] per member like the reference."""
+        if validate:
+            raise NotImplementedError("DynamicsEnsemble.train(validate=True): the validation pass and its best_validate "
+                                      "checkpoint (dynamics.py:82-108, 252-268) stay with the reference class")
+        if save_checkpoints:
+            raise NotImplementedError("DynamicsEnsemble.train(save_checkpoints=True): per-model epoch checkpoints "
+                                      "(dynamics.py:355-378) stay with the reference class; save_ensemble() writes "
+                                      "the reference's ensemble.pt")
         ds = self.train_dataset
         n = len(ds)
         B = min(int(self.batch_size), n)

@@ -23,6 +23,23 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _check_i32(t, name, n):
+    """member / step-counter vectors cross the ABI as raw int32 pointers: refuse anything else instead of
+    reinterpreting it."""
+    if t is None:
+        return
+    if not (torch.is_tensor(t) and t.dtype == torch.int32 and t.is_cuda and t.is_contiguous() and t.numel() == n):
+        raise TypeError(f"{name} must be a contiguous CUDA int32 tensor with {n} elements, got "
+                        f"{getattr(t, 'dtype', type(t))} {tuple(getattr(t, 'shape', ()))}")
+
+
+def _check_f32(t, name, shape):
+    if not (torch.is_tensor(t) and t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+            and tuple(t.shape) == tuple(shape)):
+        raise TypeError(f"{name} must be a contiguous CUDA float32 tensor of shape {tuple(shape)}, got "
+                        f"{getattr(t, 'dtype', type(t))} {tuple(getattr(t, 'shape', ()))}")
+
+
 def _dev_f32(x, device):
     """Contiguous fp32 CUDA tensor (no copy when it already is one)."""
     if not torch.is_tensor(x):
@@ -233,6 +250,8 @@ class Engine:
              want_done=True):
         """In-place batched env step on device tensors. Returns (next_state, disc, done)."""
         E = state.shape[0]
+        _check_f32(state, "state", (E, self.S)); _check_f32(action, "action", (E, self.A))
+        _check_i32(member, "member", E); _check_i32(num_steps, "num_steps", E)
         if next_state is None:
             next_state = torch.empty_like(state)
         if disc is None and want_disc:
@@ -246,6 +265,8 @@ class Engine:
     def step_cost(self, state, action, member, num_steps, w, lambda_b, threshold, c_min=-1.0, c_max=0.0,
                   clamp_cost=True, next_state=None, disc=None, done=None, cost=None, ipm=None, bonus=None):
         E = state.shape[0]
+        _check_f32(state, "state", (E, self.S)); _check_f32(action, "action", (E, self.A))
+        _check_i32(member, "member", E); _check_i32(num_steps, "num_steps", E)
         f32 = dict(device=self.device, dtype=torch.float32)
         next_state = torch.empty_like(state) if next_state is None else next_state
         disc = torch.empty((E,), **f32) if disc is None else disc

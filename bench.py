@@ -80,7 +80,7 @@ def hbm_roofline(post_ms, envs, precision, peaks, n_models, split):
     b = fused_bytes_per_env_step(n_models)
     gbs = b * envs / (post_ms * 1e-3) / 1e9
     io = post_kernel_io_bytes(precision, n_models, split=split)
-    traffic, src = profile_note("post_dram_bytes_per_launch")
+    traffic, src = profile_note("post_step_dram_bytes_per_launch")
     return {"kernel": "post_step_tma_kernel (next state + discrepancy + termination; also writes the cost operand rows)",
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             "algorithmic_bytes_per_env_step": b, "kernel_io_bytes_per_env_step": io,
@@ -503,7 +503,7 @@ def run_ours(args):
         rew = torch.empty(E, device=device)
     stats = RolloutStats(eng, device, world, every=10, ring=oring)
     q_every = C["quantile_every"]
-    q_state = {"value": None, "calls": 0, "wall_s": 0.0}
+    q_state = {"value": None, "calls": 0, "wall_s": 0.0, "events": []}
 
     def one_step(i):
         k, o = i % ring, i % oring
@@ -517,8 +517,12 @@ def run_ours(args):
             imit.reward(p, v, t, out=rew)
         if q_every and (i + 1) % q_every == 0:
             t0 = time.perf_counter()
+            qe0, qe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            qe0.record()
             q_state["value"] = parallel.global_quantile(disc[o], 0.9, engine=eng)  # one host sync, inside the region
-            q_state["wall_s"] += time.perf_counter() - t0
+            qe1.record()
+            q_state["events"].append((qe0, qe1))
+            q_state["wall_s"] += time.perf_counter() - t0   # includes draining the steps queued ahead of the sync
             q_state["calls"] += 1
 
     def barrier():
@@ -587,8 +591,14 @@ def run_ours(args):
         dist.all_reduce(e_total, op=dist.ReduceOp.SUM)
     envs_global = float(e_total.item())
     value = envs_global * args.steps / (total_ms * 1e-3)
-    quantile = dict(q_state, ms_per_call=(q_state["wall_s"] / q_state["calls"] * 1e3) if q_state["calls"] else None)
-    q_state.update(calls=0, wall_s=0.0)
+    torch.cuda.synchronize(device)
+    quantile = {"value": q_state["value"], "calls": q_state["calls"],
+                "device_ms_per_call": (sum(a.elapsed_time(b) for a, b in q_state["events"]) / len(q_state["events"]))
+                if q_state["events"] else None,
+                "host_wall_ms_per_call": (q_state["wall_s"] / q_state["calls"] * 1e3) if q_state["calls"] else None,
+                "note": "device = the quantile's own launches and collectives (CUDA events); host wall also counts the "
+                        "queued steps the call's single synchronisation has to drain"}
+    q_state.update(calls=0, wall_s=0.0, events=[])
 
     # ---- sustained: the same loop for >= 2 s, with its own clock record ---------------------------------------
     sustained = None
@@ -603,7 +613,7 @@ def run_ours(args):
         sustained = {"value": envs_global * n_sus / (sus_ms * 1e-3), "unit": UNIT, "steps": n_sus,
                      "ms_per_step": sus_ms / n_sus, "seconds": sus_ms * 1e-3,
                      "clocks": s2.stop(tw0, tw1) if rank == 0 else None}
-        q_state.update(calls=0, wall_s=0.0)
+        q_state.update(calls=0, wall_s=0.0, events=[])
 
     # ---- diagnostic: the same steps replayed from CUDA graphs (no per-launch CPU work at all) ------------
     graph_ms = None
@@ -639,15 +649,18 @@ def run_ours(args):
         per_step = {k: v[0] / prof_steps for k, v in prof.items() if v[1] > 0}
     imit_ms = None
     if imit is not None:
+        n_im = 30
+        for i in range(3):
+            imit.reward(*poses[i % 2], out=rew)
         torch.cuda.synchronize(device)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        for i in range(prof_steps):
+        for i in range(n_im):
             p, v, t = poses[i % 2]
             imit.reward(p, v, t, out=rew)
         a1.record()
         torch.cuda.synchronize(device)
-        imit_ms = a0.elapsed_time(a1) / prof_steps
+        imit_ms = a0.elapsed_time(a1) / n_im
         per_step["imitation"] = imit_ms
 
     if args.skip_e2e:

@@ -81,9 +81,9 @@ if os.path.exists(lp):
         for i, (k, g, b, v) in enumerate(seq):
             if "simstep::" in k:
                 w.writerow([i, k.split("(")[0], g, b, int(v)])
-    ends = [i for i, s in enumerate(seq) if "cost_combine" in s[0]]
-    if len(ends) >= 2:
-        a, b = ends[-2] + 1, ends[-1] + 1
+    starts = [i for i, s in enumerate(seq) if "prep_input_kernel" in s[0]]   # a step begins with the input preparation
+    if len(starts) >= 2:
+        a, b = starts[-2], starts[-1]
         tot = sum(s[3] for s in seq[a:b])
         with open(os.path.join(P, f"{out}_step_share.txt"), "w") as f:
             f.write("# one step of bench.py (40000 env-steps, fp16 operands) under\n"
@@ -115,7 +115,17 @@ if os.path.exists(ip):
     for k, v in t.items():
         if k != "__order__" and "imitation_reward" in k:
             tr["imitation_dram_bytes_per_launch"] = v[0]
+    hdr, units, data, idx = ncu_table(ip)
+    key = "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"
+    if key in idx and data:
+        tr["imitation_fp32_pipe_frac"] = float(data[0][idx[key]].replace(",", "")) / 100.0
 if tr:
+    old_path = os.path.join(P, "roofline_traffic.json")
+    if os.path.exists(old_path):   # keep the keys this round did not re-measure
+        with open(old_path) as f:
+            prev = json.load(f)
+        for k, v in prev.items():
+            tr.setdefault(k, v)
     tr["source"] = f"profiles/{out}_ncu_step.txt, profiles/{out}_ncu_imit.txt (ncu --set full, per launch)"
     with open(os.path.join(P, "roofline_traffic.json"), "w") as f:
         json.dump(tr, f, indent=1)
