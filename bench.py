@@ -742,6 +742,16 @@ def run_ours(args):
                                                 lean.collect_chunks),
                        "d2h_bytes_per_step": lean.d2h_bytes_per_step, "what": "obs + cost + done only"}
         del lean
+        # half-precision observations (opt-in): half the bytes per step where the host's PCIe is the limit
+        half = HostEnvPipeline(eng, E, groups=2, n_chunks=chunks, with_cost=True, want_disc=False, want_steps=False,
+                               obs_dtype=torch.float16)
+        half.reset(0, hs[0], hm)
+        half.reset(1, hs[1], hm)
+        e2e["obs_fp16"] = {"value": timed_host_loop(lambda i: half.submit(i % 2, ha[i % 4], w, LAMBDA_B, threshold),
+                                                    half.collect_chunks),
+                           "d2h_bytes_per_step": half.d2h_bytes_per_step,
+                           "what": "obs (fp16, 2^-11 relative rounding) + cost + done; the state stays fp32 on the device"}
+        del half
         # (2) stateless callers: the full state crosses PCIe both ways every step
         if E <= 65536:
             pipe = HostStepPipeline(eng, E, n_chunks=chunks, with_cost=True)

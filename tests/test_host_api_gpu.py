@@ -81,3 +81,32 @@ def test_host_env_pipeline_keeps_state_on_the_device(E):
     with pytest.raises(RuntimeError):
         pipe.submit(0, actions[0], w, 0.1, 0.7)
         pipe.submit(0, actions[0], w, 0.1, 0.7)
+
+
+@pytest.mark.parametrize("mode", ["lean", "obs_fp16"])
+def test_host_env_pipeline_optional_blocks_and_half_precision_observations(mode):
+    """want_disc / want_steps = False drop those blocks from the download (one copy of the record's core); with
+    obs_dtype=float16 the observations come back as the fp16 rounding of the fp32 state, which itself stays exact
+    on the device (the next step starts from the fp32 state, not from the rounded copy)."""
+    from amp_extensions_b200.host_api import HostEnvPipeline
+    E = 513
+    c, eng, w, states, actions, member = _setup(E)
+    kw = dict(want_disc=False, want_steps=False)
+    if mode == "obs_fp16":
+        kw["obs_dtype"] = torch.float16
+    pipe = HostEnvPipeline(eng, E, groups=1, n_chunks=2, with_cost=True, **kw)
+    pipe.reset(0, states[0], member)
+    ref_state = states[0].cuda()
+    ref_steps = torch.zeros(E, dtype=torch.int32).cuda()
+    for i in range(3):
+        pipe.submit(0, actions[i], w, 0.1, 0.7)
+        obs_h, cost_h, done_h, disc_h, st_h = pipe.collect()
+        nxt, disc, done, cst, _, _ = eng.step_cost(ref_state, actions[i].cuda(), member.cuda(), ref_steps, w, 0.1, 0.7)
+        ref_state = nxt
+        assert disc_h is None and st_h is None
+        assert torch.equal(cost_h, cst.cpu()) and torch.equal(done_h, done.cpu())
+        if mode == "obs_fp16":
+            assert obs_h.dtype == torch.float16 and torch.equal(obs_h, nxt.cpu().to(torch.float16)), i
+        else:
+            assert torch.equal(obs_h, nxt.cpu()), i
+    assert pipe.d2h_bytes_per_step == E * (eng.S * (2 if mode == "obs_fp16" else 4) + 1 + 4)
