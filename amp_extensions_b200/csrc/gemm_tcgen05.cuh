@@ -242,7 +242,9 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 // cos(x) for the random-feature epilogue: two-constant Cody-Waite reduction to [-pi, pi] then the SFU
 // approximation (abs error < 1e-6 for |x| up to ~1e4, far inside the 1e-3 budget of the cost).
 __device__ __forceinline__ float fast_cos(float x) {
-  const float k = rintf(x * 0.15915494309189535f);
+  // round-to-nearest through the 1.5 * 2^23 trick (two full-rate FADDs; rintf is an FRND on the quarter-rate pipe
+  // that the MUFU.COS below needs too); exact for |x / 2 pi| < 2^22, far beyond any pre-activation seen here
+  const float k = (fmaf(x, 0.15915494309189535f, 12582912.f)) - 12582912.f;
   float r = fmaf(k, -6.28318548202514648f, x);   // 2*pi rounded to fp32
   r = fmaf(k, 1.74845553e-7f, r);                // 2*pi_fp32 - 2*pi
   return __cosf(r);
