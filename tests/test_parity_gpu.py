@@ -567,3 +567,32 @@ def test_unaligned_state_rows_take_the_fallback_kernel_with_the_same_results(pre
     assert torch.equal(out_odd[0], out_al[0]) and torch.equal(out_odd[2], out_al[2])
     assert_close(out_odd[1], out_al[1], out_al[1].mean().item(), rel=2e-6, what="disc")
     assert_close(out_odd[3], out_al[3], out_al[3].abs().max().item(), rel=1e-5, what="cost")
+
+
+def test_fused_final_kernel_matches_the_default_two_launch_path(tmp_path):
+    """SIMSTEP_FINAL_FUSED=1 runs the final ensemble layer and the env step's tail as ONE launch (csrc/gemm_final.cuh:
+    transposed L2 scratch, tickets, tail warps).  Same fp32 arithmetic per element as the final-layer GEMM followed by
+    post_step_tma_kernel, so next states, step counters and termination masks are bit-identical (including the NaN row
+    of an out-of-range member index); the discrepancy sums its squares in a different order (1e-6)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = {}
+    for flag in ("0", "1"):
+        out = str(tmp_path / f"fused{flag}.npz")
+        env = dict(os.environ, SIMSTEP_FINAL_FUSED=flag)
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "final_fused_check.py"), out], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        files[flag] = np.load(out)
+    a, b = files["0"], files["1"]
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        x, y = a[k], b[k]
+        if k.endswith(("_next", "_done", "_steps")):
+            assert np.array_equal(x, y, equal_nan=True), k
+        else:
+            scale = max(float(np.nanmax(np.abs(x))), 1e-12)
+            assert float(np.nanmax(np.abs(x - y))) <= 2e-6 * scale, (k, float(np.nanmax(np.abs(x - y))), scale)
+    assert np.isnan(a["E2000_s1_next"][3]).all() and not np.isnan(a["E2000_s1_next"][4]).any()
