@@ -1,7 +1,8 @@
 """In-tree build of libsimstep.so (nvcc, sm_100a only).
 
 `python -m amp_extensions_b200.build` compiles every translation unit under amp_extensions_b200/csrc
-(api.cu: the C ABI and most kernels; final_fused.cu: the fused final-layer kernel's instantiations) in
+(api.cu: the C ABI and most kernels; final_fused.cu: the fused final-layer kernel's instantiations; chain.cu: the column-fused
+ensemble forward kernel's) in
 parallel and links them into amp_extensions_b200/csrc/libsimstep.so.  nvcc cross-compiles without a GPU.
 """
 import hashlib
@@ -22,7 +23,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
-UNITS = ("api.cu", "final_fused.cu")
+UNITS = ("api.cu", "final_fused.cu", "chain.cu")
 
 
 def _sources():

