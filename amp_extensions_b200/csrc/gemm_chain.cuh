@@ -141,6 +141,10 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; the leader arms the barrier for both) =====
+    // ONE elected thread runs the whole loop: ptxas then knows the code is single-threaded and emits each TMA / MMA
+    // instruction once, instead of wrapping every one of them in an ELECT / BRA.U.ANY loop over the active lanes
+    // (about 100 instructions per k-block when the issue sits under `if (lane == 0)`, 40 this way)
+    if (ptx::elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     uint32_t have = 0;  // last value seen in stored_cnt
@@ -168,23 +172,22 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
               }
             }
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (lane == 0) {
-              uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
-              uint8_t* sb = sa + kABytes;
-              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CG);
-              if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
-              else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
-              ptx::tma_load_2d<CG>(sb, &maps.w[l], &full_bar[stage], kb * BK, row_b);
-            }
-            __syncwarp();
+            uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CG);
+            if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
+            else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
+            ptx::tma_load_2d<CG>(sb, &maps.w[l], &full_bar[stage], kb * BK, row_b);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader) {
+    if (leader && ptx::elect_one()) {
       constexpr uint32_t idesc = make_idesc<E, CG>();
       int stage = 0;
       uint32_t phase = 0;
@@ -201,23 +204,21 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
             for (int kb = 0; kb < kb_total; ++kb) {
               ptx::mbar_wait(&full_bar[stage], phase);
               ptx::tcgen05_fence_after();
-              if (lane == 0) {
-                const uint32_t sa = ptx::smem_u32(smem_tiles + size_t(stage) * S::kStageBytes);
-                const uint64_t da = ptx::umma_desc_k_sw128(sa);
-                const uint64_t db = ptx::umma_desc_k_sw128(sa + kABytes);
+              const uint32_t sa = ptx::smem_u32(smem_tiles + size_t(stage) * S::kStageBytes);
+              const uint64_t da = ptx::umma_desc_k_sw128(sa);
+              const uint64_t db = ptx::umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-                for (int k = 0; k < kMmasPerBlock; ++k)
-                  ptx::umma_ss<E::kKind, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                ptx::umma_commit<CG>(&empty_bar[stage]);
-                if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
-              }
-              __syncwarp();
+              for (int k = 0; k < kMmasPerBlock; ++k)
+                ptx::umma_ss<E::kKind, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_commit<CG>(&empty_bar[stage]);
+              if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
     }
+    __syncwarp();
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;

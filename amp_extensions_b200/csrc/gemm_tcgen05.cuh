@@ -344,6 +344,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair; the leader arms the barrier for both) =====
+    // ONE elected thread runs the whole loop (and likewise the MMA issuer below): ptxas then knows the code is
+    // single-threaded and emits each TMA / MMA instruction once, instead of wrapping every one of them in an
+    // ELECT / BRA.U.ANY loop over the active lanes (about 100 instructions per k-block under `if (lane == 0)`, 40 so)
+    if (ptx::elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     int held_b = -1;  // (group, n-tile) whose weight k-blocks sit in the stages' B halves (B-resident mode)
@@ -359,24 +363,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
       held_b = this_b;
       for (int kb = 0; kb < kb_total; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
-          uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (load_b ? S::kStageBytes : kABytes) * CG);
-          if (kb < args.kb_x) {
-            ptx::tma_load_2d<CG>(sa, &tmap_ax, &full_bar[stage], kb * BK, row_ax);
-          } else {
-            ptx::tma_load_2d<CG>(sa, &tmap_ah, &full_bar[stage], (args.kb_h0 + kb - args.kb_x) * BK, row_ah);
-          }
-          if (load_b) ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+        uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (load_b ? S::kStageBytes : kABytes) * CG);
+        if (kb < args.kb_x) {
+          ptx::tma_load_2d<CG>(sa, &tmap_ax, &full_bar[stage], kb * BK, row_ax);
+        } else {
+          ptx::tma_load_2d<CG>(sa, &tmap_ah, &full_bar[stage], (args.kb_h0 + kb - args.kb_x) * BK, row_ah);
         }
-        __syncwarp();
+        if (load_b) ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
         if (++stage == ring) { stage = 0; phase ^= 1; }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader) {
+    if (leader && ptx::elect_one()) {
       constexpr uint32_t idesc = make_idesc<E, CG>();
       int stage = 0;
       uint32_t phase = 0;
@@ -389,23 +392,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
         for (int kb = 0; kb < kb_total; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tcgen05_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = ptx::smem_u32(smem_tiles + size_t(stage) * S::kStageBytes);
-            const uint64_t da = ptx::umma_desc_k_sw128(sa);
-            const uint64_t db = ptx::umma_desc_k_sw128(sa + kABytes);
+          const uint32_t sa = ptx::smem_u32(smem_tiles + size_t(stage) * S::kStageBytes);
+          const uint64_t da = ptx::umma_desc_k_sw128(sa);
+          const uint64_t db = ptx::umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-            for (int k = 0; k < kMmasPerBlock; ++k) {
-              // advance 32 bytes (= UMMA_K elements) along K inside the swizzle atom
-              ptx::umma_ss<E::kKind, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            }
-            ptx::umma_commit<CG>(&empty_bar[stage]);
-            if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
+          for (int k = 0; k < kMmasPerBlock; ++k) {
+            // advance 32 bytes (= UMMA_K elements) along K inside the swizzle atom
+            ptx::umma_ss<E::kKind, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          __syncwarp();
+          ptx::umma_commit<CG>(&empty_bar[stage]);
+          if (kb == kb_total - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
           if (++stage == ring) { stage = 0; phase ^= 1; }
         }
       }
     }
+    __syncwarp();
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may read

@@ -26,7 +26,7 @@ python - <<PY
 import json
 try:
     d = json.loads(open("$OUT/${TAG}_${mode}_$i.json").read().strip().splitlines()[-1])
-    print("$mode run $i", "value %.4g ms %.4f" % (d["value"], d["ms_per_step"]), d.get("kernels_ms_per_step"), d["clocks"])
+    print("$mode run $i", "value %.4g ms %.4f" % (d["value"], d["ms_per_step"]), d.get("kernels_ms_per_step"), d.get("clocks"))
 except Exception as e:
     print("$mode failed", e); print(open("$OUT/${TAG}_${mode}_$i.err").read()[-1500:])
 PY
