@@ -46,6 +46,7 @@ struct Layer {
   void* w = nullptr;      // [N][o_pad][k_pad] operand storage
   float* bias = nullptr;  // [N][o_pad]
   CUtensorMap tmap_w;
+  CUtensorMap tmap_w64;  // the same operand with a 64-row box (column halves of the chain kernel's shared units)
 };
 
 }  // namespace
@@ -73,6 +74,7 @@ struct simstep_handle {
   void* hbuf = nullptr;
   float* dws = nullptr;
   unsigned int* tickets = nullptr;  // fused final layer: one arrival counter per 128-row block (gemm_final.cuh)
+  unsigned int* chain_cnt = nullptr;  // chain kernel: tile counters of the shared units of the last round (zero between launches)
   CUtensorMap tmap_x, tmap_h, tmap_dws;
 
   // RFF cost
@@ -322,6 +324,7 @@ void free_workspace(simstep_handle* h) {
   cudaFree(h->hbuf); h->hbuf = nullptr;
   cudaFree(h->dws); h->dws = nullptr;
   cudaFree(h->tickets); h->tickets = nullptr;
+  cudaFree(h->chain_cnt); h->chain_cnt = nullptr;
   cudaFree(h->rffin); h->rffin = nullptr;
   cudaFree(h->rff_part); h->rff_part = nullptr;
   h->cap_rows = 0;
@@ -347,6 +350,8 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
     CU_TRY(h, cudaMalloc(&h->tickets, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
     CU_TRY(h, cudaMemset(h->tickets, 0, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
+    CU_TRY(h, cudaMalloc(&h->chain_cnt, size_t(h->sm_count) * 2 * sizeof(unsigned int)));
+    CU_TRY(h, cudaMemset(h->chain_cnt, 0, size_t(h->sm_count) * 2 * sizeof(unsigned int)));
     CU_TRY(h, cudaMemset(h->xbuf, 0, size_t(rows) * h->XP * h->esize));
     if (h->HT > 0) CU_TRY(h, cudaMemset(h->hbuf, 0, size_t(h->N) * rows * h->HT * h->esize));
     int rc = encode_operand(h, &h->tmap_x, prec, h->xbuf, h->XP, rows, h->XP, kBlockM);
@@ -465,12 +470,13 @@ int launch_final(simstep_handle* h, long long n, long long rows_pad, const StepT
 // The column-fused forward pass (gemm_chain.cuh): every layer of a (member, 256-row env tile) on one CTA pair, the
 // activations handed from layer to layer through L2.  SIMSTEP_CHAIN=0 restores one launch per layer (A/B runs);
 // SIMSTEP_CHAIN_SLOT=0 keeps the activation rows at their env rows instead of in the pair's L2-resident slot.
+// SIMSTEP_CHAIN (A/B runs): 0 one launch per layer; 1 activation rows at their env rows instead of in the pair's
+// L2-resident slot; 2 the default; 3 the last, partial round as a plain round instead of shared between pairs.
 int chain_mode() {
   static const int mode = [] {
     const char* e = std::getenv("SIMSTEP_CHAIN");
-    if (e && e[0] == '0') return 0;
-    const char* s = std::getenv("SIMSTEP_CHAIN_SLOT");
-    return (s && s[0] == '0') ? 1 : 2;
+    if (e && e[0] >= '0' && e[0] <= '3') return e[0] - '0';
+    return 2;
   }();
   return mode;
 }
@@ -491,7 +497,7 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
   ca.groups = h->N;
   ca.a_rows_per_group = int(h->cap_rows);
   ca.out_rows_per_group = int(h->cap_rows);
-  ca.h_slot = chain_mode() == 2 ? 1 : 0;
+  ca.h_slot = chain_mode() == 1 ? 0 : 1;
   ca.scale = h->cfg.transform ? h->out_scale_dev : nullptr;
   ca.shift = h->cfg.transform ? h->out_shift_dev : nullptr;
   for (int l = 0; l <= h->L; ++l) {
@@ -506,6 +512,21 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
     c.out_col0 = ly.out_col0;
     c.bias = ly.bias;
     if (l < h->L) ca.hidden_tiles += c.n_tiles;
+  }
+  cl.maps.w_final64 = h->layers[h->L].tmap_w64;
+  // the last, partial round: when its units are at most half the pairs, two pairs share each of them
+  const int units = ca.m_tiles * ca.groups;
+  const int pairs = std::min(units, h->sm_count / 2);
+  const int tail = units % pairs;
+  if (chain_mode() != 3 && tail > 0 && 2 * tail <= pairs && ca.hidden_tiles <= kChainMaxDepTiles && h->chain_cnt) {
+    ca.tail_units = tail;
+    ca.tail_cnt = h->chain_cnt;
+    int t = 0;
+    for (int l = 0; l < h->L; ++l)
+      for (int n = 0; n < ca.layer[l].n_tiles; ++n, ++t) {
+        ca.dep_role[t] = static_cast<unsigned char>(n & 1);
+        ca.dep_ord[t] = static_cast<unsigned char>(ca.tiles_per_role[n & 1]++);
+      }
   }
   CU_TRY(h, launch_ensemble_chain(h->cfg.precision, h->cfg.activation != SIMSTEP_ACT_RELU, cl, h->sm_count, h->device, st));
   g_launches++;
@@ -820,6 +841,9 @@ int upload_layer(simstep_handle* h, int l, const float* const* weights_host, con
     CU_TRY(h, cudaStreamSynchronize(st));  // tmp and the pageable host source are reused
   }
   cudaFree(tmp);
+  if (int rc = encode_operand(h, &ly.tmap_w64, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
+                              ly.k_pad, kBlockN / 4))
+    return rc;
   return encode_operand(h, &ly.tmap_w, h->cfg.precision, ly.w, ly.k_pad, static_cast<long long>(h->N) * ly.o_pad,
                         ly.k_pad, kBlockN / h->cg);
 }

@@ -10,7 +10,7 @@
 //   * the epilogue publishes "hidden tile k of this CTA has been stored" through a shared-memory counter after the
 //     tile's TMA stores have COMPLETED (cp.async.bulk.wait_group, not .read); the TMA producer looks at the counter
 //     only before the first k-block that comes from that tile's 256 columns.  No global-memory flags, no gpu-scope
-//     fences, no other CTA is ever waited for (the per-layer tile order of the earlier fused experiment needed both).
+//     fences, no other CTA is waited for (the per-layer tile order of the earlier fused experiment needed both).
 //   * the K loop of layer l+1 reads [x | h_1 | ... | h_l] in that order, so the blocks that depend on the tile just
 //     finished come LAST: the MMAs of the next layer start on x and the older slices while the epilogue drains.
 //   * the activation rows of a unit are written and read back by the same SM pair within tens of microseconds, i.e.
@@ -18,9 +18,21 @@
 //     row for 226 outputs) and the short first layer (epilogue-bound alone) disappear into the tensor-bound average.
 //   * slot mode (h_slot != 0): a pair keeps its unit's activation rows in ITS OWN 256-row slot of the activation
 //     buffer instead of at the unit's rows - the live part of the buffer is then 74 pairs x 256 rows x 4 KB = 78 MB
-//     whatever the batch, it stays resident in the 126 MB L2 and the activations need not travel to HBM at all.  Safe without extra synchronisation: the first
-//     store into the slot for unit u+1 follows an MMA that was issued after every MMA of unit u, and those had
-//     consumed every load from the slot.
+//     whatever the batch.  Safe without extra synchronisation: the first store into the slot for unit u+1 follows an
+//     MMA that was issued after every MMA of unit u, and those had consumed every load from the slot.
+//   * THE LAST, PARTIAL ROUND.  628 units of the bench batch are 8 rounds of 74 pairs plus 36 units; run as a ninth
+//     round they leave 38 pairs idle for a whole unit (6 % of the launch).  When the T left-over units are at most half
+//     the pairs, TWO pairs share each of them: pair 2u + p computes the n-tiles n % 2 == p of every hidden layer and the
+//     column half p of every final-layer tile (an M 256 x N 128 product), so the last round takes half a unit.  Only
+//     here does a dependency cross CTA pairs: the epilogue also publishes its tile count in global memory
+//     (st.release.gpu) and the partner's producer polls it (ld.acquire.gpu) before the k-blocks that come from the
+//     partner's column tiles; the reader zeroes the counter when it is through, so the buffer is clean for the next
+//     launch (and for CUDA-graph replays).  All pairs are co-resident (one CTA per SM), nobody waits on work that has
+//     not been scheduled.
+//
+// Tried and dropped: a cluster of FOUR CTAs per unit (both pairs on one unit throughout, the A operand multicast between
+// them: 25 % fewer bytes out of L2, bit-identical results).  Only 33 such clusters are co-schedulable on the 148 SMs
+// (GPC sizes), 132 SMs instead of 148, and the launch was 12 % slower; the multicast itself changed nothing.
 //
 // Pipeline, barriers, TMEM double-buffering, the operand ring and the TMA-store epilogue are those of
 // gemm_tcgen05.cuh (CG = 2, one epilogue group); the accumulation order of every output element is the same as in
@@ -45,6 +57,8 @@ struct ChainLayer {
   const float* bias;      // [groups][n_tiles * kBlockN] or nullptr
 };
 
+constexpr int kChainMaxDepTiles = 64;
+
 struct ChainArgs {
   int n_layers;            // hidden layers + the final one (the last entry of layer[])
   int m_tiles, groups;
@@ -54,12 +68,19 @@ struct ChainArgs {
   int hidden_tiles;        // hidden tiles per unit (sum of n_tiles over the hidden layers)
   const float* scale;      // final layer: [n_tiles * kBlockN] or nullptr (dynamics.py:231-232)
   const float* shift;
+  // the last, partial round: units [units - tail_units, units) are shared by two pairs each (0: plain extra round)
+  int tail_units;
+  int tiles_per_role[2];                      // hidden tiles role p stores per shared unit
+  unsigned char dep_role[kChainMaxDepTiles];  // column tile T of the activation buffer: the role that stores it ...
+  unsigned char dep_ord[kChainMaxDepTiles];   // ... and its ordinal among that role's tiles of the unit
+  unsigned int* tail_cnt;                     // [tail_units][2 roles][2 row halves], zero between launches
   ChainLayer layer[kChainMaxLayers];
 };
 
 struct ChainMaps {
   CUtensorMap x, h, out_final;
   CUtensorMap w[kChainMaxLayers];
+  CUtensorMap w_final64;   // the final layer's weights with a 64-row box (column halves of the shared units)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_cta_smem(const uint32_t* p) {
@@ -72,6 +93,35 @@ __device__ __forceinline__ void st_release_cta_smem(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void chain_fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <typename E>
+__host__ __device__ constexpr uint32_t make_idesc_n(int n) {
+  return (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>((kBlockM * 2) >> 4) << 24);
+}
+
+// One work item of a CTA pair: a whole unit (role < 0) or one of the two roles of a shared unit of the last round.
+struct ChainItem {
+  int unit;
+  int role;
+};
+__device__ __forceinline__ bool chain_item(const ChainArgs& a, int pair, int pairs, int i, ChainItem& it) {
+  const int units = a.m_tiles * a.groups;
+  const int full_units = units - a.tail_units;
+  const int u = pair + i * pairs;
+  if (u < full_units) { it.unit = u; it.role = -1; return true; }
+  // the shared units come after the pair's last whole unit
+  const int n_full = full_units > pair ? (full_units - pair + pairs - 1) / pairs : 0;
+  if (i == n_full && pair < 2 * a.tail_units) { it.unit = full_units + (pair >> 1); it.role = pair & 1; return true; }
+  return false;
 }
 
 template <typename E, bool TANH>
@@ -86,6 +136,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
   constexpr int kStages = Plan::kStages;
   constexpr int kOutStages = Plan::kOutStages;
   constexpr int kKbPerTile = kBlockN / BK;  // k-blocks of the activation buffer that one hidden tile produces
+  constexpr int kHalfN = kBlockN / 2;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -136,8 +187,12 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
 
   const int pair = blockIdx.x / CG;
   const int pairs = gridDim.x / CG;
-  const int units = args.m_tiles * args.groups;
+  const int n_hidden = args.n_layers - 1;
   const int slot_row = (pair * CG + int(cta_rank)) * kBlockM;
+  // Tiles of layer l an item runs: every n-tile of a whole unit; of a shared unit the n-tiles n % 2 == role of a hidden
+  // layer and the column half `role` of every final-layer tile.
+  auto n_begin = [&](const ChainItem& it, int l) { return (it.role < 0 || l == n_hidden) ? 0 : it.role; };
+  auto n_step = [&](const ChainItem& it, int l) { return (it.role < 0 || l == n_hidden) ? 1 : 2; };
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; the leader arms the barrier for both) =====
@@ -145,57 +200,93 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
     // instruction once, instead of wrapping every one of them in an ELECT / BRA.U.ANY loop over the active lanes
     // (about 100 instructions per k-block when the issue sits under `if (lane == 0)`, 40 this way)
     if (ptx::elect_one()) {
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t have = 0;  // last value seen in stored_cnt
-    uint32_t unit_base = 0;
-    for (int unit = pair; unit < units; unit += pairs, unit_base += args.hidden_tiles) {
-      const int g = unit % args.groups;
-      const int m_row = ((unit / args.groups) * CG + int(cta_rank)) * kBlockM;
-      const int row_ah = args.h_slot ? slot_row : g * args.a_rows_per_group + m_row;
-      for (int l = 0; l < args.n_layers; ++l) {
-        const ChainLayer& ly = args.layer[l];
-        const int kb_total = ly.kb_x + ly.kb_h;
-        for (int n_tile = 0; n_tile < ly.n_tiles; ++n_tile) {
-          const int row_b = g * ly.b_rows_per_group + n_tile * kBlockN + int(cta_rank) * S::kBRows;
-          for (int kb = 0; kb < kb_total; ++kb) {
-            const int hk = ly.kb_h0 + kb - ly.kb_x;  // k-block inside the activation buffer (kb >= kb_x)
-            if (kb >= ly.kb_x) {
-              const uint32_t need = unit_base + uint32_t(hk / kKbPerTile) + 1u;
-              if (have < need) {
-                unsigned int spins = 0;
-                while ((have = ld_acquire_cta_smem(stored_cnt)) < need) {
-                  __nanosleep(32);
-                  if (++spins > (1u << 26)) __trap();  // a dependency that never arrives is a bug: trap, do not hang
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t have = 0;       // last value seen in stored_cnt
+      uint32_t done_tiles = 0; // hidden tiles this CTA stored in the items before the current one
+      ChainItem item;
+      for (int i = 0; chain_item(args, pair, pairs, i, item); ++i) {
+        const bool shared = item.role >= 0;
+        const int g = item.unit % args.groups;
+        const int m_row = ((item.unit / args.groups) * CG + int(cta_rank)) * kBlockM;
+        const int row_ah = (args.h_slot && !shared) ? slot_row : g * args.a_rows_per_group + m_row;
+        // shared unit: the partner's tile counter for this row half (polled), zeroed again when this item is through
+        unsigned int* partner_cnt = nullptr;
+        uint32_t have_partner = 0;
+        if (shared)
+          partner_cnt = args.tail_cnt + (((item.unit - (args.m_tiles * args.groups - args.tail_units)) * 2 +
+                                          (1 - item.role)) * 2 + int(cta_rank));
+        for (int l = 0; l < args.n_layers; ++l) {
+          const ChainLayer& ly = args.layer[l];
+          const bool half = shared && l == n_hidden;
+          const int kb_total = ly.kb_x + ly.kb_h;
+          const uint32_t stage_bytes = uint32_t(kABytes + (half ? S::kBBytes / 2 : S::kBBytes)) * CG;
+          const CUtensorMap* wmap = half ? &maps.w_final64 : &maps.w[l];
+          for (int n_tile = n_begin(item, l); n_tile < ly.n_tiles; n_tile += n_step(item, l)) {
+            // weight rows of this CTA: half of the pair's 256 (or, for a column half, 128) output features
+            const int row_b = g * ly.b_rows_per_group + n_tile * kBlockN +
+                              (half ? item.role * kHalfN + int(cta_rank) * (kHalfN / 2) : int(cta_rank) * S::kBRows);
+            for (int kb = 0; kb < kb_total; ++kb) {
+              const int hk = ly.kb_h0 + kb - ly.kb_x;  // k-block inside the activation buffer (kb >= kb_x)
+              if (kb >= ly.kb_x) {
+                const int t = hk / kKbPerTile;         // column tile of the activation buffer
+                if (!shared || args.dep_role[t] == item.role) {
+                  const uint32_t need = done_tiles + (shared ? uint32_t(args.dep_ord[t]) : uint32_t(t)) + 1u;
+                  if (have < need) {
+                    unsigned int spins = 0;
+                    while ((have = ld_acquire_cta_smem(stored_cnt)) < need) {
+                      __nanosleep(32);
+                      if (++spins > (1u << 26)) __trap();  // a dependency that never arrives is a bug: trap, do not hang
+                    }
+                    chain_fence_proxy_async_global();  // the rows are read by the async proxy (TMA) next
+                  }
+                } else {
+                  const uint32_t need = uint32_t(args.dep_ord[t]) + 1u;
+                  if (have_partner < need) {
+                    unsigned int spins = 0;
+                    while ((have_partner = ld_acquire_gpu_u32(partner_cnt)) < need) {
+                      __nanosleep(64);
+                      if (++spins > (1u << 25)) __trap();
+                    }
+                    chain_fence_proxy_async_global();
+                  }
                 }
-                chain_fence_proxy_async_global();  // the rows are read by the async proxy (TMA) next
               }
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
+              uint8_t* sb = sa + kABytes;
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+              if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
+              else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
+              ptx::tma_load_2d<CG>(sb, wmap, &full_bar[stage], kb * BK, row_b);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CG);
-            if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
-            else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
-            ptx::tma_load_2d<CG>(sb, &maps.w[l], &full_bar[stage], kb * BK, row_b);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (shared) {
+          // every tile the partner stores has been seen (the final layer reads them all): leave the counter clean
+          if (args.tiles_per_role[1 - item.role] > 0) *partner_cnt = 0u;
+          done_tiles += uint32_t(args.tiles_per_role[item.role]);
+        } else {
+          done_tiles += uint32_t(args.hidden_tiles);
+        }
       }
-    }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
     if (leader && ptx::elect_one()) {
-      constexpr uint32_t idesc = make_idesc<E, CG>();
+      constexpr uint32_t idesc_full = make_idesc_n<E>(kBlockN);
+      constexpr uint32_t idesc_half = make_idesc_n<E>(kHalfN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int unit = pair; unit < units; unit += pairs) {
+      ChainItem item;
+      for (int i = 0; chain_item(args, pair, pairs, i, item); ++i) {
         for (int l = 0; l < args.n_layers; ++l) {
           const int kb_total = args.layer[l].kb_x + args.layer[l].kb_h;
-          for (int n_tile = 0; n_tile < args.layer[l].n_tiles; ++n_tile, ++it) {
+          const uint32_t idesc = (item.role >= 0 && l == n_hidden) ? idesc_half : idesc_full;
+          for (int n_tile = n_begin(item, l); n_tile < args.layer[l].n_tiles; n_tile += n_step(item, l), ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -229,21 +320,29 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
     int it = 0;
     uint32_t published = 0;   // epi_tid 0: value last written to stored_cnt
     bool pending = false;     // epi_tid 0: the previous hidden tile's stores are committed but not yet published
-    for (int unit = pair; unit < units; unit += pairs) {
-      const int g = unit % args.groups;
-      const int m_row = ((unit / args.groups) * CG + int(cta_rank)) * kBlockM;
-      const int row_h = args.h_slot ? slot_row : g * args.a_rows_per_group + m_row;
+    ChainItem item;
+    for (int i = 0; chain_item(args, pair, pairs, i, item); ++i) {
+      const bool shared = item.role >= 0;
+      const int g = item.unit % args.groups;
+      const int m_row = ((item.unit / args.groups) * CG + int(cta_rank)) * kBlockM;
+      const int row_h = (args.h_slot && !shared) ? slot_row : g * args.a_rows_per_group + m_row;
+      unsigned int* my_cnt = nullptr;   // shared unit: this CTA's tile counter, read by the partner pair
+      uint32_t my_tiles = 0;
+      if (shared)
+        my_cnt = args.tail_cnt + (((item.unit - (args.m_tiles * args.groups - args.tail_units)) * 2 + item.role) * 2 +
+                                  int(cta_rank));
       for (int l = 0; l < args.n_layers; ++l) {
         const ChainLayer& ly = args.layer[l];
-        const bool is_final = l == args.n_layers - 1;
-        for (int n_tile = 0; n_tile < ly.n_tiles; ++n_tile, ++it) {
+        const bool is_final = l == n_hidden;
+        const bool half = shared && is_final;
+        for (int n_tile = n_begin(item, l); n_tile < ly.n_tiles; n_tile += n_step(item, l), ++it) {
           const int acc = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
-          const int n0 = n_tile * kBlockN;
+          const int n0 = n_tile * kBlockN + (half ? item.role * kHalfN : 0);
           const float* bias_g = ly.bias ? ly.bias + size_t(g) * ly.n_tiles * kBlockN + n0 : nullptr;
           // stage the tile's per-column constants while its MMAs are still running
           float* cst = smem_const + (it & 1) * kEpiConstFloats;
-          {
+          if (!half || epi_tid < kHalfN / 2) {
             const int c0 = 2 * epi_tid;
             const float2 bv = bias_g ? __ldg(reinterpret_cast<const float2*>(bias_g + c0)) : make_float2(0.f, 0.f);
             *reinterpret_cast<float2*>(cst + c0) = bv;
@@ -261,7 +360,6 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
           ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
           ptx::tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
-          constexpr int kChunks = kBlockN / 32;
           uint32_t ra[32], rb[32];
           ptx::tmem_ld_32x32(taddr, ra);
 
@@ -340,14 +438,14 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
               ++store_it;
             }
           };
-          auto run_tile = [&](auto final_tag) {
+          auto run_tile = [&](auto final_tag, int n_chunks) {
 #pragma unroll 1
-            for (int c = 0; c < kChunks; c += 2) {
+            for (int c = 0; c < n_chunks; c += 2) {
               ptx::tmem_ld_wait();
               ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
               process(final_tag, ra, c);
               ptx::tmem_ld_wait();
-              if (c + 2 < kChunks) {
+              if (c + 2 < n_chunks) {
                 ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
               } else {
                 ptx::tcgen05_fence_before();
@@ -358,11 +456,11 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
             }
           };
           if (is_final) {
-            run_tile(std::true_type{});
+            run_tile(std::true_type{}, (half ? kHalfN : kBlockN) / 32);
           } else {
-            run_tile(std::false_type{});
+            run_tile(std::false_type{}, kBlockN / 32);
             if (epi_tid == 0) {
-              if (n_tile + 1 < ly.n_tiles) {
+              if (!shared && n_tile + 1 < ly.n_tiles) {
                 pending = true;   // the next tile (same layer) does not read this one: publish behind its first store
               } else {
                 // the next layer's K loop ends in these columns: publish as soon as the stores have landed
@@ -371,6 +469,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 published += pending ? 2u : 1u;
                 pending = false;
                 st_release_cta_smem(stored_cnt, published);
+                if (shared) st_release_gpu_u32(my_cnt, ++my_tiles);  // ... and the partner pair's next layer too
               }
             }
           }

@@ -596,3 +596,29 @@ def test_fused_final_kernel_matches_the_default_two_launch_path(tmp_path):
             scale = max(float(np.nanmax(np.abs(x))), 1e-12)
             assert float(np.nanmax(np.abs(x - y))) <= 2e-6 * scale, (k, float(np.nanmax(np.abs(x - y))), scale)
     assert np.isnan(a["E2000_s1_next"][3]).all() and not np.isnan(a["E2000_s1_next"][4]).any()
+
+
+def test_column_fused_forward_is_bit_identical_to_one_launch_per_layer(tmp_path):
+    """The default forward pass is ONE launch (csrc/gemm_chain.cuh): a CTA pair runs every layer of a (member, 256-row
+    env tile), the activations handed on through L2, the last partial round shared between pairs with the final layer
+    as M 256 x N 128 halves.  Every output element accumulates its K blocks in the same order as in the per-layer
+    launches (SIMSTEP_CHAIN=0), so ALL outputs of the step are bit-identical - for batches of 1 .. 40 001 rows, i.e.
+    with fewer units than CTA pairs, whole rounds only, and shared units in the last round (4 800 and 40 001 rows)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = {}
+    for mode in ("0", "1", "2", "3"):
+        out = str(tmp_path / f"chain{mode}.npz")
+        env = dict(os.environ, SIMSTEP_CHAIN=mode)
+        env.pop("SIMSTEP_FINAL_FUSED", None)
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "final_fused_check.py"), out], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        files[mode] = np.load(out)
+    ref = files["0"]
+    for mode in ("1", "2", "3"):
+        assert sorted(ref.files) == sorted(files[mode].files)
+        for k in ref.files:
+            assert np.array_equal(ref[k], files[mode][k], equal_nan=True), (mode, k)

@@ -25,7 +25,7 @@ def main(out_path):
     oc.w = torch.randn(512, generator=g) * 0.01
     eng.load_rff(oc.rff_weight, oc.rff_bias, split=True)
     res = {}
-    for E in (1, 127, 2000, 40001):
+    for E in (1, 127, 2000, 4800, 40001):
         s = H.humanoid_like_states(E, seed=70 + E % 7)
         a = torch.randn(E, 28, generator=g)
         member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32)
