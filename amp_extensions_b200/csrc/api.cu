@@ -481,8 +481,22 @@ int chain_mode() {
   return mode;
 }
 
-bool chain_ok(const simstep_handle* h) {
-  return chain_mode() != 0 && h->cg == 2 && h->L >= 1 && h->L + 1 <= kChainMaxLayers && h->have_ensemble;
+// The chain kernel lives on L2 hits: every pair re-reads its unit's activation rows layer after layer while all members'
+// weights stream past.  It is used while that working set - the packed weights plus one unit's [x | h] rows per CTA
+// pair - fits 90 % of the L2 (108 of 126 MB at 4 x (512 x 4); measured 10 % faster than one launch per layer); an
+// 8 x (1024 x 4) ensemble (136 MB of weights, 2.2 MB of activations per unit) thrashes it and was measured 14 % SLOWER,
+// so such shapes keep one launch per layer.
+bool chain_ok(const simstep_handle* h, long long rows_pad) {
+  if (chain_mode() == 0 || h->cg != 2 || h->L < 1 || h->L + 1 > kChainMaxLayers || !h->have_ensemble) return false;
+  static int l2_bytes[kMaxDevices] = {};
+  int& l2 = l2_bytes[h->device % kMaxDevices];
+  if (l2 == 0 && cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device) != cudaSuccess) l2 = 1;
+  double weights = 0;
+  for (const Layer& ly : h->layers) weights += double(h->N) * ly.o_pad * ly.k_pad * h->esize;
+  const long long units = rows_pad / (kBlockM * 2) * h->N;
+  const double pairs = double(std::min<long long>(units, h->sm_count / 2));
+  const double unit_bytes = double(kBlockM * 2) * (h->XP + h->HT) * h->esize;
+  return weights + pairs * unit_bytes <= 0.9 * double(l2);
 }
 
 int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
@@ -554,7 +568,7 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
-  if (last_layer == h->L && chain_ok(h) && !(tail != nullptr && final_fused_ok(h, *tail)))
+  if (last_layer == h->L && chain_ok(h, rows_pad) && !(tail != nullptr && final_fused_ok(h, *tail)))
     return launch_chain(h, rows_pad, st);
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
@@ -632,6 +646,8 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
   static const bool tma_off = [] { const char* e = std::getenv("SIMSTEP_POST_TMA"); return e && e[0] == '0'; }();
   const bool tma = !tma_off && plan.ok && vec2 && state != nullptr && next_state != nullptr &&
                    reinterpret_cast<uintptr_t>(state) % 16 == 0;
+  // the chain kernel writes the deltas in row order: the last rows are the ones still in L2 (SIMSTEP_POST_REVERSE=0: A/B)
+  static const int post_reverse = [] { const char* e = std::getenv("SIMSTEP_POST_REVERSE"); return (e && e[0] == '0') ? 0 : 1; }();
 #define POST_TMA_LAUNCH(NM, ET)                                                                                \
   do {                                                                                                         \
     auto kern = h->S == 226 ? post_step_tma_kernel<NM, ET, 226> : post_step_tma_kernel<NM, ET, 0>;             \
@@ -644,7 +660,7 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
     const long long pairs = (n + 1) / 2;                                                                       \
     const int grid = int(std::min<long long>((pairs + plan.rings - 1) / plan.rings, h->sm_count));             \
     launch_pdl(kern, dim3(grid), dim3(plan.rings * 64), plan.smem, st, h->dws, h->cap_rows, h->DP, state, member, \
-               num_steps, h->S, n, next_state, disc, done, h->term, rff, plan.stages);                         \
+               num_steps, h->S, n, next_state, disc, done, h->term, rff, plan.stages, post_reverse);           \
   } while (0)
 #define POST_CASE(NM)                                                                                          \
   case NM:                                                                                                     \
@@ -1199,6 +1215,13 @@ int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t rese
   CU_TRY(h, cudaMemcpy(&v, h->sat_dev, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with the device
   if (reset) CU_TRY(h, cudaMemset(h->sat_dev, 0, sizeof(v)));
   *count_out = static_cast<int64_t>(v);
+  return SIMSTEP_OK;
+}
+
+int simstep_forward_launches(const simstep_handle* h, int64_t n_envs, int32_t* launches_out) {
+  if (!h || !launches_out || n_envs < 1) return SIMSTEP_EINVAL;
+  const long long rows = std::min<long long>(round_up(n_envs, h->row_align), chunk_limit(h));
+  *launches_out = chain_ok(h, rows) && !final_fused_enabled() ? 1 : h->L + 1;
   return SIMSTEP_OK;
 }
 

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kPostTmaMaxWarps * 32, 1)
 post_step_tma_kernel(const float* __restrict__ delta, long long delta_rows, int DP, const float* state,
                      const int32_t* __restrict__ member, int32_t* num_steps, int S, long long n_rows,
                      float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done,
-                     const TermConst tc, const PostRff rff, int stages) {
+                     const TermConst tc, const PostRff rff, int stages, int reverse) {
   if (SC) S = SC;
   extern __shared__ __align__(128) uint8_t sm_post[];
   const int lane = threadIdx.x & 31;
@@ -294,9 +294,11 @@ post_step_tma_kernel(const float* __restrict__ delta, long long delta_rows, int 
   const long long t_global = blockIdx.x * static_cast<long long>(rings) + team;
   const long long t_total = static_cast<long long>(gridDim.x) * rings;
 
+  // reverse: walk the row pairs from the end - the delta rows the forward kernel wrote LAST are still in L2
+  auto phys = [&](long long pair) { return reverse ? n_pairs - 1 - pair : pair; };
   auto issue = [&](int stage, long long pair) {  // producer warp only
     uint8_t* dst = ring + size_t(stage) * stage_bytes;
-    const long long r0 = pair * 2;
+    const long long r0 = phys(pair) * 2;
     if (r0 + 1 < n_rows) {
       if (lane == 0) {
         ptx::mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
@@ -328,7 +330,7 @@ post_step_tma_kernel(const float* __restrict__ delta, long long delta_rows, int 
 
   // per-row scalars (active member, step counter) are fetched one pair ahead so their latency never stalls the warp
   auto scalars = [&](long long pair, int& mem, int& stp) {
-    const long long row = pair * 2 + trank;
+    const long long row = phys(pair) * 2 + trank;
     mem = 0;
     stp = 0;
     if (pair < n_pairs && row < n_rows) {
@@ -342,7 +344,7 @@ post_step_tma_kernel(const float* __restrict__ delta, long long delta_rows, int 
   int stage = 0;
   uint32_t phase = 0;
   for (long long pair = t_global; pair < n_pairs; pair += t_total) {
-    const long long row = pair * 2 + trank;
+    const long long row = phys(pair) * 2 + trank;
     const int mem = mem_n, stp = stp_n;
     scalars(pair + t_total, mem_n, stp_n);
     ptx::mbar_wait(&full[stage], phase);

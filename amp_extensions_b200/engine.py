@@ -197,6 +197,13 @@ class Engine:
         self._check(self.lib.simstep_saturation_count(self._h, C.byref(n), int(bool(reset))))
         return int(n.value)
 
+    def forward_launches(self, n_envs):
+        """Launches the ensemble forward pass takes for n_envs rows: 1 = the column-fused kernel (csrc/gemm_chain.cuh),
+        n_hidden + 1 = one grouped launch per layer (simstep_forward_launches)."""
+        n = C.c_int32(0)
+        self._check(self.lib.simstep_forward_launches(self._h, int(n_envs), C.byref(n)))
+        return int(n.value)
+
     def set_rff_split(self, split):
         """Turn the hi/lo (three-product) evaluation of the random-feature layer on or off (simstep_set_rff_split)."""
         self._check(self.lib.simstep_set_rff_split(self._h, int(bool(split))))

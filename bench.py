@@ -803,7 +803,10 @@ def run_ours(args):
             cpu, _ = time_cpu_reference(args.config, 1024 if n_models <= 4 else 512, min_seconds=12.0, max_reps=200)
             if single_env and "value" in single_env:
                 cpu["per_env_mode"]["gpu_plugin_single_env"] = single_env
-        roof = {"kernel": f"gemm_tcgen05_kernel ({len(hidden) + 1} ensemble layer launches per step)", "bound": "tensor",
+        fwd = eng.forward_launches(E)
+        roof = {"kernel": ("ensemble_chain_kernel (all ensemble layers of a (member, 256-row env tile) on one CTA pair, "
+                           "one launch per chunk)" if fwd == 1 else
+                           f"gemm_tcgen05_kernel ({fwd} ensemble layer launches per chunk)"), "bound": "tensor",
                 "unit": "TFLOP/s", "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["source"],
                 "algorithmic_flop_per_env_step": flop, "ms_per_step": gemm_ms}
         roof.update(tensor_roofline(achieved, total_ms * 1e-3, peaks))

@@ -123,6 +123,13 @@ int simstep_set_termination(simstep_handle* h, const simstep_termination* t);
  * the device.  A non-zero count means: use SIMSTEP_PREC_TF32 for this data. */
 int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t reset);
 
+/* How many launches the ensemble forward pass (DYN:422-433 for every member, all layers) takes for a pass of
+ * n_envs rows on this handle: 1 when the column-fused kernel runs (a CTA pair carries a (member, 256-row env tile)
+ * through every layer, activations handed on through L2 - used while the packed weights plus one unit's activation
+ * rows per CTA pair fit the L2), n_hidden + 1 when every layer is a grouped launch of its own.  No reference
+ * counterpart (BasicMLP.forward is one Python loop, DYN:427-432); reported by bench.py beside the timings. */
+int simstep_forward_launches(const simstep_handle* h, int64_t n_envs, int32_t* launches_out);
+
 /* Replaces the rff layer of RBFLinearCost (LC:53-55): weight_host [D,in_dim],
  * bias_host [D].  in_dim must be S (input_type 's'), 2S ('ss'), S+A ('sa') or
  * 2S+A ('sas').  split != 0 keeps ~21 mantissa bits of the pre-activation by

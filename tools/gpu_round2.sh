@@ -14,7 +14,7 @@ timeout 300 python tools/bench_imitation.py > $OUT/${TAG}_imit.json 2> $OUT/${TA
 CMD="python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline --skip-sustained"
 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1; echo "ncu_launches=$?"
-ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|post_step|prep_input' -s 16 -c 9 \
+ncu --set full --clock-control none --import-source on -k regex:'ensemble_chain|gemm_tcgen05|post_step|prep_input' -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-4} \
   -o $OUT/${TAG}_prof_step $CMD > $OUT/${TAG}_ncu_step.log 2>&1; echo "ncu_step=$?"
 python tools/bench_imitation.py --iters 3 --warmup 1 > $OUT/${TAG}_plain_imit.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:imitation_reward -s 1 -c 1 \

@@ -104,6 +104,9 @@ if os.path.exists(sp):
     gem = [b for (k, b) in t.get("__order__", []) if "gemm_tcgen05_kernel" in k and
            any(m in k for m in (", 0>", ", 1>", ", 0,", ", 1,"))]
     tr["ensemble_gemm_dram_bytes_per_step"] = sum(gem[:5]) if len(gem) >= 5 else None
+    chain = [b for (k, b) in t.get("__order__", []) if "ensemble_chain_kernel" in k]
+    if chain:   # the column-fused forward: one launch per step
+        tr["ensemble_gemm_dram_bytes_per_step"] = chain[0]
     for k, v in t.items():
         if k == "__order__":
             continue
