@@ -528,6 +528,12 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
     if (l < h->L) ca.hidden_tiles += c.n_tiles;
   }
   cl.maps.w_final64 = h->layers[h->L].tmap_w64;
+  // L2 eviction priorities of the kernel's TMA traffic: weights and activations evict_last (every unit of a member
+  // re-reads the same 5 MB of weights, a unit re-reads its own rows layer after layer), measured -2.5 % on the launch
+  // (and +2.5 us on the post-step kernel, whose delta rows find less room in L2); marking x / the output evict_first
+  // on top was measured neutral and is off.  SIMSTEP_CHAIN_HINTS=<mask> overrides for A/B runs.
+  static const int hints = [] { const char* e = std::getenv("SIMSTEP_CHAIN_HINTS"); return e ? std::atoi(e) : 3; }();
+  ca.l2_hints = hints;
   // the last, partial round: when its units are at most half the pairs, two pairs share each of them
   const int units = ca.m_tiles * ca.groups;
   const int pairs = std::min(units, h->sm_count / 2);

@@ -32,7 +32,9 @@
 //
 // Tried and dropped: a cluster of FOUR CTAs per unit (both pairs on one unit throughout, the A operand multicast between
 // them: 25 % fewer bytes out of L2, bit-identical results).  Only 33 such clusters are co-schedulable on the 148 SMs
-// (GPC sizes), 132 SMs instead of 148, and the launch was 12 % slower; the multicast itself changed nothing.
+// (GPC sizes), 132 SMs instead of 148, and the launch was 12 % slower; the multicast itself changed nothing.  Also
+// tried: running the first layer of the NEXT unit in front of the final layer of the current one (two slots per pair),
+// so that the short first layer's epilogues drain behind 36 k-blocks of MMAs - bit-identical, 1 % slower.
 //
 // Pipeline, barriers, TMEM double-buffering, the operand ring and the TMA-store epilogue are those of
 // gemm_tcgen05.cuh (CG = 2, one epilogue group); the accumulation order of every output element is the same as in
@@ -66,6 +68,7 @@ struct ChainArgs {
   int out_rows_per_group;  // row stride between members in the final output (delta workspace)
   int h_slot;              // slot mode: activation rows live at pair * 256 (+ 128 for the second CTA)
   int hidden_tiles;        // hidden tiles per unit (sum of n_tiles over the hidden layers)
+  int l2_hints;            // bit 0: weights evict_last, 1: activations evict_last, 2: x evict_first, 3: output evict_first
   const float* scale;      // final layer: [n_tiles * kBlockN] or nullptr (dynamics.py:231-232)
   const float* shift;
   // the last, partial round: units [units - tail_units, units) are shared by two pairs each (0: plain extra round)
@@ -102,6 +105,35 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const unsigned int* p) {
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// L2 eviction-priority policies and the hinted forms of the pair's TMA load / the TMA store
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                                      int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(bar) & 0xFEFFFFFFu),
+        "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+
 template <typename E>
 __host__ __device__ constexpr uint32_t make_idesc_n(int n) {
   return (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
@@ -202,6 +234,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
       uint32_t have = 0;       // last value seen in stored_cnt
       uint32_t done_tiles = 0; // hidden tiles this CTA stored in the items before the current one
       ChainItem item;
@@ -256,9 +289,15 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
               uint8_t* sa = smem_tiles + size_t(stage) * S::kStageBytes;
               uint8_t* sb = sa + kABytes;
               if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-              if (kb < ly.kb_x) ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
-              else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
-              ptx::tma_load_2d<CG>(sb, wmap, &full_bar[stage], kb * BK, row_b);
+              if (kb < ly.kb_x) {
+                if (args.l2_hints & 4) tma_load_2d_pair_hint(sa, &maps.x, &full_bar[stage], kb * BK, m_row, pol_first);
+                else ptx::tma_load_2d<CG>(sa, &maps.x, &full_bar[stage], kb * BK, m_row);
+              } else {
+                if (args.l2_hints & 2) tma_load_2d_pair_hint(sa, &maps.h, &full_bar[stage], hk * BK, row_ah, pol_last);
+                else ptx::tma_load_2d<CG>(sa, &maps.h, &full_bar[stage], hk * BK, row_ah);
+              }
+              if (args.l2_hints & 1) tma_load_2d_pair_hint(sb, wmap, &full_bar[stage], kb * BK, row_b, pol_last);
+              else ptx::tma_load_2d<CG>(sb, wmap, &full_bar[stage], kb * BK, row_b);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -420,11 +459,19 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
               ptx::named_bar_sync(2, kNumEpiThreads);
               if (epi_tid == 0) {
                 const int col = (kFinal ? 0 : ly.out_col0) + n0 + (c / kChunksPerStore) * kTileCols;
-                if constexpr (kFinal)
-                  ptx::tma_store_2d(&maps.out_final, smem_out + size_t(buf) * kOutStageBytes, col,
-                                    g * args.out_rows_per_group + m_row);
-                else
-                  ptx::tma_store_2d(&maps.h, smem_out + size_t(buf) * kOutStageBytes, col, row_h);
+                if constexpr (kFinal) {
+                  if (args.l2_hints & 8)
+                    tma_store_2d_hint(&maps.out_final, smem_out + size_t(buf) * kOutStageBytes, col,
+                                      g * args.out_rows_per_group + m_row, l2_policy_evict_first());
+                  else
+                    ptx::tma_store_2d(&maps.out_final, smem_out + size_t(buf) * kOutStageBytes, col,
+                                      g * args.out_rows_per_group + m_row);
+                } else {
+                  if (args.l2_hints & 2)
+                    tma_store_2d_hint(&maps.h, smem_out + size_t(buf) * kOutStageBytes, col, row_h, l2_policy_evict_last());
+                  else
+                    ptx::tma_store_2d(&maps.h, smem_out + size_t(buf) * kOutStageBytes, col, row_h);
+                }
                 ptx::tma_store_commit();
                 if (pending) {
                   // the previous hidden tile (same layer: nothing this CTA runs next reads it yet) - every group but
