@@ -64,7 +64,10 @@ __device__ __forceinline__ typename Pair<typename E::storage>::type make_pair_cv
 // instructions for 61 MB of traffic), hence the per-thread source pointer,
 // the hoisted reciprocal scale and the pointer-stepped row loop.
 constexpr int kPrepThreads = 128;
-constexpr int kPrepRows = 4;
+#ifndef SIMSTEP_PREP_ROWS
+#define SIMSTEP_PREP_ROWS 4
+#endif
+constexpr int kPrepRows = SIMSTEP_PREP_ROWS;
 template <typename E, bool VEC>
 __global__ void __launch_bounds__(kPrepThreads)
 prep_input_kernel(const float* __restrict__ state, const float* __restrict__ action, int S, int A, int XP,
