@@ -204,6 +204,17 @@ class Engine:
         self._check(self.lib.simstep_forward_launches(self._h, int(n_envs), C.byref(n)))
         return int(n.value)
 
+    def round_rows(self, n_envs):
+        """Row granule at which a pass of the column-fused forward kernel ends on a whole round of its CTA pairs: the
+        kernel's units are (256-row env tile, member) pairs taken round-robin by sm_count / 2 CTA pairs, so a chunk of
+        lcm(pairs, N) / N env tiles leaves no partial round.  256 when every layer is a launch of its own.  Callers that
+        split a batch into chunks (HostEnvPipeline) cut at multiples of it."""
+        if self.forward_launches(n_envs) != 1:
+            return 256
+        import math
+        pairs = torch.cuda.get_device_properties(self.device).multi_processor_count // 2
+        return 256 * (math.lcm(pairs, self.N) // self.N)
+
     def set_rff_split(self, split):
         """Turn the hi/lo (three-product) evaluation of the random-feature layer on or off (simstep_set_rff_split)."""
         self._check(self.lib.simstep_set_rff_split(self._h, int(bool(split))))
