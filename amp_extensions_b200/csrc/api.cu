@@ -74,6 +74,7 @@ struct simstep_handle {
   void* hbuf = nullptr;
   float* dws = nullptr;
   unsigned int* tickets = nullptr;  // fused final layer: one arrival counter per 128-row block (gemm_final.cuh)
+  bool forward_was_chain = false;     // the workspace's deltas were written by the chain kernel (in row order)
   unsigned int* chain_cnt = nullptr;  // chain kernel: tile counters of the shared units of the last round (zero between launches)
   CUtensorMap tmap_x, tmap_h, tmap_dws;
 
@@ -574,8 +575,11 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   }
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
-  if (last_layer == h->L && chain_ok(h, rows_pad) && !(tail != nullptr && final_fused_ok(h, *tail)))
+  h->forward_was_chain = false;
+  if (last_layer == h->L && chain_ok(h, rows_pad) && !(tail != nullptr && final_fused_ok(h, *tail))) {
+    h->forward_was_chain = true;
     return launch_chain(h, rows_pad, st);
+  }
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
     if (l == h->L && tail != nullptr && final_fused_ok(h, *tail)) {
@@ -652,8 +656,10 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
   static const bool tma_off = [] { const char* e = std::getenv("SIMSTEP_POST_TMA"); return e && e[0] == '0'; }();
   const bool tma = !tma_off && plan.ok && vec2 && state != nullptr && next_state != nullptr &&
                    reinterpret_cast<uintptr_t>(state) % 16 == 0;
-  // the chain kernel writes the deltas in row order: the last rows are the ones still in L2 (SIMSTEP_POST_REVERSE=0: A/B)
-  static const int post_reverse = [] { const char* e = std::getenv("SIMSTEP_POST_REVERSE"); return (e && e[0] == '0') ? 0 : 1; }();
+  // the chain kernel writes the deltas in row order: the last rows are the ones still in L2, so the rows are walked
+  // backwards (SIMSTEP_POST_REVERSE=0: A/B); the per-layer final GEMM itself runs backwards, its LAST rows are row 0's
+  static const int post_reverse_on = [] { const char* e = std::getenv("SIMSTEP_POST_REVERSE"); return (e && e[0] == '0') ? 0 : 1; }();
+  const int post_reverse = (post_reverse_on && h->forward_was_chain) ? 1 : 0;
 #define POST_TMA_LAUNCH(NM, ET)                                                                                \
   do {                                                                                                         \
     auto kern = h->S == 226 ? post_step_tma_kernel<NM, ET, 226> : post_step_tma_kernel<NM, ET, 0>;             \
