@@ -622,3 +622,38 @@ def test_column_fused_forward_is_bit_identical_to_one_launch_per_layer(tmp_path)
         assert sorted(ref.files) == sorted(files[mode].files)
         for k in ref.files:
             assert np.array_equal(ref[k], files[mode][k], equal_nan=True), (mode, k)
+
+
+def test_column_fused_forward_replays_from_a_cuda_graph_with_shared_units():
+    """4 800 rows are 76 units for 74 CTA pairs: two units of the last round are shared between pairs through the
+    global tile counters, which the kernel itself leaves clean - so the step can be captured once and replayed (the
+    rollout and the single-env plugin do) with bit-identical results, replay after replay."""
+    from amp_extensions_b200.engine import Engine, HumanoidTermination
+    c = H.ns_case()
+    eng = Engine(c["S"], c["A"], c["N"], c["hidden"], dense_connect=True, activation="relu", transform=True,
+                 precision="fp16")
+    eng.load_ensemble(c["ws"], c["bs"], c["tf"])
+    eng.set_termination(HumanoidTermination(enable_velocity_check=True))
+    E = 4800
+    assert eng.forward_launches(E) == 1
+    g = torch.Generator().manual_seed(9)
+    s = H.humanoid_like_states(E, seed=3).cuda()
+    a = torch.randn(E, 28, generator=g).cuda()
+    member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32).cuda()
+    steps0 = torch.zeros(E, dtype=torch.int32, device="cuda")
+    ref = eng.step(s, a, member, steps0.clone())
+    ref = [t.clone() for t in ref]
+    steps = steps0.clone()
+    out = [torch.empty_like(t) for t in ref]
+    eng.step(s, a, member, steps, next_state=out[0], disc=out[1], done=out[2])      # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.step(s, a, member, steps, next_state=out[0], disc=out[1], done=out[2])
+    for _ in range(3):
+        for t in out:
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for got, want in zip(out, ref):
+            assert torch.equal(got, want)
