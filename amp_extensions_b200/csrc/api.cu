@@ -603,10 +603,6 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
     if (l < h->L) {
       // bias + activation straight into this layer's K-slice of the concat buffer
       ga.out_col0 = ly.out_col0;
-      // short-K layers (the first one): the tile's weight half stays in the ring while consecutive tiles of a CTA
-      // pair share their (member, n-tile); SIMSTEP_GEMM_B_RESIDENT=0/1 overrides for A/B runs
-      static const int bres = [] { const char* e = std::getenv("SIMSTEP_GEMM_B_RESIDENT"); return e ? std::atoi(e) : -1; }();
-      ga.b_resident = bres >= 0 ? bres : 0;
       rc = h->cfg.activation == SIMSTEP_ACT_RELU
                ? launch_gemm<kEpiHidden>(h, h->cfg.precision, h->cg, h->tmap_x, h->tmap_h, ly.tmap_w, h->tmap_h, ga,
                                          h->sm_count, st)

@@ -203,7 +203,6 @@ struct GemmArgs {
   int group_fastest;      // tile -> (m_tile, group, n_tile): the members of an env tile run side by side on
                           // neighbouring CTA pairs, so the shared x tile is read from HBM once instead of per member
   int reverse;            // walk the tile space backwards: the rows the previous layer wrote LAST (still in L2) first
-  int b_resident;         // whole K fits the ring: keep a stage's weight half while consecutive tiles share (group, n)
   int m_tiles;
   int n_tiles;
   int groups;
@@ -339,7 +338,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     if (args.group_fastest) { g = t2 % args.groups; m_tile = t2 / args.groups; }
     else { m_tile = t2 % args.m_tiles; g = t2 / args.m_tiles; }
   };
-  const bool b_resident = (SIMSTEP_GEMM_B_RESIDENT != 0 || args.b_resident != 0) && kb_total <= kStages;
+  const bool b_resident = SIMSTEP_GEMM_B_RESIDENT != 0 && kb_total <= kStages;
   const int ring = b_resident ? kb_total : kStages;
 
   if (warp == 0) {
