@@ -137,6 +137,57 @@ class RolloutBatch:
         return out
 
 
+class HostPathStream:
+    """Double-buffered download of rollout batches for a learner on the host: the paths of collect() k cross PCIe on a
+    copy stream into pinned memory while collect() k+1 already runs on the compute stream (the reference's sampler hands
+    its paths over in one piece per batch as well, milo/milo/sampler.py:87-130).
+
+        dl = HostPathStream(device)
+        dl.submit(rollout.collect(T))            # returns at once
+        dl.submit(rollout.collect(T))            # second horizon computes while the first downloads
+        host = dl.collect()                      # pinned tensors of the OLDEST submitted batch (waits for its copy)
+    """
+
+    NAMES = ("observations", "actions", "rewards", "done", "disc")
+
+    def __init__(self, device, names=None, depth=2):
+        self.device = torch.device(device)
+        self.names = tuple(names or self.NAMES)
+        self.depth = int(depth)
+        self.stream = torch.cuda.Stream(self.device)
+        self._slots = [None] * self.depth      # pinned host tensors per slot, allocated on first use
+        self._queue = []                       # (slot, event, batch) in submission order
+        self._next = 0
+        self.bytes_per_batch = 0
+
+    def submit(self, batch):
+        if len(self._queue) >= self.depth:
+            raise RuntimeError("HostPathStream: collect() the oldest batch before submitting another")
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        src = {n: getattr(batch, n) for n in self.names}
+        if self._slots[slot] is None or any(self._slots[slot][n].shape != t.shape for n, t in src.items()):
+            self._slots[slot] = {n: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for n, t in src.items()}
+        self.bytes_per_batch = sum(t.numel() * t.element_size() for t in src.values())
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            for n, t in src.items():
+                self._slots[slot][n].copy_(t, non_blocking=True)
+                t.record_stream(self.stream)   # the caching allocator must not hand the buffer out before the copy
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        self._queue.append((slot, done, batch))
+
+    def collect(self):
+        if not self._queue:
+            raise RuntimeError("HostPathStream: nothing submitted")
+        slot, done, _ = self._queue.pop(0)
+        done.synchronize()
+        return self._slots[slot]
+
+
 class DeviceRollout:
     """E-environment rollout loop on one GPU.
 

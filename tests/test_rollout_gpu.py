@@ -499,3 +499,37 @@ def test_reward_replacement_matches_the_reference_train_step():
         ref = g[f"info_{key}"]
         assert float(np.abs(np.asarray(infos[key]) - ref).max()) < 1e-3 * max(float(np.abs(ref).max()), r_scale), key
     assert abs(infos["bonus_mmd"] - float(g["bonus_mmd"])) < 1e-3 * max(abs(float(g["bonus_mmd"])), r_scale)
+
+
+def test_host_path_stream_downloads_behind_the_next_collect():
+    """HostPathStream: batch k is copied to pinned memory on a copy stream while collect() k+1 is already queued; what
+    arrives equals a plain .cpu() of the same batch, batches come back in submission order, and a third submit without
+    a collect is refused."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, HumanoidTermination, VecSimEnv
+    from amp_extensions_b200.rollout import DeviceRollout, HostPathStream
+    c = H.tiny_case("tiny_dense")
+    S, A = c["S"], c["A"]
+    s, a, s2 = c["ds"]
+    ens = DynamicsEnsemble(S, A, AmpDataset(s, a, s2), None, num_models=c["N"], hidden_sizes=c["hidden"],
+                           dense_connect=True, transform=True, base_seed=100)
+    env = VecSimEnv(ens, 48, termination=HumanoidTermination(horizon=5, fall_contact_bodies=()), reset_states=s[:32],
+                    seed=0)
+    env.reset()
+    g = torch.Generator().manual_seed(0)
+    ws = [torch.randn(8, S, generator=g) * 0.1, torch.randn(A, 8, generator=g) * 0.1]
+    bs = [torch.zeros(8), torch.zeros(A)]
+    ro = DeviceRollout(env, _Policy(_FC(ws, bs, "tanh"), np.full(A, -1.0, np.float32)), seed=0)
+    dl = HostPathStream(env.device)
+    b0 = ro.collect(6)
+    dl.submit(b0)
+    b1 = ro.collect(6)
+    dl.submit(b1)
+    with pytest.raises(RuntimeError):
+        dl.submit(b1)
+    for b in (b0, b1):
+        host = dl.collect()
+        for n in HostPathStream.NAMES:
+            assert torch.equal(host[n], getattr(b, n).cpu()), n
+    assert dl.bytes_per_batch == sum(getattr(b1, n).numel() * getattr(b1, n).element_size() for n in HostPathStream.NAMES)
+    with pytest.raises(RuntimeError):
+        dl.collect()
