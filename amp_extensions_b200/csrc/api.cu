@@ -74,6 +74,11 @@ struct simstep_handle {
   void* hbuf = nullptr;
   float* dws = nullptr;
   unsigned int* tickets = nullptr;  // fused final layer: one arrival counter per 128-row block (gemm_final.cuh)
+  // SIMSTEP_DEBUG_GUARDS=1 (read at simstep_create): every workspace buffer sits between two 64 KB guard zones filled with
+  // 0xA5; simstep_debug_check_guards counts the guard bytes that no longer are (compute-sanitizer is not available on
+  // the GPU boxes: this is the out-of-bounds check the test suite runs instead)
+  bool guards_on = false;
+  std::vector<std::pair<void*, size_t>> guard_allocs;  // (user pointer, user bytes)
   bool forward_was_chain = false;     // the workspace's deltas were written by the chain kernel (in row order)
   unsigned int* chain_cnt = nullptr;  // chain kernel: tile counters of the shared units of the last round (zero between launches)
   CUtensorMap tmap_x, tmap_h, tmap_dws;
@@ -320,14 +325,42 @@ int pack_matrix(simstep_handle* h, int prec, const float* src_dev, int src_pitch
   return SIMSTEP_OK;
 }
 
+constexpr size_t kGuardBytes = 64 * 1024;
+
+cudaError_t ws_alloc_bytes(simstep_handle* h, void** p, size_t bytes) {
+  if (!h->guards_on) return cudaMalloc(p, bytes);
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, bytes + 2 * kGuardBytes);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, 0xA5, kGuardBytes);
+  cudaMemset(base + kGuardBytes + bytes, 0xA5, kGuardBytes);
+  *p = base + kGuardBytes;
+  h->guard_allocs.emplace_back(*p, bytes);
+  return cudaSuccess;
+}
+template <typename T>
+cudaError_t ws_alloc(simstep_handle* h, T** p, size_t bytes) {
+  return ws_alloc_bytes(h, reinterpret_cast<void**>(p), bytes);
+}
+void ws_free(simstep_handle* h, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->guard_allocs.size(); ++i)
+    if (h->guard_allocs[i].first == p) {
+      cudaFree(static_cast<char*>(p) - kGuardBytes);
+      h->guard_allocs.erase(h->guard_allocs.begin() + i);
+      return;
+    }
+  cudaFree(p);
+}
+
 void free_workspace(simstep_handle* h) {
-  cudaFree(h->xbuf); h->xbuf = nullptr;
-  cudaFree(h->hbuf); h->hbuf = nullptr;
-  cudaFree(h->dws); h->dws = nullptr;
+  ws_free(h, h->xbuf); h->xbuf = nullptr;
+  ws_free(h, h->hbuf); h->hbuf = nullptr;
+  ws_free(h, h->dws); h->dws = nullptr;
   cudaFree(h->tickets); h->tickets = nullptr;
   cudaFree(h->chain_cnt); h->chain_cnt = nullptr;
-  cudaFree(h->rffin); h->rffin = nullptr;
-  cudaFree(h->rff_part); h->rff_part = nullptr;
+  ws_free(h, h->rffin); h->rffin = nullptr;
+  ws_free(h, h->rff_part); h->rff_part = nullptr;
   h->cap_rows = 0;
 }
 
@@ -346,9 +379,9 @@ int ensure_workspace(simstep_handle* h, long long rows) {
   free_workspace(h);
   const int prec = h->cfg.precision;
   if (h->have_ensemble || h->S > 0) {
-    CU_TRY(h, cudaMalloc(&h->xbuf, size_t(rows) * h->XP * h->esize));
-    if (h->HT > 0) CU_TRY(h, cudaMalloc(&h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
-    CU_TRY(h, cudaMalloc(&h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
+    CU_TRY(h, ws_alloc(h, &h->xbuf, size_t(rows) * h->XP * h->esize));
+    if (h->HT > 0) CU_TRY(h, ws_alloc(h, &h->hbuf, size_t(h->N) * rows * h->HT * h->esize));
+    CU_TRY(h, ws_alloc(h, &h->dws, size_t(h->N) * rows * h->DP * sizeof(float)));
     CU_TRY(h, cudaMalloc(&h->tickets, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
     CU_TRY(h, cudaMemset(h->tickets, 0, size_t(rows / kBlockM + 2) * sizeof(unsigned int)));
     CU_TRY(h, cudaMalloc(&h->chain_cnt, size_t(h->sm_count) * 2 * sizeof(unsigned int)));
@@ -370,12 +403,12 @@ int ensure_workspace(simstep_handle* h, long long rows) {
     if (rc) return rc;
   }
   if (h->have_rff && h->feat_net) {
-    CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));  // A operand = hbuf
+    CU_TRY(h, ws_alloc(h, &h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));  // A operand = hbuf
   } else if (h->have_rff) {
     const int rka = h->rff_split_cap ? 2 * h->RK : h->RK;  // [hi | lo]; the hi block is read twice by the GEMM
-    CU_TRY(h, cudaMalloc(&h->rffin, size_t(rows) * rka * h->esize));
+    CU_TRY(h, ws_alloc(h, &h->rffin, size_t(rows) * rka * h->esize));
     CU_TRY(h, cudaMemset(h->rffin, 0, size_t(rows) * rka * h->esize));
-    CU_TRY(h, cudaMalloc(&h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));
+    CU_TRY(h, ws_alloc(h, &h->rff_part, size_t(h->D_pad / kBlockN) * rows * sizeof(float)));
     int rc = encode_operand(h, &h->tmap_rffin, prec, h->rffin, rka, rows, rka, kBlockM);
     if (rc) return rc;
   }
@@ -934,6 +967,7 @@ int simstep_create(const simstep_config* cfg, simstep_handle** out) {
   h->esize = cfg->precision == SIMSTEP_PREC_TF32 ? 4 : 2;
   h->bk = 128 / h->esize;
   h->cg = gemm_cta_group();
+  { const char* e = std::getenv("SIMSTEP_DEBUG_GUARDS"); h->guards_on = e && e[0] == '1'; }
   h->row_align = kBlockM * h->cg;
   h->S = cfg->state_dim;
   h->A = cfg->action_dim;
@@ -1100,7 +1134,7 @@ int simstep_load_rff(simstep_handle* h, int32_t feature_dim, int32_t in_dim, con
   DeviceScope dev_scope(h->device);  // parameters live on the handle's device; the caller's current device is restored
   CU_TRY(h, cudaDeviceSynchronize());
   cudaFree(h->rff_w); cudaFree(h->rff_b); cudaFree(h->rff_wpad); cudaFree(h->colsum_partial);
-  cudaFree(h->rffin); cudaFree(h->rff_part);
+  ws_free(h, h->rffin); ws_free(h, h->rff_part);
   h->rff_w = nullptr; h->rff_b = nullptr; h->rff_wpad = nullptr; h->colsum_partial = nullptr;
   h->rffin = nullptr; h->rff_part = nullptr;
   h->have_rff = false;
@@ -1168,7 +1202,7 @@ int simstep_load_feature_net(simstep_handle* h, const float* const* weights_host
   if (!h->tf_dev) CU_TRY(h, cudaMalloc(&h->tf_dev, size_t(2 * h->S + 4) * sizeof(float)));
   // head = cos-feature layer over the last hidden activations (reuses the random-feature GEMM epilogue)
   cudaFree(h->rff_w); cudaFree(h->rff_b); cudaFree(h->rff_wpad); cudaFree(h->colsum_partial);
-  cudaFree(h->rffin); cudaFree(h->rff_part);
+  ws_free(h, h->rffin); ws_free(h, h->rff_part);
   h->rff_w = nullptr; h->rff_b = nullptr; h->rff_wpad = nullptr; h->colsum_partial = nullptr;
   h->rffin = nullptr; h->rff_part = nullptr;
   h->have_rff = false;
@@ -1223,6 +1257,24 @@ int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t rese
   CU_TRY(h, cudaMemcpy(&v, h->sat_dev, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises with the device
   if (reset) CU_TRY(h, cudaMemset(h->sat_dev, 0, sizeof(v)));
   *count_out = static_cast<int64_t>(v);
+  return SIMSTEP_OK;
+}
+
+int simstep_debug_check_guards(simstep_handle* h, int64_t* buffers_out, int64_t* bad_bytes_out) {
+  if (!h || !buffers_out || !bad_bytes_out) return fail(h, SIMSTEP_EINVAL, "null argument");
+  *buffers_out = static_cast<int64_t>(h->guard_allocs.size());
+  *bad_bytes_out = 0;
+  if (!h->guards_on) return SIMSTEP_OK;
+  CU_TRY(h, cudaDeviceSynchronize());
+  std::vector<unsigned char> host(kGuardBytes);
+  for (const auto& g : h->guard_allocs) {
+    const char* user = static_cast<const char*>(g.first);
+    const char* zones[2] = {user - kGuardBytes, user + g.second};
+    for (const char* z : zones) {
+      CU_TRY(h, cudaMemcpy(host.data(), z, kGuardBytes, cudaMemcpyDeviceToHost));
+      for (unsigned char b : host) *bad_bytes_out += b != 0xA5;
+    }
+  }
   return SIMSTEP_OK;
 }
 

@@ -204,6 +204,13 @@ class Engine:
         self._check(self.lib.simstep_forward_launches(self._h, int(n_envs), C.byref(n)))
         return int(n.value)
 
+    def check_guards(self):
+        """(guarded buffers, overwritten guard bytes) of the handle's workspaces; buffers are only guarded when
+        SIMSTEP_DEBUG_GUARDS=1 was set when the engine was created (simstep_debug_check_guards).  Synchronises."""
+        n, bad = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.simstep_debug_check_guards(self._h, C.byref(n), C.byref(bad)))
+        return int(n.value), int(bad.value)
+
     def round_rows(self, n_envs):
         """Row granule at which a pass of the column-fused forward kernel ends on a whole round of its CTA pairs: the
         kernel's units are (256-row env tile, member) pairs taken round-robin by sm_count / 2 CTA pairs, so a chunk of

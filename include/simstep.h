@@ -130,6 +130,13 @@ int simstep_saturation_count(simstep_handle* h, int64_t* count_out, int32_t rese
  * counterpart (BasicMLP.forward is one Python loop, DYN:427-432); reported by bench.py beside the timings. */
 int simstep_forward_launches(const simstep_handle* h, int64_t n_envs, int32_t* launches_out);
 
+/* Out-of-bounds check of the handle's workspaces (compute-sanitizer is not available where the GPU tests run): with
+ * SIMSTEP_DEBUG_GUARDS=1 in the environment at simstep_create every workspace buffer (normalised inputs, activations,
+ * member deltas, cost operand rows, partial dots) is allocated between two 64 KB guard zones filled with 0xA5.
+ * buffers_out = guarded buffers currently allocated (0 when the switch is off), bad_bytes_out = guard bytes that
+ * have been overwritten.  Synchronises with the device.  No reference counterpart. */
+int simstep_debug_check_guards(simstep_handle* h, int64_t* buffers_out, int64_t* bad_bytes_out);
+
 /* Replaces the rff layer of RBFLinearCost (LC:53-55): weight_host [D,in_dim],
  * bias_host [D].  in_dim must be S (input_type 's'), 2S ('ss'), S+A ('sa') or
  * 2S+A ('sas').  split != 0 keeps ~21 mantissa bits of the pre-activation by

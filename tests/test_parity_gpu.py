@@ -657,3 +657,49 @@ def test_column_fused_forward_replays_from_a_cuda_graph_with_shared_units():
         torch.cuda.synchronize()
         for got, want in zip(out, ref):
             assert torch.equal(got, want)
+
+
+def test_workspace_guard_zones_stay_intact(tmp_path):
+    """compute-sanitizer is not available on the GPU boxes; SIMSTEP_DEBUG_GUARDS=1 puts every workspace buffer between
+    two 64 KB guard zones instead (simstep_debug_check_guards).  A separate process (the switch is read at
+    simstep_create) runs the step + cost at ragged and tile-aligned batch sizes - one launch per layer, the
+    column-fused forward kernel with whole rounds only, with shared units, and the chunked path - and no guard byte
+    may change."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import milo_oracle as mo
+from tests import helpers as H
+from amp_extensions_b200.engine import Engine, HumanoidTermination
+c = H.ns_case()
+for prec, chunk in (("fp16", 0), ("tf32", 0), ("fp16", 4096)):
+    eng = Engine(c["S"], c["A"], c["N"], c["hidden"], dense_connect=True, activation="relu", transform=True,
+                 precision=prec, **({"max_chunk_envs": chunk} if chunk else {}))
+    eng.load_ensemble(c["ws"], c["bs"], c["tf"])
+    eng.set_termination(HumanoidTermination(enable_velocity_check=True))
+    oc = mo.RffCostOracle(H.ns_expert(), feature_dim=512, input_type="ss", bw_quantile=0.1, lambda_b=0.0025, seed=100)
+    eng.load_rff(oc.rff_weight, oc.rff_bias, split=True)
+    g = torch.Generator().manual_seed(1)
+    w = (torch.randn(512, generator=g) * 0.01).cuda()
+    for E in (1, 255, 256, 257, 4800, 9473, 20001):
+        s = H.humanoid_like_states(E, seed=E %% 5).cuda()
+        a = torch.randn(E, 28, generator=g).cuda()
+        member = torch.randint(0, 4, (E,), generator=g, dtype=torch.int32).cuda()
+        steps = torch.zeros(E, dtype=torch.int32, device="cuda")
+        for split in (True, False):
+            eng.set_rff_split(split)
+            eng.step_cost(s, a, member, steps, w, 0.0025, c["threshold"])
+        eng.discrepancy(s, a)
+    n, bad = eng.check_guards()
+    print("GUARDS", prec, chunk, n, bad)
+    assert n >= 4 and bad == 0, (prec, chunk, n, bad)
+''' % root
+    for chain in ("0", "2"):
+        env = dict(os.environ, SIMSTEP_DEBUG_GUARDS="1", SIMSTEP_CHAIN=chain)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+        assert res.stdout.count("GUARDS") == 3
