@@ -10,6 +10,7 @@ offset, KinCharacter.cpp:573-640) plus an optional world offset of its origin.
 import torch
 
 from . import engine as _engine
+from . import reset_noise as _reset_noise
 from .character import Character, humanoid3d
 from .motion import MotionClip
 
@@ -43,10 +44,16 @@ class ImitationReward:
             raise NotImplementedError("state features need the body attach rotations this character was loaded without")
         return self.engine.record_state(pose, vel, **flags)
 
-    def reset_states(self, kin_time, kin_origin=None, **flags):
-        """Initial env states for clip times (sim_env.py:270-285 with resolve / noise off: the character is set
-        to the kinematic pose and velocity at `kin_time` and its state is recorded)."""
+    def reset_states(self, kin_time, kin_origin=None, reset_args=None, generator=None, draws=None, **flags):
+        """Initial env states for clip times (sim_env.py:270-285): the character is set to the kinematic pose and
+        velocity at `kin_time`, perturbed as `reset_args` says (the plugin's dict, sim_env.py:28-31: noise_bef_rot,
+        noise_min / noise_max, radian, rot_vel_w_pose, vel_noise, interp, knee_rot -> cKinCharacter::AddNoise,
+        KinCharacter.cpp:340-532, batched in reset_noise.add_reset_noise; `resolve` needs the simulator and is not
+        applied) and its state is recorded.  generator: torch generator of the noise draws; draws: explicit draws."""
         pose, vel = self.sample(kin_time, kin_origin)
+        kw = _reset_noise.reset_kwargs(reset_args)
+        if kw is not None:
+            pose, vel = _reset_noise.add_reset_noise(self.character, pose, vel, generator=generator, draws=draws, **kw)
         return self.record_state(pose, vel, **flags)
 
     @staticmethod

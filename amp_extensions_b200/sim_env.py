@@ -79,14 +79,27 @@ class VecSimEnv:
 
     # -- gym-like surface -------------------------------------------------------------------
     @staticmethod
-    def clip_reset_fn(imitation, device=None, **record_flags):
-        """reset_fn that starts envs on the reference motion at t ~ U(0, duration), as SimEnv.reset() does through
-        the simulator (sim_env.py:270-285: reset_time(time) then record_state) — here without the simulator: the
-        clip is sampled on the device and the state features are built kinematically
-        (ImitationReward.reset_states; resolve-ground-intersection and noise options are not applied)."""
+    def clip_reset_fn(imitation, device=None, reset_args=None, **record_flags):
+        """reset_fn that starts envs on the reference motion at t ~ U(0, duration) - or U(time_min, time_max) with
+        reset_args['custom_time'] (sim_env.py:76-77) - as SimEnv.reset() does through the simulator (sim_env.py:270-285:
+        reset_time(time, **reset_dict) then record_state) — here without the simulator: the clip is sampled on the
+        device, the pose / velocity noise of `reset_args` (the plugin's dict, sim_env.py:28-31) is applied there too
+        (reset_noise.add_reset_noise = cKinCharacter::AddNoise, KinCharacter.cpp:340-532) and the state features are
+        built kinematically (ImitationReward.reset_states).  `resolve` (ground intersection of the simulated character)
+        needs the simulator and is not applied."""
+        t_lo, t_hi = 0.0, float(imitation.clip.duration)
+        if reset_args and reset_args.get("custom_time", False):
+            t_lo, t_hi = float(reset_args["time_min"]), float(reset_args["time_max"])
+        gen = [None]
+
         def fn(n, rng):
-            t = torch.as_tensor(rng.uniform(0.0, float(imitation.clip.duration), size=n), dtype=torch.float32)
-            return imitation.reset_states(t.to(imitation.engine.device), **record_flags)
+            t = torch.as_tensor(rng.uniform(t_lo, t_hi, size=n), dtype=torch.float32)
+            dev = imitation.engine.device
+            if reset_args and gen[0] is None:      # the noise stream is seeded from the env's own generator
+                gen[0] = torch.Generator(device=dev)
+                gen[0].manual_seed(int(rng.integers(0, 2 ** 31 - 1)) if hasattr(rng, "integers")
+                                   else int(rng.randint(0, 2 ** 31 - 1)))
+            return imitation.reset_states(t.to(dev), reset_args=reset_args, generator=gen[0], **record_flags)
         return fn
 
     def _draw_initial(self, n):

@@ -529,3 +529,97 @@ def imitation_reward_batch(ch, clip, pose, vel, kin_time, kin_origin=None):
         rew[e], terms[e] = calc_reward_imitate(ch, np.asarray(pose[e], dtype=np.float64),
                                                np.asarray(vel[e], dtype=np.float64), p1, v1, org[1], True)
     return rew, terms
+
+
+# ---- reset noise (anim/KinCharacter.cpp:340-532) ---------------------------------------------------------
+
+def euler_to_quat(euler):
+    """cMathUtil::EulerToQuaternion (MathUtil.cpp:423-429) over EulerToAxisAngle (:347-378) and
+    AxisAngleToQuaternion (:455-466)."""
+    x, y, z = float(euler[0]), float(euler[1]), float(euler[2])
+    xs, xc, ys, yc, zs, zc = np.sin(x), np.cos(x), np.sin(y), np.cos(y), np.sin(z), np.cos(z)
+    c = (yc * zc + xs * ys * zs + xc * zc + xc * yc - 1) * 0.5
+    c = min(max(c, -1.0), 1.0)
+    theta = np.arccos(c)
+    if abs(theta) < 0.00001:
+        axis = np.array([0.0, 0.0, 1.0])
+    else:
+        m21 = xs * yc - xc * ys * zs + xs * zc
+        m02 = xc * ys * zc + xs * zs + ys
+        m10 = yc * zs - xs * ys * zc + xc * zs
+        axis = np.array([m21, m02, m10]) / np.sqrt(m21 * m21 + m02 * m02 + m10 * m10)
+    h = theta / 2
+    return np.array([np.cos(h), np.sin(h) * axis[0], np.sin(h) * axis[1], np.sin(h) * axis[2]])
+
+
+def reset_noise(ch, pose, vel, u_pose, u_vel, r, noise_bef_rot=False, noise_min=0.0, noise_max=0.0, radian=0.0,
+                rot_vel_w_pose=False, vel_noise=False, interp=1.0, knee_rot=False):
+    """cKinCharacter::AddNoise (KinCharacter.cpp:340-352) = AddNoisePoseVel (:354-366) and RandomRotatePoseVel
+    (:367-532, root through cCharacter::RotateRoot, Character.cpp:210-216) in the order `noise_bef_rot` selects, for ONE
+    character.  The reference's random draws are inputs: u_pose / u_vel [dof] in [0, 1) become U(noise_min, noise_max);
+    r in [-1, 1) times `radian` are RandomRotatePoseVel's draws in the order it makes them (root yaw; 1 per noisy
+    revolute joint, 3 per noisy spherical joint; with vel_noise 3 for the root's angular velocity, then again per
+    joint).  The joint-index rules are the reference's, quirks included: knees (4, 10) only with knee_rot, hips and
+    ankles (3, 5, 9, 11) never, and the revolute branch of the velocity noise tests `!(j == 4 || j != 10)` (:506), which
+    is true for joint 10 alone.  Returns (pose, vel, number of r values consumed)."""
+    offs, sizes = param_layout(ch)
+    pose = np.array(pose, dtype=np.float64)
+    vel = np.array(vel, dtype=np.float64)
+    used = [0]
+
+    def add_noise_pose_vel():
+        if noise_min == 0 and noise_max == 0:
+            return
+        pose[:] = pose + (noise_min + (noise_max - noise_min) * np.asarray(u_pose, dtype=np.float64))
+        vel[:] = vel + (noise_min + (noise_max - noise_min) * np.asarray(u_vel, dtype=np.float64))
+
+    def draw():
+        v = radian * float(r[used[0]])
+        used[0] += 1
+        return v
+
+    def random_rotate():
+        if radian == 0:
+            return
+        yaw = draw()
+        rot = np.array([np.cos(yaw / 2), 0.0, np.sin(yaw / 2), 0.0])
+        q = quat_mul(rot, pose[3:7])
+        pose[3:7] = q / np.linalg.norm(q)
+        vel[:] = interp * vel            # root velocity, root angular velocity and every joint's segment (:398-417)
+        for j in range(1, len(sizes)):
+            o, t = offs[j], ch["joint_type"][j]
+            if t == REVOLUTE:
+                if not (j == 4 or j == 10) or knee_rot:
+                    pose[o] = pose[o] + draw()
+            elif t == SPHERICAL:
+                if j not in (3, 5, 9, 11):
+                    rr = euler_to_quat([draw(), draw(), draw()])
+                    pose[o:o + 4] = quat_mul(rr, pose[o:o + 4])
+                    if rot_vel_w_pose:
+                        vel[o:o + 4] = quat_mul(rr, vel[o:o + 4])
+        if vel_noise:
+            rr = euler_to_quat([draw(), draw(), draw()])
+            vel[3:7] = quat_mul(rr, vel[3:7])
+            for j in range(1, len(sizes)):
+                o, t = offs[j], ch["joint_type"][j]
+                if t == REVOLUTE:
+                    if (not (j == 4 or j != 10)) or knee_rot:
+                        vel[o] = vel[o] + draw()
+                elif t == SPHERICAL:
+                    if j not in (3, 5, 9, 11):
+                        rr = euler_to_quat([draw(), draw(), draw()])
+                        vel[o:o + 4] = quat_mul(rr, vel[o:o + 4])
+        # cKinTree::PostProcessPose (KinTree.cpp:1558-1575)
+        pose[3:7] = pose[3:7] / np.linalg.norm(pose[3:7])
+        for j in range(1, len(sizes)):
+            if ch["joint_type"][j] == SPHERICAL:
+                o = offs[j]
+                pose[o:o + 4] = pose[o:o + 4] / np.linalg.norm(pose[o:o + 4])
+
+    if noise_bef_rot:
+        add_noise_pose_vel()
+        random_rotate()
+    else:
+        random_rotate()
+        add_noise_pose_vel()
+    return pose, vel, used[0]

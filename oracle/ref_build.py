@@ -116,6 +116,8 @@ def load():
     lib.dmref_reward.argtypes, lib.dmref_reward.restype = [pd, pd, pd, pd, d, pd], d
     lib.dmref_record_state.argtypes, lib.dmref_record_state.restype = [pd, pd, i, i, i, d, pd], None
     lib.dmref_reward_batch.argtypes, lib.dmref_reward_batch.restype = [i, pd, pd, pd, pd, pd, pd], None
+    lib.dmref_reset_noise.argtypes = [pd, pd, i, d, d, d, i, i, d, i, pd, pd, pd, pd, pd]
+    lib.dmref_reset_noise.restype = i
     # cMotion::Load reports on stdout (Motion.cpp); keep the caller's stdout clean (bench lines are parsed as JSON)
     sys.stdout.flush()
     saved = os.dup(1)

@@ -20,6 +20,8 @@
 //   * cCtController::BuildStatePose / BuildStateVel (sim/CtController.cpp:378-495): the loop that lays out the env
 //     state; body positions / rotations / velocities, which the reference reads from Bullet bodies, come from the
 //     reference's kinematic equivalents cKinTree::{BodyWorldTrans, CalcBodyPartVel, CalcJointWorldAngularVel}
+//   * cKinCharacter::AddNoise / AddNoisePoseVel / RandomRotatePoseVel (anim/KinCharacter.cpp:340-532): the reset noise,
+//     with the reference's random draws turned into inputs (dmref_reset_noise)
 // Used by tests/test_imitation_ref.py and tests/golden/make_imitation_ref_golden.py; never by the product.
 #include <cstring>
 #include <fstream>
@@ -378,6 +380,121 @@ void dmref_record_state(const double* pose_in, const double* vel_in, int record_
     }
     FromVec(out_pose, out);
     FromVec(out_vel, out + out_pose.size());
+}
+
+// cKinCharacter::AddNoise over AddNoisePoseVel and RandomRotatePoseVel (anim/KinCharacter.cpp:340-532) with
+// cCharacter::RotateRoot (anim/Character.cpp:210-216): KinCharacter.cpp itself needs the OpenGL headers (Character.h
+// includes render/DrawMesh.h) and cannot be compiled here, so the loop is restated around the reference's own
+// cMathUtil::{AxisAngleToQuaternion, EulerToQuaternion, VecToQuat, QuatToVec} and cKinTree::{Get/SetRootRot,
+// Get/SetRootVel, Get/SetRootAngVel, GetParamOffset/Size, GetJointType, PostProcessPose}.  The reference draws from its
+// global generator (cMathUtil::RandDouble); here every draw is an INPUT, consumed in the reference's order:
+//   u_pose[dof], u_vel[dof] in [0, 1)  - AddNoisePoseVel, scaled to [noise_min, noise_max)
+//   r[...] in [-1, 1)                  - RandomRotatePoseVel, scaled by `radian`: root yaw, then per joint 1 (revolute) or
+//                                        3 (spherical) values for the pose, then (vel_noise) 3 for the root's angular
+//                                        velocity and again 1 / 3 per joint; joints that get no noise consume none.
+// Returns the number of r values consumed.
+int dmref_reset_noise(const double* pose_in, const double* vel_in, int noise_bef_rot, double noise_min, double noise_max,
+                      double radian, int rot_vel_w_pose, int vel_noise, double interp, int knee_rot,
+                      const double* u_pose, const double* u_vel, const double* r, double* pose_out, double* vel_out) {
+    Eigen::VectorXd mPose = ToVec(pose_in, g.dof), mVel = ToVec(vel_in, g.dof);
+    auto add_noise_pose_vel = [&]() {
+        if (noise_min == 0 && noise_max == 0) return;
+        for (int i = 0; i < g.dof; ++i) mPose[i] += noise_min + (noise_max - noise_min) * u_pose[i];
+        for (int i = 0; i < g.dof; ++i) mVel[i] += noise_min + (noise_max - noise_min) * u_vel[i];
+    };
+    int used = 0;
+    auto random_rotate = [&]() {
+        if (radian == 0) return;
+        double range = radian;
+        auto draw = [&]() { return range * r[used++]; };
+        tQuaternion root_rotate = cMathUtil::AxisAngleToQuaternion(tVector(0, 1, 0, 0), draw());
+        tQuaternion root_rot = cKinTree::GetRootRot(mPose);
+        root_rot = root_rotate * root_rot;
+        root_rot.normalize();
+        cKinTree::SetRootRot(root_rot, mPose);
+
+        tVector vel = cKinTree::GetRootVel(mVel);
+        vel = interp * vel;
+        cKinTree::SetRootVel(vel, mVel);
+        tVector ang_vel = cKinTree::GetRootAngVel(mVel);
+        ang_vel = interp * ang_vel;
+        cKinTree::SetRootAngVel(ang_vel, mVel);
+        for (int j = 1; j < g.num_joints; ++j) {
+            int param_offset = cKinTree::GetParamOffset(g.joint_mat, j);
+            int param_size = cKinTree::GetParamSize(g.joint_mat, j);
+            tVector v = tVector::Zero();
+            v.segment(0, param_size) = mVel.segment(param_offset, param_size);
+            v = interp * v;
+            mVel.segment(param_offset, param_size) = v.segment(0, param_size);
+        }
+        for (int j = 1; j < g.num_joints; ++j) {
+            int param_offset = cKinTree::GetParamOffset(g.joint_mat, j);
+            int param_size = cKinTree::GetParamSize(g.joint_mat, j);
+            cKinTree::eJointType joint_type = cKinTree::GetJointType(g.joint_mat, j);
+            if (joint_type == cKinTree::eJointTypeRevolute) {
+                if (!(j == 4 || j == 10) || knee_rot) mPose(param_offset) = mPose(param_offset) + draw();
+            } else if (joint_type == cKinTree::eJointTypeSpherical) {
+                if (j != 3 && j != 5 && j != 9 && j != 11) {
+                    double rand_psi = draw();
+                    double rand_theta = draw();
+                    double rand_phi = draw();
+                    tQuaternion rand_rotate = cMathUtil::EulerToQuaternion(tVector(rand_psi, rand_theta, rand_phi, 0));
+                    tVector seg = tVector::Zero();
+                    seg.segment(0, param_size) = mPose.segment(param_offset, param_size);
+                    tQuaternion rot = cMathUtil::VecToQuat(seg);
+                    rot = rand_rotate * rot;
+                    mPose.segment(param_offset, param_size) = cMathUtil::QuatToVec(rot).segment(0, param_size);
+                    if (rot_vel_w_pose) {
+                        tVector vseg = tVector::Zero();
+                        vseg.segment(0, param_size) = mVel.segment(param_offset, param_size);
+                        tQuaternion vq = cMathUtil::VecToQuat(vseg);
+                        vq = rand_rotate * vq;
+                        mVel.segment(param_offset, param_size) = cMathUtil::QuatToVec(vq).segment(0, param_size);
+                    }
+                }
+            }
+        }
+        if (vel_noise) {
+            tQuaternion av = cMathUtil::VecToQuat(cKinTree::GetRootAngVel(mVel));
+            double rand_psi = draw();
+            double rand_theta = draw();
+            double rand_phi = draw();
+            tQuaternion rand_rotate = cMathUtil::EulerToQuaternion(tVector(rand_psi, rand_theta, rand_phi, 0));
+            av = rand_rotate * av;
+            cKinTree::SetRootAngVel(cMathUtil::QuatToVec(av), mVel);
+            for (int j = 1; j < g.num_joints; ++j) {
+                int param_offset = cKinTree::GetParamOffset(g.joint_mat, j);
+                int param_size = cKinTree::GetParamSize(g.joint_mat, j);
+                cKinTree::eJointType joint_type = cKinTree::GetJointType(g.joint_mat, j);
+                if (joint_type == cKinTree::eJointTypeRevolute) {
+                    if (!(j == 4 || j != 10) || knee_rot) mVel(param_offset) = mVel(param_offset) + draw();
+                } else if (joint_type == cKinTree::eJointTypeSpherical) {
+                    if (j != 3 && j != 5 && j != 9 && j != 11) {
+                        double p0 = draw();
+                        double p1 = draw();
+                        double p2 = draw();
+                        tQuaternion rr = cMathUtil::EulerToQuaternion(tVector(p0, p1, p2, 0));
+                        tVector vseg = tVector::Zero();
+                        vseg.segment(0, param_size) = mVel.segment(param_offset, param_size);
+                        tQuaternion vq = cMathUtil::VecToQuat(vseg);
+                        vq = rr * vq;
+                        mVel.segment(param_offset, param_size) = cMathUtil::QuatToVec(vq).segment(0, param_size);
+                    }
+                }
+            }
+        }
+        cKinTree::PostProcessPose(g.joint_mat, mPose);
+    };
+    if (noise_bef_rot) {
+        add_noise_pose_vel();
+        random_rotate();
+    } else {
+        random_rotate();
+        add_noise_pose_vel();
+    }
+    FromVec(mPose, pose_out);
+    FromVec(mVel, vel_out);
+    return used;
 }
 
 }  // extern "C"

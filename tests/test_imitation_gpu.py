@@ -191,6 +191,54 @@ def test_clip_reset_states_feed_the_env(setup):
     assert not mo.simenv_collided(ob.astype(np.float64)).any()          # the reference motion never falls
 
 
+def test_reset_noise_states_match_the_oracle(setup):
+    """reset_states(reset_args=...) = clip sample -> cKinCharacter::AddNoise (KinCharacter.cpp:340-532, batched on the
+    device in reset_noise.add_reset_noise) -> record_state, against the float64 oracle fed the same draws (the oracle
+    itself is pinned to the reference's compiled primitives in tests/test_imitation_ref.py); then the plugin's own call:
+    VecSimEnv.clip_reset_fn(reset_args=<the reference's dict>) gives finite, upright, perturbed states and honours
+    custom_time."""
+    from amp_extensions_b200 import AmpDataset, DynamicsEnsemble, VecSimEnv
+    from amp_extensions_b200 import reset_noise as rn
+    imit, clip = setup
+    rng = np.random.default_rng(11)
+    E, dof = 40, 43
+    ra = dict(custom_time=False, time_min=0, time_max=0, resolve=True, noise_bef_rot=True, noise_min=-0.01,
+              noise_max=0.02, radian=0.25, rot_vel_w_pose=True, vel_noise=True, interp=0.6, knee_rot=False)
+    kw = rn.reset_kwargs(ra)
+    n_r = rn.num_rotation_draws(imit.character, kw["vel_noise"], kw["knee_rot"])
+    t = np.linspace(0.0, float(clip.duration) * 0.999, E).astype(np.float32)
+    u_pose = rng.uniform(0, 1, (E, dof)).astype(np.float32)
+    u_vel = rng.uniform(0, 1, (E, dof)).astype(np.float32)
+    r = rng.uniform(-1, 1, (E, n_r)).astype(np.float32)
+    states = imit.reset_states(torch.from_numpy(t).cuda(), reset_args=ra, draws=(u_pose, u_vel, r)).cpu().numpy()
+    ref = []
+    for e in range(E):
+        p, v, used = io.reset_noise(io.HUMANOID3D, clip.kin_pose(float(t[e])), clip.kin_vel(float(t[e])),
+                                    u_pose[e].astype(np.float64), u_vel[e].astype(np.float64), r[e].astype(np.float64), **kw)
+        assert used == n_r
+        ref.append(io.record_state(io.HUMANOID3D, p, v))
+    ref = np.stack(ref)
+    np.testing.assert_allclose(states[:, :136], ref[:, :136], rtol=0, atol=3e-4)
+    np.testing.assert_allclose(states[:, 136:], ref[:, 136:], rtol=0, atol=2e-3 * max(1.0, np.abs(ref[:, 136:]).max()))
+    plain = imit.reset_states(torch.from_numpy(t).cuda()).cpu().numpy()
+    assert np.abs(states - plain).max() > 1e-2                        # the noise did something
+
+    s, a, s2 = H.synth_dataset(512, 226, 28, 0)
+    ens = DynamicsEnsemble(226, 28, AmpDataset(s, a, s2), None, num_models=2, hidden_sizes=[64, 64], dense_connect=True,
+                           transform=True, base_seed=100)
+    ra2 = dict(ra, custom_time=True, time_min=0.2, time_max=0.2, noise_min=0.0, noise_max=0.0, radian=0.05)
+    env = VecSimEnv(ens, 32, reset_fn=VecSimEnv.clip_reset_fn(imit, reset_args=ra2), seed=3)
+    ob = env.reset().cpu().numpy()
+    assert ob.shape == (32, 226) and np.isfinite(ob).all()
+    assert (ob[:, 0] > 0.6).all() and (ob[:, 0] < 1.3).all()
+    at = imit.reset_states(torch.full((1,), 0.2).cuda()).cpu().numpy()[0]
+    d = np.abs(ob[:, :136] - at[:136]).max()                           # all at t = 0.2 s, each perturbed a little (0.05 rad);
+    assert 1e-4 < d < 0.3                                               # the velocities are also scaled by interp = 0.6
+    assert np.abs(ob[0] - ob[1]).max() > 1e-4
+    ob2 = VecSimEnv(ens, 32, reset_fn=VecSimEnv.clip_reset_fn(imit, reset_args=ra2), seed=3).reset().cpu().numpy()
+    np.testing.assert_array_equal(ob, ob2)                             # seeded: reproducible
+
+
 # ---- against outputs of the reference's own compiled kinematics code (tests/golden/imitation_ref_golden.npz) ----
 
 def _ref_golden():

@@ -236,3 +236,66 @@ def test_a_different_skeleton_matches_the_reference():
     r, terms = io.imitation_reward_batch(dog, c, GOLD["dog/pose"][:n], GOLD["dog/vel"][:n], GOLD["dog/t"][:n])
     np.testing.assert_allclose(terms, GOLD["dog/terms"][:n], atol=ATOL)
     np.testing.assert_allclose(r, GOLD["dog/reward"][:n], atol=ATOL)
+
+
+# ---- reset noise (KinCharacter.cpp:340-532) ---------------------------------------------------------------
+
+RESET_CASES = [
+    dict(noise_bef_rot=False, noise_min=0.0, noise_max=0.0, radian=0.3, rot_vel_w_pose=False, vel_noise=False, interp=1.0, knee_rot=False),
+    dict(noise_bef_rot=True, noise_min=-0.05, noise_max=0.1, radian=0.5, rot_vel_w_pose=True, vel_noise=True, interp=0.4, knee_rot=True),
+    dict(noise_bef_rot=False, noise_min=-0.02, noise_max=0.02, radian=1.2, rot_vel_w_pose=False, vel_noise=True, interp=0.0, knee_rot=False),
+    dict(noise_bef_rot=True, noise_min=0.01, noise_max=0.03, radian=0.0, rot_vel_w_pose=True, vel_noise=True, interp=0.5, knee_rot=True),
+    dict(noise_bef_rot=False, noise_min=0.0, noise_max=0.0, radian=1e-7, rot_vel_w_pose=True, vel_noise=False, interp=1.0, knee_rot=True),
+]
+
+
+@pytest.mark.parametrize("case", range(len(RESET_CASES)))
+def test_reset_noise_matches_the_reference_primitives(lib, clip, case):
+    """oracle.reset_noise against dmref_reset_noise: cKinCharacter::AddNoise's loop restated in the driver around the
+    reference's own compiled cMathUtil / cKinTree calls (KinCharacter.cpp itself needs OpenGL headers), fed the same
+    draws: every flag combination incl. radian == 0 (no rotation, no interpolation), a vanishing rotation (the
+    |theta| < 1e-5 branch of EulerToAxisAngle), the knee rules and the `!(j == 4 || j != 10)` condition of the
+    velocity noise."""
+    kw = RESET_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    dof = 43
+    for trial in range(6):
+        t = float(rng.uniform(0, clip.duration))
+        pose, vel = clip.kin_pose(t), clip.kin_vel(t)
+        u_pose, u_vel = rng.uniform(0, 1, dof), rng.uniform(0, 1, dof)
+        r = rng.uniform(-1, 1, 64)
+        want_p, want_v = np.zeros(dof), np.zeros(dof)
+        used = lib.dmref_reset_noise(P(np.ascontiguousarray(pose)), P(np.ascontiguousarray(vel)), int(kw["noise_bef_rot"]),
+                                     kw["noise_min"], kw["noise_max"], kw["radian"], int(kw["rot_vel_w_pose"]),
+                                     int(kw["vel_noise"]), kw["interp"], int(kw["knee_rot"]), P(u_pose), P(u_vel), P(r),
+                                     P(want_p), P(want_v))
+        got_p, got_v, got_used = io.reset_noise(CH, pose, vel, u_pose, u_vel, r, **kw)
+        assert got_used == used
+        np.testing.assert_allclose(got_p, want_p, atol=ATOL)
+        np.testing.assert_allclose(got_v, want_v, atol=ATOL)
+        if kw["radian"] == 0 and kw["noise_min"] == 0 and kw["noise_max"] == 0:
+            np.testing.assert_array_equal(got_p, pose)
+
+
+def test_reset_noise_product_matches_the_oracle_on_cpu():
+    """The batched torch implementation the product uses (amp_extensions_b200/reset_noise.py; plain tensor ops, so it
+    also runs on the CPU) against the float64 restatement with the same draws, all flag sets, float64 tensors."""
+    import torch
+    from amp_extensions_b200 import reset_noise as rn
+    from amp_extensions_b200.character import humanoid3d
+    ch = humanoid3d()
+    c = io.Clip(H.spinkick_raw(), CH, "wrap")
+    rng = np.random.default_rng(7)
+    E, dof = 9, 43
+    for kw in RESET_CASES:
+        n_r = rn.num_rotation_draws(ch, kw["vel_noise"], kw["knee_rot"])
+        ts = rng.uniform(0, c.duration, E)
+        pose = np.stack([c.kin_pose(float(t)) for t in ts])
+        vel = np.stack([c.kin_vel(float(t)) for t in ts])
+        u_pose, u_vel, r = rng.uniform(0, 1, (E, dof)), rng.uniform(0, 1, (E, dof)), rng.uniform(-1, 1, (E, n_r))
+        got_p, got_v = rn.add_reset_noise(ch, torch.from_numpy(pose), torch.from_numpy(vel), draws=(u_pose, u_vel, r), **kw)
+        for e in range(E):
+            want_p, want_v, used = io.reset_noise(CH, pose[e], vel[e], u_pose[e], u_vel[e], r[e], **kw)
+            assert used == (n_r if kw["radian"] != 0 else 0)
+            np.testing.assert_allclose(got_p[e].numpy(), want_p, atol=1e-12)
+            np.testing.assert_allclose(got_v[e].numpy(), want_v, atol=1e-12)
