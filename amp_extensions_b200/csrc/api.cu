@@ -571,7 +571,11 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
   // the last, partial round: when its units are at most half the pairs, two pairs share each of them
   const int units = ca.m_tiles * ca.groups;
   const int pairs = std::min(units, h->sm_count / 2);
-  const int tail = units % pairs;
+  // whole rounds run with the members of an env tile in sequence on one pair: all pairs then stream the SAME member's
+  // weights at any time (measured -1.5 % on the launch against members side by side; SIMSTEP_CHAIN_SEQ=0 for A/B)
+  static const bool seq = [] { const char* e = std::getenv("SIMSTEP_CHAIN_SEQ"); return !(e && e[0] == '0'); }();
+  if (seq && units > pairs) ca.seq_rounds = ca.m_tiles / pairs;
+  const int tail = (units - ca.seq_rounds * pairs * ca.groups) % pairs;
   if (chain_mode() != 3 && tail > 0 && 2 * tail <= pairs && ca.hidden_tiles <= kChainMaxDepTiles && h->chain_cnt) {
     ca.tail_units = tail;
     ca.tail_cnt = h->chain_cnt;

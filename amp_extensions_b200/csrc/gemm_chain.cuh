@@ -73,6 +73,7 @@ struct ChainArgs {
   const float* shift;
   // the last, partial round: units [units - tail_units, units) are shared by two pairs each (0: plain extra round)
   int tail_units;
+  int seq_rounds;          // whole rounds run with the members of an env tile in sequence on one pair (0: none)
   int tiles_per_role[2];                      // hidden tiles role p stores per shared unit
   unsigned char dep_role[kChainMaxDepTiles];  // column tile T of the activation buffer: the role that stores it ...
   unsigned char dep_ord[kChainMaxDepTiles];   // ... and its ordinal among that role's tiles of the unit
@@ -146,13 +147,23 @@ struct ChainItem {
   int role;
 };
 __device__ __forceinline__ bool chain_item(const ChainArgs& a, int pair, int pairs, int i, ChainItem& it) {
+  // seq_rounds whole rounds in which a pair takes ALL members of an env tile one after the other (the members of an env
+  // tile then meet inside one CTA pair) ...
+  const int seq_items = a.seq_rounds * a.groups;
+  if (i < seq_items) {
+    it.unit = (pair + (i / a.groups) * pairs) * a.groups + i % a.groups;
+    it.role = -1;
+    return true;
+  }
+  // ... then the remaining units round-robin, the last partial round shared between pairs
   const int units = a.m_tiles * a.groups;
+  const int base = a.seq_rounds * pairs * a.groups;
   const int full_units = units - a.tail_units;
-  const int u = pair + i * pairs;
+  const int j = i - seq_items;
+  const int u = base + pair + j * pairs;
   if (u < full_units) { it.unit = u; it.role = -1; return true; }
-  // the shared units come after the pair's last whole unit
-  const int n_full = full_units > pair ? (full_units - pair + pairs - 1) / pairs : 0;
-  if (i == n_full && pair < 2 * a.tail_units) { it.unit = full_units + (pair >> 1); it.role = pair & 1; return true; }
+  const int n_full = full_units > base + pair ? (full_units - base - pair + pairs - 1) / pairs : 0;
+  if (j == n_full && pair < 2 * a.tail_units) { it.unit = full_units + (pair >> 1); it.role = pair & 1; return true; }
   return false;
 }
 
