@@ -79,6 +79,7 @@ struct simstep_handle {
   // the GPU boxes: this is the out-of-bounds check the test suite runs instead)
   bool guards_on = false;
   std::vector<std::pair<void*, size_t>> guard_allocs;  // (user pointer, user bytes)
+  long long tail_rows_done = 0;       // rows [0, tail_rows_done) of the chunk had their step tail run inside the chain kernel
   bool forward_was_chain = false;     // the workspace's deltas were written by the chain kernel (in row order)
   unsigned int* chain_cnt = nullptr;  // chain kernel: tile counters of the shared units of the last round (zero between launches)
   CUtensorMap tmap_x, tmap_h, tmap_dws;
@@ -520,6 +521,18 @@ int chain_mode() {
 // pair - fits 90 % of the L2 (108 of 126 MB at 4 x (512 x 4); measured 10 % faster than one launch per layer); an
 // 8 x (1024 x 4) ensemble (136 MB of weights, 2.2 MB of activations per unit) thrashes it and was measured 14 % SLOWER,
 // so such shapes keep one launch per layer.
+// SIMSTEP_CHAIN_TAIL=1: the env step's tail (next state, discrepancy, termination, cost operand rows) runs INSIDE the
+// chain kernel, on four extra warps per CTA, for the env tiles of its whole rounds but the last
+// (SIMSTEP_CHAIN_TAIL_KEEP=<rounds left to the post-step kernel>, default 1).  Correct - next states, counters and masks
+// bit-identical to the post-step kernel, the discrepancy within 2e-6 - and NOT the default: the chain kernel is bound by
+// the L2->SM path its operands already saturate, so the tail's bytes cost there what they cost the post-step kernel
+// outside (first round fused: launch +16 us, post-step kernel -18 us; all rounds: the last tiles' tails run after the
+// MMAs have finished, +62 us against -36 us).
+bool chain_tail_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SIMSTEP_CHAIN_TAIL"); return e && e[0] == '1'; }();
+  return on;
+}
+
 bool chain_ok(const simstep_handle* h, long long rows_pad) {
   if (chain_mode() == 0 || h->cg != 2 || h->L < 1 || h->L + 1 > kChainMaxLayers || !h->have_ensemble) return false;
   static int l2_bytes[kMaxDevices] = {};
@@ -533,7 +546,21 @@ bool chain_ok(const simstep_handle* h, long long rows_pad) {
   return weights + pairs * unit_bytes <= 0.9 * double(l2);
 }
 
-int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
+// The cost operand rows the step's tail also writes for input_type 'ss' (post kernels and the chain kernel's tail warps)
+PostRff make_post_rff(const simstep_handle* h, bool fuse_rff) {
+  PostRff rff{};
+  if (fuse_rff) {
+    rff.out = h->rffin;
+    rff.prec = h->cfg.precision;
+    rff.RK = h->RK;
+    rff.split = h->rff_split;
+    rff.col2 = h->rff_col2;
+    rff.pitch = h->rff_split_cap ? 2 * h->RK : h->RK;
+  }
+  return rff;
+}
+
+int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st, const StepTail* step_tail, long long n) {
   ChainLaunch cl;
   cl.maps.x = h->tmap_x;
   cl.maps.h = h->tmap_h;
@@ -586,6 +613,31 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st) {
         ca.dep_ord[t] = static_cast<unsigned char>(ca.tiles_per_role[n & 1]++);
       }
   }
+  // The env step's tail inside this launch (gemm_chain.cuh, tail warps) for the env tiles of the whole rounds; the
+  // post-step kernel then only gets the rows of the remaining units.
+  static const int tail_keep = [] { const char* e = std::getenv("SIMSTEP_CHAIN_TAIL_KEEP"); return e ? std::atoi(e) : 1; }();
+  const int tail_rounds = ca.seq_rounds - tail_keep;   // the last round's rows stay with the post-step kernel
+  if (step_tail != nullptr && chain_tail_enabled() && tail_rounds > 0 && h->N == 4 && h->S % 2 == 0 &&
+      h->S <= kPostMaxElems && reinterpret_cast<uintptr_t>(step_tail->state) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(step_tail->next_state) % 8 == 0 && (step_tail->next_state == nullptr || step_tail->state != nullptr)) {
+    ChainTail& t = ca.tail;
+    t.enabled = 1;
+    t.rounds = tail_rounds;
+    t.delta = h->dws;
+    t.delta_rows = h->cap_rows;
+    t.DP = h->DP;
+    t.state = step_tail->state;
+    t.next_state = step_tail->next_state;
+    t.member = step_tail->member;
+    t.num_steps = step_tail->num_steps;
+    t.disc = step_tail->disc;
+    t.done = step_tail->done;
+    t.n_rows = n;
+    t.S = h->S;
+    t.tc = h->term;
+    t.rff = make_post_rff(h, step_tail->rff);
+    h->tail_rows_done = std::min<long long>(n, static_cast<long long>(tail_rounds) * pairs * kBlockM * 2);
+  }
   CU_TRY(h, launch_ensemble_chain(h->cfg.precision, h->cfg.activation != SIMSTEP_ACT_RELU, cl, h->sm_count, h->device, st));
   g_launches++;
   return SIMSTEP_OK;
@@ -613,9 +665,10 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
   CU_TRY(h, cudaGetLastError());
   ProfScope ps(h, SIMSTEP_PROF_ENSEMBLE_GEMM, st);
   h->forward_was_chain = false;
+  h->tail_rows_done = 0;
   if (last_layer == h->L && chain_ok(h, rows_pad) && !(tail != nullptr && final_fused_ok(h, *tail))) {
     h->forward_was_chain = true;
-    return launch_chain(h, rows_pad, st);
+    return launch_chain(h, rows_pad, st, tail, n);
   }
   for (int l = 0; l <= last_layer; ++l) {
     const Layer& ly = h->layers[l];
@@ -667,6 +720,20 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
 int launch_post(simstep_handle* h, const float* state, const int32_t* member, int32_t* num_steps, long long n,
                 float* next_state, float* disc, uint8_t* done, cudaStream_t st, bool fuse_rff = false) {
   if (h->S > kPostMaxElems) return fail(h, SIMSTEP_EINVAL, "state_dim > 256 is not supported by the post kernel");
+  // rows whose tail already ran inside the chain kernel (launch_chain) are skipped: everything below is offset by row0
+  const long long row0 = h->tail_rows_done;
+  h->tail_rows_done = 0;
+  if (row0 >= n) return SIMSTEP_OK;
+  if (row0 > 0) {
+    n -= row0;
+    if (state) state += row0 * h->S;
+    if (member) member += row0;
+    if (num_steps) num_steps += row0;
+    if (next_state) next_state += row0 * h->S;
+    if (disc) disc += row0;
+    if (done) done += row0;
+  }
+  const float* dws_base = h->dws + row0 * h->DP;
   ProfScope ps(h, SIMSTEP_PROF_POST, st);
   // one warp per row and one row per warp: the block scheduler balances the tail, no grid-stride quantisation
   const int blocks = int(std::min<long long>((n + kPostWarps - 1) / kPostWarps, 1LL << 30));
@@ -674,16 +741,9 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
   // float2 lanes need 8-byte aligned rows: even S and 8-byte aligned base pointers
   const bool vec2 = (h->S % 2 == 0) && (reinterpret_cast<uintptr_t>(state) % 8 == 0) &&
                     (reinterpret_cast<uintptr_t>(next_state) % 8 == 0);
-  PostRff rff{};
-  if (fuse_rff) {
-    if (!vec2) return fail(h, SIMSTEP_EINVAL, "internal: fused RFF operand needs the float2 path");
-    rff.out = h->rffin;
-    rff.prec = h->cfg.precision;
-    rff.RK = h->RK;
-    rff.split = h->rff_split;
-    rff.col2 = h->rff_col2;
-    rff.pitch = h->rff_split_cap ? 2 * h->RK : h->RK;
-  }
+  if (fuse_rff && !vec2) return fail(h, SIMSTEP_EINVAL, "internal: fused RFF operand needs the float2 path");
+  PostRff rff = make_post_rff(h, fuse_rff);
+  if (rff.out != nullptr) rff.out = static_cast<char*>(rff.out) + size_t(row0) * rff.pitch * h->esize;
   // TMA-staged persistent kernel (post_tma.cuh) whenever rows pair up into 16-byte granular spans
   const PostTmaPlan plan = post_tma_plan(h->S, h->DP, h->N);
   static const bool tma_off = [] { const char* e = std::getenv("SIMSTEP_POST_TMA"); return e && e[0] == '0'; }();
@@ -704,7 +764,7 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
     }                                                                                                          \
     const long long pairs = (n + 1) / 2;                                                                       \
     const int grid = int(std::min<long long>((pairs + plan.rings - 1) / plan.rings, h->sm_count));             \
-    launch_pdl(kern, dim3(grid), dim3(plan.rings * 64), plan.smem, st, h->dws, h->cap_rows, h->DP, state, member, \
+    launch_pdl(kern, dim3(grid), dim3(plan.rings * 64), plan.smem, st, dws_base, h->cap_rows, h->DP, state, member, \
                num_steps, h->S, n, next_state, disc, done, h->term, rff, plan.stages, post_reverse);           \
   } while (0)
 #define POST_CASE(NM)                                                                                          \
@@ -714,10 +774,10 @@ int launch_post(simstep_handle* h, const float* state, const int32_t* member, in
       else if (h->cfg.precision == SIMSTEP_PREC_TF32) POST_TMA_LAUNCH(NM, ElemTF32);                           \
       else POST_TMA_LAUNCH(NM, ElemBF16);                                                                      \
     } else if (vec2)                                                                                           \
-      launch_pdl(post_step_kernel<NM, 2>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->DP, \
+      launch_pdl(post_step_kernel<NM, 2>, dim3(blocks), dim3(kPostWarps * 32), smem, st, dws_base, h->cap_rows, h->DP, \
                  state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     else                                                                                                       \
-      launch_pdl(post_step_kernel<NM, 1>, dim3(blocks), dim3(kPostWarps * 32), smem, st, h->dws, h->cap_rows, h->DP, \
+      launch_pdl(post_step_kernel<NM, 1>, dim3(blocks), dim3(kPostWarps * 32), smem, st, dws_base, h->cap_rows, h->DP, \
                  state, member, num_steps, h->S, n, next_state, disc, done, h->term, rff);                      \
     break;
   switch (h->N) {

@@ -269,143 +269,154 @@ __device__ __forceinline__ void post_rff_store(const PostRff& r, long long row, 
 //   delta  [NM][delta_rows][SP] fp32 workspace of the final GEMM, row = chunk-local
 //   state  [E][S], next_state [E][S] (may alias state)
 // VEC = 2 when S is even: every row then starts 8-byte aligned and lanes move float2.
+// One env row, one warp: the body of post_step_kernel, also run by the tail warps of the column-fused forward kernel
+// (gemm_chain.cuh) on rows whose member deltas that same kernel has just stored - CG_LOADS reads them with ld.global.cg
+// (L2, never a stale L1 line).  srow: this warp's shared-memory row of (S + 3) & ~3 floats.
+template <int NM, int VEC, bool CG_LOADS>
+__device__ __forceinline__ void post_row_warp(const float* __restrict__ delta, long long delta_rows, int SP,
+                                              const float* state, const int32_t* __restrict__ member,
+                                              int32_t* num_steps, int S, long long row, float* next_state,
+                                              float* __restrict__ disc, uint8_t* __restrict__ done,
+                                              const TermConst& tc, const PostRff& rff, float* srow, int lane) {
+  using V = typename PostVec<VEC>::type;
+  constexpr int kPerLane = kPostMaxElems / (32 * VEC);
+  constexpr int NP = NM * (NM - 1) / 2;
+  const int nvec = S / VEC;
+  V d[NM][kPerLane];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const V* drow = reinterpret_cast<const V*>(delta + (static_cast<long long>(m) * delta_rows + row) * SP);
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int j = lane + 32 * i;
+      d[m][i] = (j < nvec) ? (CG_LOADS ? __ldcg(drow + j) : __ldg(drow + j)) : PostVec<VEC>::zero();
+    }
+  }
+  V sv[kPerLane];
+  if (next_state != nullptr) {
+    const V* srow_g = reinterpret_cast<const V*>(state + row * S);
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int j = lane + 32 * i;
+      sv[i] = (j < nvec) ? srow_g[j] : PostVec<VEC>::zero();
+    }
+  }
+
+  if (disc != nullptr) {
+    float acc[NP > 0 ? NP : 1];
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < NM; ++a) {
+#pragma unroll
+      for (int b = a + 1; b < NM; ++b) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) s2 = PostVec<VEC>::sub_sq(d[a][i], d[b][i], s2);
+        acc[p++] = s2;
+      }
+    }
+    float best = 0.f;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      float s2 = acc[k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+      // NaN must propagate like torch.max does
+      if (s2 != s2) best = s2;
+      else if (best == best && s2 > best) best = s2;
+    }
+    if (lane == 0) disc[row] = sqrtf(best);
+  }
+
+  if (next_state != nullptr) {
+    const int mem = member ? member[row] : 0;
+    V nxt[kPerLane];
+    V* nrow_g = reinterpret_cast<V*>(next_state + row * S);
+    V* srow_v = reinterpret_cast<V*>(srow);
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int j = lane + 32 * i;
+      V dm = PostVec<VEC>::nan();  // a member index outside [0, N) (the reference raises IndexError): NaN next state
+#pragma unroll
+      for (int m = 0; m < NM; ++m) dm = (m == mem) ? d[m][i] : dm;
+      nxt[i] = PostVec<VEC>::add(sv[i], dm);
+      if (j < nvec) {
+        nrow_g[j] = nxt[i];
+        srow_v[j] = nxt[i];
+      }
+    }
+    if constexpr (VEC == 2) {
+      if (rff.out != nullptr) {  // cost features' operand rows for input_type 'ss' (linear_cost.py:119)
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+          const int j = lane + 32 * i;
+          if (j < nvec) {
+            if (rff.prec == SIMSTEP_PREC_FP16) {
+              post_rff_store<ElemF16>(rff, row, 2 * j, sv[i]);
+              post_rff_store<ElemF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
+            } else if (rff.prec == SIMSTEP_PREC_TF32) {
+              post_rff_store<ElemTF32>(rff, row, 2 * j, sv[i]);
+              post_rff_store<ElemTF32>(rff, row, rff.col2 + 2 * j, nxt[i]);
+            } else {
+              post_rff_store<ElemBF16>(rff, row, 2 * j, sv[i]);
+              post_rff_store<ElemBF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
+            }
+          }
+        }
+      }
+    }
+    int steps = 0;
+    if (num_steps != nullptr) {
+      steps = num_steps[row] + 1;
+      if (lane == 0) num_steps[row] = steps;
+    }
+    if (done != nullptr) {
+      __syncwarp();
+      bool flag = false;
+      if (lane < tc.n_bodies) {
+        const int off = tc.body_offset[lane];
+        const int shape = tc.body_shape[lane];
+        float y = srow[off + 1];
+        if (!(tc.record_all_world || (lane == 0 && tc.record_world_root_pos))) y += srow[0];
+        const float lim = tc.body_radius[lane] + 0.0001f;
+        if (shape == SIMSTEP_SHAPE_SPHERE) {
+          flag = y <= lim;
+        } else if (shape == SIMSTEP_SHAPE_CAPSULE) {
+          const float cap = tc.body_half_height[lane] * srow[off + tc.pos_dim + 1];
+          flag = (y + cap <= lim) || (y - cap <= lim);
+        }
+      }
+      if (tc.enable_velocity_check) {
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+          const int j = (lane + 32 * i) * VEC;  // first element of this lane's slot
+          if (j < S) flag = flag || PostVec<VEC>::vel_over(nxt[i], j, tc.vel_offset, tc.vel_inv_divisor, tc.vel_threshold);
+        }
+      }
+      const bool any = __any_sync(0xffffffffu, flag);
+      if (lane == 0) done[row] = (any || (num_steps != nullptr && steps >= tc.horizon)) ? 1 : 0;
+      __syncwarp();
+    }
+  }
+}
+
 template <int NM, int VEC>
 __global__ void __launch_bounds__(kPostWarps * 32, NM <= 4 ? 3 : 2)
 post_step_kernel(const float* __restrict__ delta, long long delta_rows, int SP, const float* state,
                  const int32_t* __restrict__ member, int32_t* num_steps, int S, long long n_rows,
                  float* next_state, float* __restrict__ disc, uint8_t* __restrict__ done, const TermConst tc,
                  const PostRff rff) {
-  using V = typename PostVec<VEC>::type;
-  constexpr int kPerLane = kPostMaxElems / (32 * VEC);
   extern __shared__ float sm_rows[];  // [kPostWarps][S]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   float* srow = sm_rows + size_t(wib) * ((S + 3) & ~3);
   const long long warp_global = blockIdx.x * static_cast<long long>(kPostWarps) + wib;
   const long long n_warps = static_cast<long long>(gridDim.x) * kPostWarps;
-  constexpr int NP = NM * (NM - 1) / 2;
-  const int nvec = S / VEC;
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();
-
-  for (long long row = warp_global; row < n_rows; row += n_warps) {
-    V d[NM][kPerLane];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      const V* drow = reinterpret_cast<const V*>(delta + (static_cast<long long>(m) * delta_rows + row) * SP);
-#pragma unroll
-      for (int i = 0; i < kPerLane; ++i) {
-        const int j = lane + 32 * i;
-        d[m][i] = (j < nvec) ? __ldg(drow + j) : PostVec<VEC>::zero();
-      }
-    }
-    V sv[kPerLane];
-    if (next_state != nullptr) {
-      const V* srow_g = reinterpret_cast<const V*>(state + row * S);
-#pragma unroll
-      for (int i = 0; i < kPerLane; ++i) {
-        const int j = lane + 32 * i;
-        sv[i] = (j < nvec) ? srow_g[j] : PostVec<VEC>::zero();
-      }
-    }
-
-    if (disc != nullptr) {
-      float acc[NP > 0 ? NP : 1];
-      int p = 0;
-#pragma unroll
-      for (int a = 0; a < NM; ++a) {
-#pragma unroll
-        for (int b = a + 1; b < NM; ++b) {
-          float s2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < kPerLane; ++i) s2 = PostVec<VEC>::sub_sq(d[a][i], d[b][i], s2);
-          acc[p++] = s2;
-        }
-      }
-      float best = 0.f;
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        float s2 = acc[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-        // NaN must propagate like torch.max does
-        if (s2 != s2) best = s2;
-        else if (best == best && s2 > best) best = s2;
-      }
-      if (lane == 0) disc[row] = sqrtf(best);
-    }
-
-    if (next_state != nullptr) {
-      const int mem = member ? member[row] : 0;
-      V nxt[kPerLane];
-      V* nrow_g = reinterpret_cast<V*>(next_state + row * S);
-      V* srow_v = reinterpret_cast<V*>(srow);
-#pragma unroll
-      for (int i = 0; i < kPerLane; ++i) {
-        const int j = lane + 32 * i;
-        V dm = PostVec<VEC>::nan();  // a member index outside [0, N) (the reference raises IndexError): NaN next state
-#pragma unroll
-        for (int m = 0; m < NM; ++m) dm = (m == mem) ? d[m][i] : dm;
-        nxt[i] = PostVec<VEC>::add(sv[i], dm);
-        if (j < nvec) {
-          nrow_g[j] = nxt[i];
-          srow_v[j] = nxt[i];
-        }
-      }
-      if constexpr (VEC == 2) {
-        if (rff.out != nullptr) {  // cost features' operand rows for input_type 'ss' (linear_cost.py:119)
-#pragma unroll
-          for (int i = 0; i < kPerLane; ++i) {
-            const int j = lane + 32 * i;
-            if (j < nvec) {
-              if (rff.prec == SIMSTEP_PREC_FP16) {
-                post_rff_store<ElemF16>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
-              } else if (rff.prec == SIMSTEP_PREC_TF32) {
-                post_rff_store<ElemTF32>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemTF32>(rff, row, rff.col2 + 2 * j, nxt[i]);
-              } else {
-                post_rff_store<ElemBF16>(rff, row, 2 * j, sv[i]);
-                post_rff_store<ElemBF16>(rff, row, rff.col2 + 2 * j, nxt[i]);
-              }
-            }
-          }
-        }
-      }
-      int steps = 0;
-      if (num_steps != nullptr) {
-        steps = num_steps[row] + 1;
-        if (lane == 0) num_steps[row] = steps;
-      }
-      if (done != nullptr) {
-        __syncwarp();
-        bool flag = false;
-        if (lane < tc.n_bodies) {
-          const int off = tc.body_offset[lane];
-          const int shape = tc.body_shape[lane];
-          float y = srow[off + 1];
-          if (!(tc.record_all_world || (lane == 0 && tc.record_world_root_pos))) y += srow[0];
-          const float lim = tc.body_radius[lane] + 0.0001f;
-          if (shape == SIMSTEP_SHAPE_SPHERE) {
-            flag = y <= lim;
-          } else if (shape == SIMSTEP_SHAPE_CAPSULE) {
-            const float cap = tc.body_half_height[lane] * srow[off + tc.pos_dim + 1];
-            flag = (y + cap <= lim) || (y - cap <= lim);
-          }
-        }
-        if (tc.enable_velocity_check) {
-#pragma unroll
-          for (int i = 0; i < kPerLane; ++i) {
-            const int j = (lane + 32 * i) * VEC;  // first element of this lane's slot
-            if (j < S) flag = flag || PostVec<VEC>::vel_over(nxt[i], j, tc.vel_offset, tc.vel_inv_divisor, tc.vel_threshold);
-          }
-        }
-        const bool any = __any_sync(0xffffffffu, flag);
-        if (lane == 0) done[row] = (any || (num_steps != nullptr && steps >= tc.horizon)) ? 1 : 0;
-        __syncwarp();
-      }
-    }
-  }
+  for (long long row = warp_global; row < n_rows; row += n_warps)
+    post_row_warp<NM, VEC, false>(delta, delta_rows, SP, state, member, num_steps, S, row, next_state, disc, done, tc,
+                                  rff, srow, lane);
 }
 
 // delta workspace -> dense [NM][E][S] rows (DynamicsModel.forward's return value)

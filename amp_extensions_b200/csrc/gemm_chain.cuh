@@ -30,6 +30,12 @@
 //     launch (and for CUDA-graph replays).  All pairs are co-resident (one CTA per SM), nobody waits on work that has
 //     not been scheduled.
 //
+//   * ORDER OF THE UNITS.  Whole rounds take the members of an env tile in sequence on one pair (all pairs then stream
+//     the same member's weights at any time: 1.5 % faster than members side by side); the units that do not fill a
+//     whole number of such rounds go round-robin, and the last partial round is shared as described above.  Because an
+//     env tile's members meet inside one CTA this way, the env step's tail can run here too (ChainTail: four extra
+//     warps, opt-in - measured break-even).
+//
 // Tried and dropped: a cluster of FOUR CTAs per unit (both pairs on one unit throughout, the A operand multicast between
 // them: 25 % fewer bytes out of L2, bit-identical results).  Only 33 such clusters are co-schedulable on the 148 SMs
 // (GPC sizes), 132 SMs instead of 148, and the launch was 12 % slower; the multicast itself changed nothing.  Also
@@ -41,6 +47,7 @@
 // the per-layer launches, so the results are bit-identical to them.
 #pragma once
 #include <type_traits>
+#include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
 
 #ifndef SIMSTEP_MAX_HIDDEN
@@ -60,6 +67,29 @@ struct ChainLayer {
 };
 
 constexpr int kChainMaxDepTiles = 64;
+constexpr int kChainTailWarps = 4;
+constexpr int kChainTailSmem = kChainTailWarps * (kPostMaxElems + 4) * 4;  // one state row per tail warp
+
+// The env step's tail (next state, discrepancy, termination, cost operand rows: what post_step_*_kernel does) for the
+// env tiles whose members all ran on this CTA pair: four extra warps pick a tile's 128 rows up when the last member's
+// deltas have been stored and run post_row_warp on them while the pair is already multiplying the next env tile.
+struct ChainTail {
+  int enabled;
+  int rounds;              // the first `rounds` whole rounds (the last round's tail would run after the kernel's MMAs are done)
+  const float* delta;      // the delta workspace [N][delta_rows][DP] this launch writes
+  long long delta_rows;
+  int DP;
+  const float* state;
+  float* next_state;
+  const int32_t* member;
+  int32_t* num_steps;
+  float* disc;
+  uint8_t* done;
+  long long n_rows;
+  int S;
+  TermConst tc;
+  PostRff rff;
+};
 
 struct ChainArgs {
   int n_layers;            // hidden layers + the final one (the last entry of layer[])
@@ -74,6 +104,7 @@ struct ChainArgs {
   // the last, partial round: units [units - tail_units, units) are shared by two pairs each (0: plain extra round)
   int tail_units;
   int seq_rounds;          // whole rounds run with the members of an env tile in sequence on one pair (0: none)
+  ChainTail tail;          // the env step's tail for the rows of those rounds (TAIL_NM > 0 instantiations)
   int tiles_per_role[2];                      // hidden tiles role p stores per shared unit
   unsigned char dep_role[kChainMaxDepTiles];  // column tile T of the activation buffer: the role that stores it ...
   unsigned char dep_ord[kChainMaxDepTiles];   // ... and its ordinal among that role's tiles of the unit
@@ -167,8 +198,8 @@ __device__ __forceinline__ bool chain_item(const ChainArgs& a, int pair, int pai
   return false;
 }
 
-template <typename E, bool TANH>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <typename E, bool TANH, int TAIL_NM>
+__global__ void __launch_bounds__(kGemmThreads + (TAIL_NM > 0 ? kChainTailWarps * 32 : 0), 1)
 ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainArgs args) {
   constexpr int CG = 2;
   using S = GemmShape<CG>;
@@ -195,6 +226,8 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   uint32_t* stored_cnt = tmem_base_smem + 1;  // hidden tiles of THIS CTA whose stores have completed
+  uint32_t* tail_ready = tmem_base_smem + 2;  // env tiles of THIS CTA whose members' deltas are all stored
+  float* tail_rows = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [kChainTailWarps][kPostMaxElems + 4]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -211,6 +244,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
       ptx::mbar_init(&tmem_empty_bar[a], kNumEpiWarps * CG);
     }
     *stored_cnt = 0;
+    *tail_ready = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&maps.x);
     ptx::prefetch_tensormap(&maps.h);
@@ -360,7 +394,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 2 + kNumEpiWarps) {
     // ===== epilogue warps =====
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
@@ -515,6 +549,16 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
           };
           if (is_final) {
             run_tile(std::true_type{}, (half ? kHalfN : kBlockN) / 32);
+            if constexpr (TAIL_NM > 0) {
+              // the last member of an env tile that ran here in sequence: its rows go to the tail warps once the deltas
+              // of all its members have landed (earlier members' stores are older groups of the same thread)
+              if (args.tail.enabled && epi_tid == 0 && i < args.tail.rounds * args.groups && n_tile + 1 == ly.n_tiles &&
+                  i % args.groups == args.groups - 1) {
+                ptx::tma_store_wait<0>();
+                chain_fence_proxy_async_global();
+                st_release_cta_smem(tail_ready, uint32_t(i / args.groups) + 1u);
+              }
+            }
           } else {
             run_tile(std::false_type{}, kBlockN / 32);
             if (epi_tid == 0) {
@@ -535,6 +579,29 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
       }
     }
     if (epi_tid == 0) ptx::tma_store_wait<0>();
+  } else {
+    // ===== tail warps (launched only with TAIL_NM > 0) =====
+    if constexpr (TAIL_NM > 0) {
+      const ChainTail& t = args.tail;
+      if (t.enabled) {
+        const int tw = warp - (2 + kNumEpiWarps);
+        float* srow = tail_rows + tw * (kPostMaxElems + 4);
+        for (int su = 0; su < t.rounds; ++su) {
+          unsigned int spins = 0;
+          while (ld_acquire_cta_smem(tail_ready) < uint32_t(su) + 1u) {
+            __nanosleep(256);
+            if (++spins > (1u << 24)) __trap();
+          }
+          const long long row0 = (static_cast<long long>(pair + su * pairs) * CG + int(cta_rank)) * kBlockM;
+          for (int r = tw; r < kBlockM; r += kChainTailWarps) {
+            const long long row = row0 + r;
+            if (row < t.n_rows)
+              post_row_warp<TAIL_NM, 2, true>(t.delta, t.delta_rows, t.DP, t.state, t.member, t.num_steps, t.S, row,
+                                              t.next_state, t.disc, t.done, t.tc, t.rff, srow, lane);
+          }
+        }
+      }
+    }
   }
 
   ptx::tcgen05_fence_before();

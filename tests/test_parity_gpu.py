@@ -703,3 +703,35 @@ for prec, chunk in (("fp16", 0), ("tf32", 0), ("fp16", 4096)):
         res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
         assert res.stdout.count("GUARDS") == 3
+
+
+def test_step_tail_inside_the_forward_kernel_matches_the_post_step_kernel(tmp_path):
+    """SIMSTEP_CHAIN_TAIL=1 (opt-in): the tail of the env step - next state, counters, termination,
+    discrepancy, cost operand rows - runs on four extra warps INSIDE the column-fused forward kernel for the env tiles
+    whose members all ran on one CTA pair (post_row_warp, the one-warp-per-row kernel's body, on deltas read back with
+    ld.global.cg), the post-step kernel only gets the remaining rows.  Same fp32 arithmetic per element: next states,
+    step counters and masks are bit-identical (including the NaN row of an out-of-range member index), the discrepancy
+    sums its squares in another order (2e-6), the cost follows."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = {}
+    for flag, keep in (("0", "1"), ("1", "1"), ("1", "0")):
+        out = str(tmp_path / f"tail{flag}{keep}.npz")
+        env = dict(os.environ, SIMSTEP_CHAIN_TAIL=flag, SIMSTEP_CHAIN_TAIL_KEEP=keep)
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "final_fused_check.py"), out], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        files[flag + keep] = np.load(out)
+    a = files["01"]
+    for key in ("11", "10"):
+        b = files[key]
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            x, y = a[k], b[k]
+            if k.endswith(("_next", "_done", "_steps")):
+                assert np.array_equal(x, y, equal_nan=True), (key, k)
+            else:
+                scale = max(float(np.nanmax(np.abs(x))), 1e-12)
+                assert float(np.nanmax(np.abs(x - y))) <= 2e-6 * scale, (key, k)
