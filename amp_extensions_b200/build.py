@@ -23,6 +23,8 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
+# extra nvcc flags for A/B builds, e.g. SIMSTEP_NVCC_EXTRA="-DSIMSTEP_GEMM_STAGES_CG2=4" (part of the build stamp)
+NVCC_FLAGS += os.environ.get("SIMSTEP_NVCC_EXTRA", "").split()
 UNITS = ("api.cu", "final_fused.cu", "chain.cu")
 
 
