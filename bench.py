@@ -691,7 +691,7 @@ def run_ours(args):
             """Two groups of envs alternate: group i+1's upload and group i-1's download overlap group i's compute.
             Every step's inputs cross PCIe host->device and every step's results (next state, cost, done, disc,
             counters; the imitation reward in config 4) come back and are read on the host."""
-            for i in range(4):
+            for i in range(8):
                 submit(i)
                 collect()
             barrier()
@@ -882,19 +882,22 @@ def device_policy_rollout(ens, cost, ds, E, device, world, barrier, horizon=32, 
     env = VecSimEnv(ens, E, horizon=300, reset_states=pool, seed=1, cost=cost)
     env.reset()
     ro = DeviceRollout(env, _Policy(S_DIM, A_DIM), seed=0)
-    from amp_extensions_b200.rollout import HostPathStream
+    from amp_extensions_b200.rollout import HostPathStream, RolloutBatch
     dl = HostPathStream(device)
-    ro.collect(horizon)
-    for _ in range(3):                          # both pinned slots and the allocator's blocks exist before the clock starts
-        dl.submit(ro.collect(horizon))
-        dl.submit(ro.collect(horizon))
-        dl.collect()
-        dl.collect()
+    # two device batches alternate (collect k+1 fills one while the other one's paths cross PCIe): no allocation in the loop
+    use_cost = env.cost is not None and getattr(env, "_w_dev", None) is not None
+    batches = [RolloutBatch(ro.eng, horizon, E, S_DIM, A_DIM, use_cost) for _ in range(2)]
+    ro.collect(horizon, batch=batches[0])
+    for k in range(4):                          # both pinned slots exist before the clock starts
+        dl.submit(ro.collect(horizon, batch=batches[k % 2]))
+        if k > 0:
+            dl.collect()
+    dl.collect()
     torch.cuda.synchronize(device)
     barrier()
     t0 = time.perf_counter()
     for i in range(iters):
-        dl.submit(ro.collect(horizon))          # horizon i computes while horizon i-1 is still crossing PCIe
+        dl.submit(ro.collect(horizon, batch=batches[i % 2]))   # horizon i computes while horizon i-1 crosses PCIe
         if i > 0:
             _ = float(dl.collect()["rewards"][0, 0])
     _ = float(dl.collect()["rewards"][0, 0])
