@@ -324,7 +324,8 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                     unsigned int spins = 0;
                     while ((have_partner = ld_acquire_gpu_u32(partner_cnt)) < need) {
                       __nanosleep(64);
-                      if (++spins > (1u << 25)) __trap();
+                      // the partner pair may not even be resident yet when other kernels share the GPU: ~20 s of patience
+                      if (++spins > (1u << 28)) __trap();
                     }
                     chain_fence_proxy_async_global();
                   }
@@ -590,7 +591,7 @@ ensemble_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
           unsigned int spins = 0;
           while (ld_acquire_cta_smem(tail_ready) < uint32_t(su) + 1u) {
             __nanosleep(256);
-            if (++spins > (1u << 24)) __trap();
+            if (++spins > (1u << 27)) __trap();
           }
           const long long row0 = (static_cast<long long>(pair + su * pairs) * CG + int(cta_rank)) * kBlockM;
           for (int r = tw; r < kBlockM; r += kChainTailWarps) {
