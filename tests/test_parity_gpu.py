@@ -603,7 +603,9 @@ def test_column_fused_forward_is_bit_identical_to_one_launch_per_layer(tmp_path)
     env tile), the activations handed on through L2, the last partial round shared between pairs with the final layer
     as M 256 x N 128 halves.  Every output element accumulates its K blocks in the same order as in the per-layer
     launches (SIMSTEP_CHAIN=0), so ALL outputs of the step are bit-identical - for batches of 1 .. 40 001 rows, i.e.
-    with fewer units than CTA pairs, whole rounds only, and shared units in the last round (4 800 and 40 001 rows)."""
+    with fewer units than CTA pairs, whole rounds only, and shared units in the last round (4 800 and 40 001 rows) - and for
+    an irregular second ensemble (three members, no dense connections, tanh, hidden 512 / 256 / 512: the pairs sharing a
+    unit get unequal work) at 6 812 and 19 193 rows."""
     import os
     import subprocess
     import sys

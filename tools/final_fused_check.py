@@ -41,6 +41,24 @@ def main(out_path):
             res[f"E{E}_s{int(split)}_steps"] = st.cpu().numpy()
         d = eng.discrepancy(s, a)
         res[f"E{E}_disc_only"] = d.cpu().numpy()
+    # a second, irregular ensemble: three members, NO dense connections, tanh, hidden sizes 512 / 256 / 512 (2, 1 and 2
+    # n-tiles: the two pairs that share a unit of the last round get unequal work), batch sizes that give the column-fused
+    # kernel shared units without (6 812 rows) and with (19 193 rows) whole rounds of members in sequence
+    from oracle import milo_oracle as mo2
+    S2, A2, N2, hid2 = 226, 28, 3, [512, 256, 512]
+    ws2, bs2 = mo2.init_ensemble(S2, A2, hid2, N2, dense_connect=False, base_seed=7)
+    eng2 = Engine(S2, A2, N2, hid2, dense_connect=False, activation="tanh", transform=True, precision="fp16")
+    eng2.load_ensemble(ws2, bs2, c["tf"])
+    eng2.set_termination(HumanoidTermination(enable_velocity_check=False))
+    for E in (6812, 19193):
+        s = H.humanoid_like_states(E, seed=E % 11)
+        a = torch.randn(E, 28, generator=g)
+        member = torch.randint(0, N2, (E,), generator=g, dtype=torch.int32)
+        st = torch.zeros(E, dtype=torch.int32).cuda()
+        out = eng2.step(s.cuda(), a.cuda(), member.cuda(), st)
+        for name, t in zip(("next", "disc", "done"), out):
+            res[f"plain_E{E}_{name}"] = t.cpu().numpy()
+        res[f"plain_E{E}_steps"] = st.cpu().numpy()
     np.savez(out_path, **res)
 
 
