@@ -86,6 +86,8 @@ _SIGNATURES = {
     "simstep_saturation_count": (C.c_int, [_c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "simstep_forward_launches": (C.c_int, [_c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "simstep_debug_check_guards": (C.c_int, [_c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "simstep_debug_chain_schedule": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "simstep_forward": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
     "simstep_discrepancy": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p, _c_void_p]),
     "simstep_step": (C.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, C.c_int64, _c_void_p,

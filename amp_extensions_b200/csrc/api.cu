@@ -596,15 +596,14 @@ int launch_chain(simstep_handle* h, long long rows_pad, cudaStream_t st, const S
   static const int hints = [] { const char* e = std::getenv("SIMSTEP_CHAIN_HINTS"); return e ? std::atoi(e) : 3; }();
   ca.l2_hints = hints;
   // the last, partial round: when its units are at most half the pairs, two pairs share each of them
-  const int units = ca.m_tiles * ca.groups;
-  const int pairs = std::min(units, h->sm_count / 2);
   // whole rounds run with the members of an env tile in sequence on one pair: all pairs then stream the SAME member's
   // weights at any time (measured -1.5 % on the launch against members side by side; SIMSTEP_CHAIN_SEQ=0 for A/B)
   static const bool seq = [] { const char* e = std::getenv("SIMSTEP_CHAIN_SEQ"); return !(e && e[0] == '0'); }();
-  if (seq && units > pairs) ca.seq_rounds = ca.m_tiles / pairs;
-  const int tail = (units - ca.seq_rounds * pairs * ca.groups) % pairs;
-  if (chain_mode() != 3 && tail > 0 && 2 * tail <= pairs && ca.hidden_tiles <= kChainMaxDepTiles && h->chain_cnt) {
-    ca.tail_units = tail;
+  int pairs = 1;
+  chain_schedule(ca.m_tiles, ca.groups, h->sm_count / 2, seq,
+                 chain_mode() != 3 && ca.hidden_tiles <= kChainMaxDepTiles && h->chain_cnt != nullptr, &pairs,
+                 &ca.seq_rounds, &ca.tail_units);
+  if (ca.tail_units > 0) {
     ca.tail_cnt = h->chain_cnt;
     int t = 0;
     for (int l = 0; l < h->L; ++l)
@@ -1338,6 +1337,35 @@ int simstep_debug_check_guards(simstep_handle* h, int64_t* buffers_out, int64_t*
       CU_TRY(h, cudaMemcpy(host.data(), z, kGuardBytes, cudaMemcpyDeviceToHost));
       for (unsigned char b : host) *bad_bytes_out += b != 0xA5;
     }
+  }
+  return SIMSTEP_OK;
+}
+
+int simstep_debug_chain_schedule(int32_t m_tiles, int32_t groups, int32_t sm_count, int32_t max_items,
+                                 int32_t* pairs_out, int32_t* seq_rounds_out, int32_t* tail_units_out,
+                                 int32_t* items_out) {
+  if (m_tiles < 1 || groups < 1 || sm_count < 2 || max_items < 1 || !pairs_out || !seq_rounds_out || !tail_units_out ||
+      !items_out)
+    return SIMSTEP_EINVAL;
+  ChainArgs a{};
+  a.m_tiles = m_tiles;
+  a.groups = groups;
+  int pairs = 1;
+  chain_schedule(m_tiles, groups, sm_count / 2, true, true, &pairs, &a.seq_rounds, &a.tail_units);
+  *pairs_out = pairs;
+  *seq_rounds_out = a.seq_rounds;
+  *tail_units_out = a.tail_units;
+  for (int p = 0; p < pairs; ++p) {
+    int32_t* row = items_out + static_cast<size_t>(p) * max_items * 2;
+    ChainItem it;
+    int i = 0;
+    for (; chain_item(a, p, pairs, i, it); ++i) {
+      if (i >= max_items - 1) return SIMSTEP_EINVAL;
+      row[2 * i] = it.unit;
+      row[2 * i + 1] = it.role;
+    }
+    row[2 * i] = -1;      // terminator
+    row[2 * i + 1] = -1;
   }
   return SIMSTEP_OK;
 }

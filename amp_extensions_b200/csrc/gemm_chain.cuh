@@ -177,7 +177,20 @@ struct ChainItem {
   int unit;
   int role;
 };
-__device__ __forceinline__ bool chain_item(const ChainArgs& a, int pair, int pairs, int i, ChainItem& it) {
+// Host side of the schedule: how many CTA pairs run, how many whole rounds take an env tile's members in sequence, and how
+// many units of the last partial round are shared between two pairs (0: it runs as a plain round).  Used by the launcher
+// and by simstep_debug_chain_schedule (the CPU test of this arithmetic).
+inline void chain_schedule(int m_tiles, int groups, int max_pairs, bool seq, bool share, int* pairs, int* seq_rounds,
+                           int* tail_units) {
+  const int units = m_tiles * groups;
+  *pairs = units < max_pairs ? units : max_pairs;
+  if (*pairs < 1) *pairs = 1;
+  *seq_rounds = (seq && units > *pairs) ? m_tiles / *pairs : 0;
+  const int tail = (units - *seq_rounds * *pairs * groups) % *pairs;
+  *tail_units = (share && tail > 0 && 2 * tail <= *pairs) ? tail : 0;
+}
+
+__host__ __device__ __forceinline__ bool chain_item(const ChainArgs& a, int pair, int pairs, int i, ChainItem& it) {
   // seq_rounds whole rounds in which a pair takes ALL members of an env tile one after the other (the members of an env
   // tile then meet inside one CTA pair) ...
   const int seq_items = a.seq_rounds * a.groups;

@@ -137,6 +137,15 @@ int simstep_forward_launches(const simstep_handle* h, int64_t n_envs, int32_t* l
  * have been overwritten.  Synchronises with the device.  No reference counterpart. */
 int simstep_debug_check_guards(simstep_handle* h, int64_t* buffers_out, int64_t* bad_bytes_out);
 
+/* The work-item schedule of the column-fused forward kernel for m_tiles 256-row env tiles and `groups` members on a
+ * device with sm_count SMs, computed on the HOST with the kernel's own code (no handle, no GPU): CTA pairs used, whole
+ * rounds that take an env tile's members in sequence, units of the last partial round shared by two pairs, and per pair
+ * the list of (unit, role) items - unit = env_tile * groups + member, role -1 = the whole unit, 0 / 1 = one half of a
+ * shared unit - terminated by (-1, -1); items_out is [pairs][max_items][2].  Test hook for the scheduling arithmetic. */
+int simstep_debug_chain_schedule(int32_t m_tiles, int32_t groups, int32_t sm_count, int32_t max_items,
+                                 int32_t* pairs_out, int32_t* seq_rounds_out, int32_t* tail_units_out,
+                                 int32_t* items_out);
+
 /* Replaces the rff layer of RBFLinearCost (LC:53-55): weight_host [D,in_dim],
  * bias_host [D].  in_dim must be S (input_type 's'), 2S ('ss'), S+A ('sa') or
  * 2S+A ('sas').  split != 0 keeps ~21 mantissa bits of the pre-activation by

@@ -106,3 +106,49 @@ def test_product_package_never_imports_the_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_forward_kernel_schedule_covers_every_unit_exactly_once():
+    """The column-fused forward kernel's unit schedule (csrc/gemm_chain.cuh: chain_schedule + chain_item, evaluated on
+    the HOST through simstep_debug_chain_schedule - no GPU involved): for every batch / ensemble shape each
+    (env tile, member) unit is run exactly once as a whole or exactly once by each of the two roles of a shared unit;
+    shared units only exist in the last round, on pairs 2u and 2u + 1, and number at most half the pairs; whole rounds
+    of members-in-sequence keep an env tile's members on one pair, in order; no pair gets more than one item more than
+    its share."""
+    lib = _lib.load(build_if_missing=False)
+    max_items = 4096
+    buf = (C.c_int32 * (74 * max_items * 2))()
+    pairs, seq, tail = C.c_int32(), C.c_int32(), C.c_int32()
+    shapes = [(m, g, sm) for g in (1, 2, 3, 4, 5, 8) for m in (1, 2, 9, 18, 19, 37, 73, 74, 75, 83, 148, 157, 256, 300)
+              for sm in (148,)] + [(157, 4, 132), (40, 4, 8), (5, 3, 2), (1000, 1, 148), (511, 7, 148)]
+    for m_tiles, groups, sm in shapes:
+        rc = lib.simstep_debug_chain_schedule(m_tiles, groups, sm, max_items, C.byref(pairs), C.byref(seq), C.byref(tail), buf)
+        assert rc == 0, (m_tiles, groups, sm)
+        P, R, T = pairs.value, seq.value, tail.value
+        units = m_tiles * groups
+        assert P == min(units, sm // 2) and 0 <= 2 * T <= P and R == (m_tiles // P if units > P else 0)
+        whole, roles, counts = {}, {}, []
+        for p in range(P):
+            items = []
+            for i in range(max_items):
+                u, r = buf[(p * max_items + i) * 2], buf[(p * max_items + i) * 2 + 1]
+                if u < 0:
+                    break
+                items.append((u, r))
+            counts.append(len(items))
+            for i, (u, r) in enumerate(items):
+                assert 0 <= u < units
+                if r < 0:
+                    assert u not in whole and u not in roles, (m_tiles, groups, u)
+                    whole[u] = (p, i)
+                else:
+                    assert i == len(items) - 1 and p < 2 * T and r == p % 2 and u == units - T + p // 2
+                    assert (u, r) not in roles and u not in whole
+                    roles[(u, r)] = p
+            # rounds of members in sequence: the first R * groups items walk R env tiles member by member
+            for k in range(R):
+                tile = p + k * P
+                assert items[k * groups:(k + 1) * groups] == [(tile * groups + g, -1) for g in range(groups)]
+        assert len(whole) == units - T and len(roles) == 2 * T, (m_tiles, groups, sm, len(whole), len(roles))
+        assert all((units - T + j, r) in roles for j in range(T) for r in (0, 1))
+        assert max(counts) - min(counts) <= 1 or T > 0 and max(counts) - min(counts) <= 2
