@@ -688,6 +688,10 @@ int run_ensemble_chunk(simstep_handle* h, const float* s, const float* a, long l
     ga.b_rows_per_group = ly.o_pad;
     ga.bias = ly.bias;
     ga.out_rows_per_group = int(h->cap_rows);
+    // weight tiles with the evict_last L2 priority: every env tile of a member re-reads them while the activations
+    // stream past (8 x (1024 x 4): -1 % on the five launches; neutral at 4 x (512 x 4); SIMSTEP_GEMM_B_HINT=0 for A/B)
+    static const int b_hint = [] { const char* e = std::getenv("SIMSTEP_GEMM_B_HINT"); return e ? std::atoi(e) : 1; }();
+    ga.b_evict_last = b_hint;
     int rc;
     if (l < h->L) {
       // bias + activation straight into this layer's K-slice of the concat buffer

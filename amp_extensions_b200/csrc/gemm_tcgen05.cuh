@@ -197,12 +197,42 @@ __device__ __forceinline__ void combine_row(const CombineArgs& c, long long row,
   if (c.cost) c.cost[row] = i_ - wb;
 }
 
+// L2 eviction-priority policies and the hinted forms of the pair's TMA load / the TMA store
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                                      int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(bar) & 0xFEFFFFFFu),
+        "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+
 struct GemmArgs {
   // tile space: tile -> (group, m_tile, n_tile), n fastest; an m_tile is CG * 128 rows
   int n_inner;            // consecutive n-tiles of one (group, m_tile) a CTA pair runs back to back (0 / 1: none)
   int group_fastest;      // tile -> (m_tile, group, n_tile): the members of an env tile run side by side on
                           // neighbouring CTA pairs, so the shared x tile is read from HBM once instead of per member
   int reverse;            // walk the tile space backwards: the rows the previous layer wrote LAST (still in L2) first
+  int b_evict_last;       // load the weight tiles with the evict_last L2 priority (cta_group::2 kernels)
   int m_tiles;
   int n_tiles;
   int groups;
@@ -347,6 +377,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
     // single-threaded and emits each TMA / MMA instruction once, instead of wrapping every one of them in an
     // ELECT / BRA.U.ANY loop over the active lanes (about 100 instructions per k-block under `if (lane == 0)`, 40 so)
     if (ptx::elect_one()) {
+    const uint64_t pol_last = l2_policy_evict_last();
     int stage = 0;
     uint32_t phase = 0;
     int held_b = -1;  // (group, n-tile) whose weight k-blocks sit in the stages' B halves (B-resident mode)
@@ -370,7 +401,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_ax, const __grid_co
         } else {
           ptx::tma_load_2d<CG>(sa, &tmap_ah, &full_bar[stage], (args.kb_h0 + kb - args.kb_x) * BK, row_ah);
         }
-        if (load_b) ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+        if (load_b) {
+          if (CG == 2 && args.b_evict_last) tma_load_2d_pair_hint(sb, &tmap_b, &full_bar[stage], kb * BK, row_b, pol_last);
+          else ptx::tma_load_2d<CG>(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+        }
         if (++stage == ring) { stage = 0; phase ^= 1; }
       }
     }
