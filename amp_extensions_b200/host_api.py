@@ -179,6 +179,21 @@ class _Record:
         return buf[off + o: off + o + sz].view(dtype).view(shape)
 
 
+def chunk_bounds(num_envs, n_chunks, gran=256):
+    """Row ranges of the chunks a step of `num_envs` envs is processed in: equal chunks of whole 256-row tiles, cut -
+    when `gran` (Engine.round_rows) says so - where the forward kernel finishes a whole round of its CTA pairs: 40 000
+    envs in two chunks are 18 944 + 21 056 rows (4 + 4.5 rounds of the kernel) instead of 20 224 + 19 776 (4.5 + 4.5).
+    The last chunk takes the remainder; there are at most n_chunks of them."""
+    E = int(num_envs)
+    n_chunks = max(1, min(int(n_chunks), (E + 255) // 256))
+    rows = -(-(-(-E // n_chunks)) // 256) * 256
+    if gran > 256 and rows >= gran and round(rows / gran) * gran * (n_chunks - 1) < E:
+        rows = round(rows / gran) * gran
+    bounds = [(r0, min(E, r0 + rows)) for r0 in range(0, E, rows)][:n_chunks]
+    bounds[-1] = (bounds[-1][0], E)
+    return bounds
+
+
 class HostEnvPipeline:
     """The reference plugin's own call shape, batched: `step(actions) -> (obs, cost, done, ...)` with the env state
     RESIDENT on the device (gym-simenv/gym_simenv/envs/sim_env.py:140-162 keeps `self.ob` inside the env and takes
@@ -202,15 +217,9 @@ class HostEnvPipeline:
         self.eng, self.E, self.with_cost = engine, int(num_envs), with_cost
         self.obs_half = obs_dtype in (torch.float16, torch.half)
         dev, S, A, E = engine.device, engine.S, engine.A, self.E
-        n_chunks = max(1, min(int(n_chunks), (E + 255) // 256))
-        rows = -(-(-(-E // n_chunks)) // 256) * 256
-        # cut where the forward kernel finishes a whole round of its CTA pairs (Engine.round_rows): 40 000 envs in two
-        # chunks are 18 944 + 21 056 rows (4 + 4.5 rounds) instead of 20 224 + 19 776 (4.5 + 4.5)
+        rows = -(-(-(-E // max(1, min(int(n_chunks), (E + 255) // 256)))) // 256) * 256
         gran = engine.round_rows(rows) if hasattr(engine, "round_rows") else 256
-        if gran > 256 and rows >= gran and round(rows / gran) * gran * (n_chunks - 1) < E:
-            rows = round(rows / gran) * gran
-        self.bounds = [(r0, min(E, r0 + rows)) for r0 in range(0, E, rows)][:n_chunks]
-        self.bounds[-1] = (self.bounds[-1][0], E)
+        self.bounds = chunk_bounds(E, n_chunks, gran)
         self.groups = []
         f32 = dict(device=dev, dtype=torch.float32)
         for _ in range(int(groups)):

@@ -239,3 +239,24 @@ def test_gym_registration_uses_the_reference_id(monkeypatch):
     params = inspect.signature(env_cls.__init__).parameters
     for kw in ("dynamic_ensemble", "deepmimic_args", "enable_velocity_check", "horizon", "device", "seed", "reset_args"):
         assert kw in params                      # sim_env.py:27-32 (note the reference's spelling `dynamic_ensemble`)
+
+
+def test_host_pipeline_chunk_bounds():
+    """host_api.chunk_bounds: the chunks of a step cover [0, E) exactly once, in order, there are at most n_chunks of
+    them, every cut is on a 256-row tile, and with the forward kernel's round granule (Engine.round_rows: 9 472 rows for
+    4 members on 148 SMs) the cuts fall on whole rounds whenever a chunk is at least one granule long."""
+    from amp_extensions_b200.host_api import chunk_bounds
+    assert chunk_bounds(40000, 2) == [(0, 20224), (20224, 40000)]
+    assert chunk_bounds(40000, 2, 9472) == [(0, 18944), (18944, 40000)]
+    assert chunk_bounds(40000, 1, 9472) == [(0, 40000)]
+    assert chunk_bounds(300, 4) == [(0, 256), (256, 300)]
+    assert chunk_bounds(5000, 2, 9472) == [(0, 2560), (2560, 5000)]           # shorter than a granule: plain halves
+    for E in (1, 255, 256, 257, 4800, 20001, 40000, 65536, 131072, 1 << 20):
+        for n in (1, 2, 3, 4, 7, 16):
+            for gran in (256, 9472, 2560, 18944):     # Engine.round_rows only returns multiples of 256
+                b = chunk_bounds(E, n, gran)
+                assert 1 <= len(b) <= n and b[0][0] == 0 and b[-1][1] == E
+                assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1)) and all(r1 > r0 for r0, r1 in b)
+                assert all(r0 % 256 == 0 for r0, _ in b)
+                if gran > 256 and len(b) > 1 and b[0][1] - b[0][0] >= gran:
+                    assert all(r0 % gran == 0 for r0, _ in b)
