@@ -244,7 +244,7 @@ def test_gym_registration_uses_the_reference_id(monkeypatch):
 def test_host_pipeline_chunk_bounds():
     """host_api.chunk_bounds: the chunks of a step cover [0, E) exactly once, in order, there are at most n_chunks of
     them, every cut is on a 256-row tile, and with the forward kernel's round granule (Engine.round_rows: 9 472 rows for
-    4 members on 148 SMs) the cuts fall on whole rounds whenever a chunk is at least one granule long."""
+    4 members on 148 SMs) the cuts fall on whole rounds whenever such a split into n chunks exists."""
     from amp_extensions_b200.host_api import chunk_bounds
     assert chunk_bounds(40000, 2) == [(0, 20224), (20224, 40000)]
     assert chunk_bounds(40000, 2, 9472) == [(0, 18944), (18944, 40000)]
@@ -258,5 +258,5 @@ def test_host_pipeline_chunk_bounds():
                 assert 1 <= len(b) <= n and b[0][0] == 0 and b[-1][1] == E
                 assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1)) and all(r1 > r0 for r0, r1 in b)
                 assert all(r0 % 256 == 0 for r0, _ in b)
-                if gran > 256 and len(b) > 1 and b[0][1] - b[0][0] >= gran:
-                    assert all(r0 % gran == 0 for r0, _ in b)
+                if not all(r0 % gran == 0 for r0, _ in b):      # no aligned split with n chunks exists: the plain one
+                    assert b == chunk_bounds(E, n, 256)
