@@ -111,8 +111,14 @@ def test_north_star_shape_gradients_match_autograd(act):
         if strict:
             assert rel_to_max(x, ref) < GRAD_REL, what
         else:
-            assert np.linalg.norm(x - ref) <= 3e-2 * np.linalg.norm(ref), what
-            assert np.median(np.abs(x - ref)) <= GRAD_REL * np.abs(ref).max(), what
+            # measured (B200, this batch): Frobenius 1.1e-2 .. 2.0e-2; 95.9 .. 99.6 % of the entries inside the strict
+            # bound, 99.84 .. 99.99 % inside ten times it - the difference to the fp32 reference IS sparse
+            d = np.abs(x - ref) / np.abs(ref).max()
+            assert np.linalg.norm(x - ref) <= 2.5e-2 * np.linalg.norm(ref), what
+            assert np.median(d) <= GRAD_REL, what
+            if x.ndim == 2:      # weight gradients (biases are 512 numbers: percentiles of them say little)
+                assert (d <= GRAD_REL).mean() >= 0.95, (what, float((d <= GRAD_REL).mean()))
+                assert (d <= 10 * GRAD_REL).mean() >= 0.997, (what, float((d <= 10 * GRAD_REL).mean()))
 
     for k in range(N):
         o = mo.TrainOracle(c["ws"][k], c["bs"][k], c["tf"], True, act)
